@@ -1,0 +1,192 @@
+/*
+ * qprop.h -- C ABI of libqprop_b200: B200-native (sm_100a) Chebyshev and Newton/Arnoldi
+ * propagation kernels behind QuantumPropagators.jl's propagator API.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its method
+ * plugin interface is Julia multiple dispatch (init_prop/prop_step!/...), and the
+ * numerical kernels below it (module Cheby, Newton, Arnoldi, SpectralRange, and the
+ * Operator mul!) are what each entry point here replaces.  The Julia host
+ * (julia/QPropB200.jl) binds these with `ccall`; the Python host
+ * mirror (quantumpropagators.jl_b200/) binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (QP_OK == 0, negative == error class);
+ *     qp_last_error(ctx) gives the message.  No exceptions cross the ABI.
+ *   - host pointers are borrowed for the duration of the call only; the library copies.
+ *   - handles are opaque and freed explicitly.  Calls on different contexts are
+ *     thread-safe; calls on one context are not (one CUDA stream per context).
+ *   - complex numbers are (re, im) pairs of float64 (Julia ComplexF64 / numpy complex128).
+ *   - a state holds B >= 1 vectors of dimension N, stored [N][B] with the batch index
+ *     fastest ("trajectory-batched"); B == 1 is a plain vector.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     QP_ERR_CUDA.
+ */
+#ifndef QPROP_H
+#define QPROP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QP_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define QP_OK 0
+#define QP_ERR_INVALID_ARG -1   /* Julia: ArgumentError / AssertionError on sizes */
+#define QP_ERR_CUDA -2          /* CUDA runtime / launch failure, no device */
+#define QP_ERR_OOM -3           /* device or host allocation failed */
+#define QP_ERR_NOT_CONVERGED -4 /* `@assert s <= max_restarts`, src/newton.jl:375 */
+#define QP_ERR_NORMALIZATION -5 /* "Incorrect normalization", src/cheby.jl:196 */
+#define QP_ERR_UNSUPPORTED -6   /* valid request outside the engine's limits */
+#define QP_ERR_INTERNAL -7
+
+/* sparse layouts accepted by qp_op_upload_sparse */
+#define QP_LAYOUT_CSC 0 /* Julia SparseMatrixCSC: colptr/rowval/nzval */
+#define QP_LAYOUT_CSR 1
+
+/* device storage formats of a generator (qp_gen_create / qp_gen_info) */
+#define QP_FORMAT_AUTO 0
+#define QP_FORMAT_CSR 1   /* merged multi-operator CSR, sub-warp per row        */
+#define QP_FORMAT_SELL 2  /* merged sliced-ELL (C = 32), thread per row           */
+#define QP_FORMAT_DENSE 3 /* dense row-major ComplexF64 operators                 */
+
+typedef struct qp_ctx_s* qp_ctx_t;
+typedef struct qp_op_s* qp_op_t;
+typedef struct qp_gen_s* qp_gen_t;
+typedef struct qp_state_s* qp_state_t;
+typedef struct qp_cheby_s* qp_cheby_t;
+typedef struct qp_krylov_s* qp_krylov_t;
+
+typedef struct {
+  double re, im;
+} qp_c128;
+
+/* ------------------------------------------------------------------ library / context */
+
+int32_t qp_version(void);
+const char* qp_status_string(int32_t status);
+
+/* One context = one device + one CUDA stream + error/timer state. */
+int32_t qp_ctx_create(int32_t device, qp_ctx_t* ctx);
+int32_t qp_ctx_destroy(qp_ctx_t ctx);
+int32_t qp_sync(qp_ctx_t ctx);
+const char* qp_last_error(qp_ctx_t ctx);
+/* raw cudaStream_t of the context (for event timing / interop by the host) */
+int32_t qp_ctx_stream(qp_ctx_t ctx, void** stream);
+/* number of kernels this library has launched on the context since creation */
+int32_t qp_ctx_launch_count(qp_ctx_t ctx, int64_t* n_launches);
+
+/* Timers under the reference's TimerOutputs labels (src/timings.jl; labels
+ * "prop_step!", "matrix-vector product", "arnoldi!", src/cheby.jl:175,
+ * src/arnoldi.jl:81, src/cheby_propagator.jl:349).  CUDA-event based, off by default. */
+int32_t qp_timer_enable(qp_ctx_t ctx, int32_t on);
+int32_t qp_timer_get(qp_ctx_t ctx, const char* label, int64_t* ncalls, double* seconds);
+int32_t qp_timer_reset(qp_ctx_t ctx);
+
+/* ------------------------------------------------------------------ operators
+ * Replaces: the component operators `A.ops[i]` of a reference `Operator`
+ * (src/generators.jl:111-125), i.e. SparseMatrixCSC{ComplexF64,Int64} or
+ * Matrix{ComplexF64}.  Sparse input is converted to device CSR with Int32 indices
+ * (CSC input is transposed: the arrays of a CSC matrix are the CSR arrays of its
+ * transpose -- SURVEY.md §7 hard part 1). */
+int32_t qp_op_upload_sparse(qp_ctx_t ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+                            const int64_t* ptr, const int64_t* idx, const qp_c128* val,
+                            int32_t layout, int32_t index_base, qp_op_t* op);
+/* column-major (Julia Matrix) n x n */
+int32_t qp_op_upload_dense(qp_ctx_t ctx, int64_t n, const qp_c128* colmajor, qp_op_t* op);
+int32_t qp_op_destroy(qp_op_t op);
+int32_t qp_op_info(qp_op_t op, int64_t* nrows, int64_t* ncols, int64_t* nnz, int32_t* is_dense);
+
+/* Lazy sum H = sum_{l<drift} ops[l] + sum_l c_l ops[drift+l], drift = n_ops - n_coeffs
+ * (src/generators.jl:111-125, 634-636).  The operators are shared, immutable, and must
+ * outlive the generator; only the n_coeffs numbers change from step to step
+ * (evaluate!, src/generators.jl:757-766).  `format` is QP_FORMAT_AUTO or a forced one. */
+int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops, int32_t n_coeffs,
+                      int32_t format, qp_gen_t* gen);
+int32_t qp_gen_destroy(qp_gen_t gen);
+/* format chosen, total stored entries (incl. padding), algorithmic matrix bytes M
+ * (sum_ops 20*nnz + 4*(N+1), or 16 N^2 per dense operator) */
+int32_t qp_gen_info(qp_gen_t gen, int32_t* format, int64_t* n, int64_t* stored_entries,
+                    int64_t* matrix_bytes);
+
+/* ------------------------------------------------------------------ states
+ * Replaces: Vector{ComplexF64} states and the level-1 verbs the reference's kernels use
+ * on them (src/interfaces/state.jl:24-47; call sites src/cheby.jl:171-211,
+ * src/arnoldi.jl:79-96, src/newton.jl:268-367). */
+int32_t qp_state_create(qp_ctx_t ctx, int64_t n, int64_t batch, qp_state_t* st);
+int32_t qp_state_destroy(qp_state_t st);
+int32_t qp_state_info(qp_state_t st, int64_t* n, int64_t* batch);
+/* current device pointer of the [n][batch] ComplexF64 buffer (may change after
+ * qp_cheby_step, which swaps buffers instead of copying) */
+int32_t qp_state_devptr(qp_state_t st, void** devptr);
+/* host layout [n][nb] (batch fastest), columns b0 .. b0+nb-1 of the state */
+int32_t qp_state_upload(qp_state_t st, const qp_c128* host, int64_t b0, int64_t nb);
+int32_t qp_state_download(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb);
+
+int32_t qp_copy(qp_state_t dst, qp_state_t src);                    /* copyto!(dst, src) */
+int32_t qp_fill(qp_state_t st, qp_c128 value);                      /* fill!            */
+int32_t qp_scal(qp_state_t st, qp_c128 alpha);                      /* lmul!(alpha, st)  */
+int32_t qp_axpy(qp_c128 alpha, qp_state_t x, qp_state_t y);         /* axpy!(alpha,x,y)  */
+int32_t qp_dot(qp_state_t x, qp_state_t y, qp_c128* out /*[batch]*/);  /* dot(x,y) = x^H y  */
+int32_t qp_norm(qp_state_t x, double* out /*[batch]*/);             /* norm(x) per column */
+
+/* y <- beta*y + alpha * (sum_l c_l H_l) x : mul!(C, A::Operator, B, alpha, beta),
+ * src/generators.jl:634-645; `coeffs` has n_coeffs entries (shared by the batch). */
+int32_t qp_gen_mul(qp_gen_t gen, const qp_c128* coeffs, qp_c128 alpha, qp_c128 beta,
+                   qp_state_t x, qp_state_t y);
+/* out[b] = <x_b| sum_l c_l H_l |y_b> : dot(x, A::Operator, y), src/generators.jl:648-660 */
+int32_t qp_gen_dot(qp_gen_t gen, const qp_c128* coeffs, qp_state_t x, qp_state_t y,
+                   qp_c128* out /*[batch]*/);
+
+/* ------------------------------------------------------------------ Chebyshev
+ * Replaces: ChebyWrk (src/cheby.jl:87-124) and cheby! (src/cheby.jl:150-213).  The
+ * coefficient table a_k comes from the host (cheby_coeffs, src/cheby.jl:25-39). */
+int32_t qp_cheby_create(qp_gen_t gen, qp_state_t like, qp_cheby_t* wrk);
+int32_t qp_cheby_destroy(qp_cheby_t wrk);
+/* (re-)upload coefficients without touching the operators (reinit_prop!,
+ * src/cheby_propagator.jl:243-299); `limit` is ChebyWrk.limit (threshold of the
+ * normalization check, src/cheby.jl:164,197) */
+int32_t qp_cheby_set_coeffs(qp_cheby_t wrk, const double* a, int32_t n_a, double Delta,
+                            double E_min, double dt_abs, double limit);
+/* One prop_step!: st <- exp(-i H dt) st with H = sum_l c_l H_l.
+ *   op_coeffs: n_coeffs numbers if coeffs_per_traj == 0 (shared by all trajectories),
+ *              else [n_coeffs][batch] (trajectory b uses op_coeffs[l*batch + b]).
+ *   dt_signed: +-dt_abs (backward propagation negates, src/cheby_propagator.jl:353-356);
+ *              |dt| must match dt_abs of qp_cheby_set_coeffs (src/cheby.jl:157).
+ *   check_normalization: src/cheby.jl:194-200; failing returns QP_ERR_NORMALIZATION. */
+int32_t qp_cheby_step(qp_cheby_t wrk, qp_state_t st, const qp_c128* op_coeffs,
+                      int32_t coeffs_per_traj, double dt_signed, int32_t check_normalization);
+/* algorithmic bytes of one prop_step! as defined in SURVEY.md §8d:
+ * (n_a - 1) * (M + 80 N B) */
+int32_t qp_cheby_step_bytes(qp_cheby_t wrk, int64_t* bytes);
+
+/* ------------------------------------------------------------------ Arnoldi / Newton
+ * Replaces: arnoldi! (src/arnoldi.jl:60-100), extend_arnoldi! (:115-129) and the vector
+ * work of newton! (src/newton.jl:346-367).  The small dense step (Ritz values, Leja
+ * points, divided differences, polynomial in the Hessenberg matrix; src/newton.jl:297-343)
+ * stays on the host, where `func` is an arbitrary closure.  Krylov workspaces hold
+ * m_max+1 vectors of a single state (batch == 1). */
+int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max, qp_krylov_t* K);
+int32_t qp_krylov_destroy(qp_krylov_t K);
+/* q_1 <- v; for j = 1..m: q_{j+1} = H q_j, orthogonalised against q_1..q_j; fills the
+ * column-major (ld x ld) host matrix `hess` exactly like the reference (entries scaled by
+ * dt, zero elsewhere).  Returns the possibly reduced dimension in *m_out. */
+int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_t v, int32_t m, double dt,
+                   int32_t extended, double norm_min, qp_c128* hess, int32_t ld, int32_t* m_out);
+/* extend an (m-1)x(m-1) non-extended decomposition to m x m; *extended_out = 0 if the
+ * Krylov space was exhausted (reference returns early, src/arnoldi.jl:116-117). */
+int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, int32_t m, double dt,
+                          double norm_min, qp_c128* hess, int32_t ld, int32_t* extended_out);
+/* st <- (accumulate ? st : 0) + sum_{i<n_w} w[i] q_{first+i}   (src/newton.jl:346-352) */
+int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* w, int32_t first, int32_t n_w,
+                          qp_state_t st, int32_t accumulate);
+/* copy Krylov vector q_{index} (0-based) to/from a state */
+int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst);
+int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPROP_H */

@@ -1,0 +1,378 @@
+// Arnoldi / Newton vector kernels: replaces arnoldi! (reference src/arnoldi.jl:60-100),
+// extend_arnoldi! (:115-129) and the vector updates of newton! (src/newton.jl:346-367).
+//
+// Orthogonalisation: the reference runs modified Gram-Schmidt, j sequential dot+axpy pairs
+// per column, i.e. 2j passes over the new vector.  Here one fused multi-dot pass computes the
+// whole Hessenberg column (plus |w|^2), one fused pass subtracts the projections and returns
+// the new norm, and a second (DGKS) round is taken only when the norm dropped by more than
+// 1/sqrt(2) -- classical Gram-Schmidt with selective re-orthogonalisation, which is at least
+// as orthogonal as MGS.  The Hessenberg entries differ from the reference's at rounding
+// level; parity is asserted on the propagated state.
+#include <cmath>
+#include <cstring>
+
+#include "spmv.cuh"
+
+constexpr int KV = 8;           // Krylov vectors handled per fused pass
+constexpr int KBLOCK = 256;
+
+struct Weights {
+  double2 w[KV];
+};
+
+// partial[block][KV+1][2]: <q_i|w> for i < nv and |w|^2 in slot KV
+template <int NV>
+__global__ void __launch_bounds__(KBLOCK)
+k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ w, int64_t n,
+           double* __restrict__ partial) {
+  double sr[NV], si[NV], ww = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sr[i] = si[i] = 0.0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const double2 wv = w[r];
+    ww += wv.x * wv.x + wv.y * wv.y;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double2 qv = q0[i * stride + r];
+      sr[i] += qv.x * wv.x + qv.y * wv.y;  // conj(q) * w
+      si[i] += qv.x * wv.y - qv.y * wv.x;
+    }
+  }
+  __shared__ double sh[KBLOCK / 32][2 * NV + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    ww += __shfl_xor_sync(0xffffffffu, ww, o);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sr[i] += __shfl_xor_sync(0xffffffffu, sr[i], o);
+      si[i] += __shfl_xor_sync(0xffffffffu, si[i], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sh[warp][2 * i] = sr[i];
+      sh[warp][2 * i + 1] = si[i];
+    }
+    sh[warp][2 * NV] = ww;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NV + 1) {
+    double t = 0.0;
+    for (int k = 0; k < KBLOCK / 32; ++k) t += sh[k][threadIdx.x];
+    const int slot = threadIdx.x == 2 * NV ? 2 * KV : threadIdx.x;
+    partial[(size_t)blockIdx.x * (2 * KV + 2) + slot] = t;
+  }
+}
+
+// h[i] = sum_blocks partial[.][i] ;  |w|^2 -> out_ww
+__global__ void k_multidot_final(const double* __restrict__ partial, int nblocks, int nv,
+                                 double2* __restrict__ h, double* __restrict__ out_ww) {
+  int t = threadIdx.x;
+  if (t < nv) {
+    double tr = 0, ti = 0;
+    for (int k = 0; k < nblocks; ++k) {
+      tr += partial[(size_t)k * (2 * KV + 2) + 2 * t];
+      ti += partial[(size_t)k * (2 * KV + 2) + 2 * t + 1];
+    }
+    h[t] = make_double2(tr, ti);
+  }
+  if (t == nv && out_ww) {
+    double s = 0;
+    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * (2 * KV + 2) + 2 * KV];
+    *out_ww = s;
+  }
+}
+
+// w -= sum_i h[i] q_i ; partial[block] = |w_new|^2 contribution
+template <int NV>
+__global__ void __launch_bounds__(KBLOCK)
+k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h,
+              double2* __restrict__ w, int64_t n, double* __restrict__ partial) {
+  double2 hv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) hv[i] = h[i];
+  double nn = 0.0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double2 wv = w[r];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double2 qv = q0[i * stride + r];
+      wv.x -= hv[i].x * qv.x - hv[i].y * qv.y;
+      wv.y -= hv[i].x * qv.y + hv[i].y * qv.x;
+    }
+    w[r] = wv;
+    nn += wv.x * wv.x + wv.y * wv.y;
+  }
+  __shared__ double sh[KBLOCK / 32];
+  for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = nn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < KBLOCK / 32; ++k) t += sh[k];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void k_sum_partial(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < nblocks; ++k) t += partial[k];
+    *out = t;
+  }
+}
+
+__global__ void k_scale_real(double2* __restrict__ x, double s, int64_t n) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double2 v = x[r];
+    x[r] = make_double2(s * v.x, s * v.y);
+  }
+}
+
+// y (+)= sum_i w_i q_i
+template <int NV>
+__global__ void __launch_bounds__(KBLOCK)
+k_combine(const double2* __restrict__ q0, int64_t stride, Weights wt, double2* __restrict__ y, int64_t n,
+          int accumulate) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double2 acc = accumulate ? y[r] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double2 qv = q0[i * stride + r];
+      acc.x += wt.w[i].x * qv.x - wt.w[i].y * qv.y;
+      acc.y += wt.w[i].x * qv.y + wt.w[i].y * qv.x;
+    }
+    y[r] = acc;
+  }
+}
+
+static int kgrid(qp_ctx_t ctx, int64_t n) {
+  int64_t want = (n + KBLOCK - 1) / KBLOCK;
+  int64_t cap = (int64_t)ctx->sm_count * 4;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+#define DISPATCH_NV(nv, CALL)          \
+  switch (nv) {                        \
+    case 1: { constexpr int NV = 1; CALL; } break; \
+    case 2: { constexpr int NV = 2; CALL; } break; \
+    case 3: { constexpr int NV = 3; CALL; } break; \
+    case 4: { constexpr int NV = 4; CALL; } break; \
+    case 5: { constexpr int NV = 5; CALL; } break; \
+    case 6: { constexpr int NV = 6; CALL; } break; \
+    case 7: { constexpr int NV = 7; CALL; } break; \
+    default: { constexpr int NV = 8; CALL; } break; \
+  }
+
+// ---------------------------------------------------------------------------------------
+
+extern "C" int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max, qp_krylov_t* out) {
+  if (!gen) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_create: null generator");
+  qp_ctx_t ctx = gen->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, out != nullptr && like != nullptr, "qp_krylov_create: null argument");
+  *out = nullptr;
+  QP_REQUIRE(ctx, like->ctx == ctx && like->n == gen->n, "qp_krylov_create: state does not match the generator");
+  if (like->batch != 1)
+    return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_krylov_create: Krylov workspaces hold a single state (batch == 1)");
+  QP_REQUIRE(ctx, m_max >= 1, "qp_krylov_create: m_max must be >= 1");
+  qp_krylov_t K = new qp_krylov_s();
+  K->ctx = ctx;
+  K->gen = gen;
+  K->n = like->n;
+  K->m_max = m_max;
+  cudaError_t e;
+  if ((e = cudaMalloc(&K->q, sizeof(double2) * (size_t)K->n * (size_t)(m_max + 1))) != cudaSuccess ||
+      (e = cudaMalloc(&K->d_h, sizeof(double2) * (size_t)(m_max + 8))) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(K->q);
+    delete K;
+    return qp_fail(ctx, QP_ERR_OOM, "qp_krylov_create: cudaMalloc of %d Krylov vectors failed: %s", m_max + 1,
+                   cudaGetErrorString(e));
+  }
+  *out = K;
+  return QP_OK;
+}
+
+extern "C" int32_t qp_krylov_destroy(qp_krylov_t K) {
+  if (!K) return QP_OK;
+  cudaSetDevice(K->ctx->device);
+  cudaStreamSynchronize(K->ctx->stream);
+  cudaFree(K->q);
+  cudaFree(K->d_h);
+  delete K;
+  return QP_OK;
+}
+
+// Orthogonalise w = q[j+1] against q[0..j].  On return h_host[0..j] holds <q_i|w> (summed over
+// DGKS rounds) and *norm_out = |w| after projection.
+static int32_t orthogonalise(qp_krylov_t K, int j, std::vector<qp_c128>& h_host, double* norm_out) {
+  qp_ctx_t ctx = K->ctx;
+  const int64_t n = K->n;
+  const int nvec = j + 1;
+  double2* w = K->q + (size_t)(j + 1) * n;
+  const int nblocks = kgrid(ctx, n);
+  // scratch: [0 .. 2 doubles): ww, nrm ; then partials
+  const size_t need = 4 + (size_t)nblocks * (2 * KV + 2);
+  QP_CHECK(qp_ctx_reserve_red(ctx, need));
+  double* d_ww = ctx->d_red;
+  double* d_nrm = ctx->d_red + 1;
+  double* partial = ctx->d_red + 4;
+  h_host.assign(nvec, qp_c128{0.0, 0.0});
+  std::vector<double2> h_round(nvec);
+  for (int round = 0; round < 3; ++round) {
+    // column (or correction) h = Q^H w, KV vectors per pass
+    for (int i0 = 0; i0 < nvec; i0 += KV) {
+      const int nv = std::min(KV, nvec - i0);
+      const double2* q0 = K->q + (size_t)i0 * n;
+      DISPATCH_NV(nv, (k_multidot<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, w, n, partial)));
+      QP_LAUNCHED(ctx);
+      k_multidot_final<<<1, 32, 0, ctx->stream>>>(partial, nblocks, nv, K->d_h + i0, i0 == 0 ? d_ww : nullptr);
+      QP_LAUNCHED(ctx);
+    }
+    for (int i0 = 0; i0 < nvec; i0 += KV) {
+      const int nv = std::min(KV, nvec - i0);
+      const double2* q0 = K->q + (size_t)i0 * n;
+      DISPATCH_NV(nv, (k_project_out<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, K->d_h + i0, w, n, partial)));
+      QP_LAUNCHED(ctx);
+    }
+    k_sum_partial<<<1, 32, 0, ctx->stream>>>(partial, nblocks, d_nrm);
+    QP_LAUNCHED(ctx);
+    double scal[2];
+    QP_CUDA(ctx, cudaMemcpyAsync(h_round.data(), K->d_h, sizeof(double2) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
+    QP_CUDA(ctx, cudaMemcpyAsync(scal, d_ww, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nvec; ++i) {
+      h_host[i].re += h_round[i].x;
+      h_host[i].im += h_round[i].y;
+    }
+    *norm_out = sqrt(scal[1]);
+    // DGKS criterion: re-orthogonalise when the projection removed more than half of |w|^2
+    if (!(scal[1] < 0.5 * scal[0]) || scal[1] == 0.0) break;
+  }
+  return QP_OK;
+}
+
+static int32_t krylov_matvec(qp_krylov_t K, int stride, int j) {
+  // q[j+1] = H q[j]   ("matrix-vector product", src/arnoldi.jl:81-83)
+  return qp_gen_apply(K->gen, stride, make_double2(1.0, 0.0), make_double2(0.0, 0.0),
+                      K->q + (size_t)j * K->n, K->q + (size_t)(j + 1) * K->n, 1);
+}
+
+extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_t v, int32_t m, double dt,
+                              int32_t extended, double norm_min, qp_c128* hess, int32_t ld, int32_t* m_out) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_arnoldi: null workspace");
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, v && v->ctx == ctx && v->n == K->n && v->batch == 1, "qp_arnoldi: bad start vector");
+  QP_REQUIRE(ctx, hess != nullptr && m_out != nullptr, "qp_arnoldi: null output");
+  QP_REQUIRE(ctx, m >= 1, "qp_arnoldi: m must be >= 1");
+  // @assert length(q) >= m + 1 ; size(Hess) >= dim_hess   src/arnoldi.jl:76-77
+  QP_REQUIRE(ctx, m <= K->m_max, "qp_arnoldi: m=%d exceeds the workspace (m_max=%d)", m, K->m_max);
+  const int dim_hess = extended ? m + 1 : m;
+  QP_REQUIRE(ctx, ld >= dim_hess, "qp_arnoldi: Hessenberg storage %d x %d too small for dimension %d", ld, ld, dim_hess);
+  QpScopedTimer timer(ctx, "arnoldi!");
+  int stride = 0;
+  QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
+  memset(hess, 0, sizeof(qp_c128) * (size_t)ld * (size_t)ld);  // fill!(Hess, 0)  :78
+  const int64_t n = K->n;
+  QP_CUDA(ctx, cudaMemcpyAsync(K->q, v->d, sizeof(double2) * n, cudaMemcpyDeviceToDevice, ctx->stream));  // :79
+  std::vector<qp_c128> h;
+  int m_eff = m;
+  for (int j = 0; j < m; ++j) {
+    QP_CHECK(krylov_matvec(K, stride, j));
+    double hn = 0.0;
+    QP_CHECK(orthogonalise(K, j, h, &hn));
+    for (int i = 0; i <= j; ++i) {  // Hess[i,j] = dt <q_i|q_{j+1}>   :85
+      hess[(size_t)j * ld + i].re = dt * h[i].re;
+      hess[(size_t)j * ld + i].im = dt * h[i].im;
+    }
+    if (j + 1 < m || extended) {  // :88-97
+      hess[(size_t)j * ld + (j + 1)].re = dt * hn;
+      hess[(size_t)j * ld + (j + 1)].im = 0.0;
+      if (hn < norm_min) {  // dimensionality exhausted
+        m_eff = j + 1;
+        break;
+      }
+      k_scale_real<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(j + 1) * n, 1.0 / hn, n);
+      QP_LAUNCHED(ctx);
+    }
+  }
+  *m_out = m_eff;
+  return QP_OK;
+}
+
+extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, int32_t m, double dt,
+                                     double norm_min, qp_c128* hess, int32_t ld, int32_t* extended_out) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_arnoldi_extend: null workspace");
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, hess != nullptr, "qp_arnoldi_extend: null Hessenberg matrix");
+  QP_REQUIRE(ctx, m >= 2 && m <= K->m_max && ld >= m, "qp_arnoldi_extend: bad dimension m=%d (m_max=%d, ld=%d)", m,
+             K->m_max, ld);
+  const int64_t n = K->n;
+  if (extended_out) *extended_out = 0;
+  double nrm2 = 0.0;
+  QP_CHECK(qp_reduce_norm2(ctx, K->q + (size_t)(m - 1) * n, n, 1, &nrm2));
+  const double hn = sqrt(nrm2);
+  if (hn < norm_min) return QP_OK;  // src/arnoldi.jl:116-117
+  int stride = 0;
+  QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
+  hess[(size_t)(m - 2) * ld + (m - 1)].re = dt * hn;  // Hess[m, m-1]
+  hess[(size_t)(m - 2) * ld + (m - 1)].im = 0.0;
+  k_scale_real<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
+  QP_LAUNCHED(ctx);
+  QP_CHECK(krylov_matvec(K, stride, m - 1));
+  std::vector<qp_c128> h;
+  double hn2 = 0.0;
+  QP_CHECK(orthogonalise(K, m - 1, h, &hn2));
+  for (int i = 0; i < m; ++i) {
+    hess[(size_t)(m - 1) * ld + i].re = dt * h[i].re;
+    hess[(size_t)(m - 1) * ld + i].im = dt * h[i].im;
+  }
+  if (extended_out) *extended_out = 1;
+  return QP_OK;
+}
+
+extern "C" int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* wts, int32_t first, int32_t n_w,
+                                     qp_state_t st, int32_t accumulate) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_combine: null workspace");
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, st && st->ctx == ctx && st->n == K->n && st->batch == 1, "qp_krylov_combine: bad state");
+  QP_REQUIRE(ctx, wts != nullptr && n_w >= 1 && first >= 0 && first + n_w <= K->m_max + 1,
+             "qp_krylov_combine: vectors [%d, %d) outside the workspace", first, first + n_w);
+  const int64_t n = K->n;
+  for (int i0 = 0; i0 < n_w; i0 += KV) {
+    const int nv = std::min(KV, n_w - i0);
+    Weights wt;
+    memset(&wt, 0, sizeof(wt));
+    for (int i = 0; i < nv; ++i) wt.w[i] = make_double2(wts[i0 + i].re, wts[i0 + i].im);
+    const double2* q0 = K->q + (size_t)(first + i0) * n;
+    const int acc = (accumulate || i0 > 0) ? 1 : 0;
+    DISPATCH_NV(nv, (k_combine<NV><<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(q0, n, wt, st->d, n, acc)));
+    QP_LAUNCHED(ctx);
+  }
+  return QP_OK;
+}
+
+extern "C" int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_get: null workspace");
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, dst && dst->ctx == ctx && dst->n == K->n && dst->batch == 1, "qp_krylov_get: bad state");
+  QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_get: index %d out of range", index);
+  QP_CUDA(ctx, cudaMemcpyAsync(dst->d, K->q + (size_t)index * K->n, sizeof(double2) * K->n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return QP_OK;
+}
+
+extern "C" int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_set: null workspace");
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, src && src->ctx == ctx && src->n == K->n && src->batch == 1, "qp_krylov_set: bad state");
+  QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_set: index %d out of range", index);
+  QP_CUDA(ctx, cudaMemcpyAsync(K->q + (size_t)index * K->n, src->d, sizeof(double2) * K->n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return QP_OK;
+}

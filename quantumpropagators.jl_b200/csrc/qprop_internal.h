@@ -1,0 +1,184 @@
+// Internal declarations of libqprop_b200 (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "qprop.h"
+
+// ---------------------------------------------------------------------------------------
+// limits of the packed column word: low 28 bits = column, high 4 bits = operator index
+// ---------------------------------------------------------------------------------------
+constexpr int QP_COL_BITS = 28;
+constexpr uint32_t QP_COL_MASK = (1u << QP_COL_BITS) - 1u;
+constexpr int QP_MAX_OPS = 16;
+constexpr int QP_SELL_C = 32;  // slice height of the sliced-ELL format = warp size
+
+struct qp_timer_rec {
+  int64_t ncalls = 0;
+  double seconds = 0.0;
+};
+
+struct qp_ctx_s {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool timers_on = false;
+  std::map<std::string, qp_timer_rec> timers;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_stage = nullptr;  // fences reuse of the pinned coefficient staging buffer
+  // reduction scratch (device partials + pinned host landing zone)
+  double* d_red = nullptr;
+  double* h_red = nullptr;
+  size_t red_doubles = 0;
+  // small pinned staging area for per-step coefficient uploads
+  qp_c128* h_stage = nullptr;
+  size_t stage_elems = 0;
+};
+
+struct qp_op_s {
+  qp_ctx_t ctx = nullptr;
+  bool dense = false;
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  // sparse: canonical CSR, Int32 indices
+  uint32_t* d_ptr = nullptr;
+  uint32_t* d_col = nullptr;
+  double2* d_val = nullptr;
+  // dense: row-major n x n
+  double2* d_dense = nullptr;
+};
+
+// device view of a merged multi-operator matrix (CSR or SELL-32)
+struct MatView {
+  const uint32_t* ptr;   // CSR: row pointers [n+1];  SELL: slice offsets [n_slices+1] (in entries)
+  const uint32_t* colop; // packed (op << 28 | col)
+  const double2* val;
+  int64_t n;             // rows
+};
+
+struct qp_gen_s {
+  qp_ctx_t ctx = nullptr;
+  int n_ops = 0, n_coeffs = 0, drift = 0;
+  int64_t n = 0;
+  int format = QP_FORMAT_CSR;
+  std::vector<qp_op_t> ops;
+  int64_t nnz_total = 0;       // true nonzeros over all operators
+  int64_t stored_entries = 0;  // entries stored in the chosen format (incl. padding)
+  int64_t matrix_bytes = 0;    // algorithmic M of SURVEY.md §8
+  int lanes = 8;               // CSR: lanes per row (power of two <= 32)
+  // merged CSR (always built for sparse generators)
+  uint32_t* d_mptr = nullptr;
+  uint32_t* d_mcolop = nullptr;
+  double2* d_mval = nullptr;
+  // SELL-32 (built when selected)
+  uint32_t* d_sptr = nullptr;
+  uint32_t* d_scolop = nullptr;
+  double2* d_sval = nullptr;
+  int64_t n_slices = 0;
+  // dense: pointers to the row-major operators
+  const double2** d_dense_ops = nullptr;
+  // device copy of the effective per-operator coefficients (drift ops = 1), [n_ops][B]
+  double2* d_coef = nullptr;
+  size_t coef_elems = 0;
+};
+
+struct qp_state_s {
+  qp_ctx_t ctx = nullptr;
+  int64_t n = 0, batch = 1;
+  double2* d = nullptr;
+};
+
+struct qp_cheby_s {
+  qp_ctx_t ctx = nullptr;
+  qp_gen_t gen = nullptr;
+  int64_t n = 0, batch = 1;
+  double2* w1 = nullptr;
+  double2* w2 = nullptr;
+  std::vector<double> a;
+  double Delta = 0, E_min = 0, dt = 0, limit = 1e-12;
+  double* d_chk = nullptr;  // normalization-check accumulators [n_a][batch][3]
+  size_t chk_doubles = 0;
+};
+
+struct qp_krylov_s {
+  qp_ctx_t ctx = nullptr;
+  qp_gen_t gen = nullptr;
+  int64_t n = 0;
+  int m_max = 0;
+  double2* q = nullptr;    // (m_max + 1) vectors of length n, contiguous
+  double2* d_h = nullptr;  // device Hessenberg column (m_max + 2 complex)
+};
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+int32_t qp_fail(qp_ctx_t ctx, int32_t code, const char* fmt, ...);
+
+#define QP_CUDA(ctx, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      cudaGetLastError();                                                                   \
+      return qp_fail((ctx), e__ == cudaErrorMemoryAllocation ? QP_ERR_OOM : QP_ERR_CUDA,    \
+                     "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,     \
+                     __LINE__);                                                             \
+    }                                                                                       \
+  } while (0)
+
+#define QP_CHECK(expr)               \
+  do {                               \
+    int32_t s__ = (expr);            \
+    if (s__ != QP_OK) return s__;    \
+  } while (0)
+
+#define QP_REQUIRE(ctx, cond, ...)                                   \
+  do {                                                               \
+    if (!(cond)) return qp_fail((ctx), QP_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+// count + check a kernel launch
+#define QP_LAUNCHED(ctx)                    \
+  do {                                      \
+    (ctx)->launches++;                      \
+    QP_CUDA((ctx), cudaGetLastError());     \
+  } while (0)
+
+int32_t qp_ctx_bind(qp_ctx_t ctx);  // cudaSetDevice
+int32_t qp_ctx_reserve_red(qp_ctx_t ctx, size_t doubles);
+int32_t qp_ctx_reserve_stage(qp_ctx_t ctx, size_t elems);
+
+// timers ("matrix-vector product", "prop_step!", ...): CUDA events on the ctx stream
+struct QpScopedTimer {
+  qp_ctx_t ctx;
+  const char* label;
+  bool active;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  QpScopedTimer(qp_ctx_t c, const char* l);
+  ~QpScopedTimer();
+};
+
+// ---------------------------------------------------------------------------------------
+// internal kernels shared between translation units
+// ---------------------------------------------------------------------------------------
+
+// upload effective per-operator coefficients: drift operators get 1, the rest op_coeffs.
+// per_traj == 0: n_coeffs numbers broadcast; else [n_coeffs][batch].
+int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, int64_t batch,
+                          int* coef_stride_out);
+
+// y <- beta*y + alpha*H x using the coefficients currently in gen->d_coef
+int32_t qp_gen_apply(qp_gen_t gen, int coef_stride, double2 alpha, double2 beta, const double2* x,
+                     double2* y, int64_t batch);
+
+// deterministic reductions; results land in ctx->h_red after a stream sync
+int32_t qp_reduce_dot(qp_ctx_t ctx, const double2* x, const double2* y, int64_t n, int64_t batch,
+                      qp_c128* out);
+int32_t qp_reduce_norm2(qp_ctx_t ctx, const double2* x, int64_t n, int64_t batch, double* out);

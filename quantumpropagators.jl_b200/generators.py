@@ -1,0 +1,274 @@
+"""Host-side generator / operator model (mirror of the operator-algebra part of the
+reference's ``src/generators.jl``).
+
+A ``Generator`` is H(t) = Σ_drift H_l + Σ_l a_l(t) H_l; evaluating it on an interval gives a
+static ``Operator`` (lazy sum Σ c_l H_l) that shares the component operators and carries only
+the numbers c_l.  The component operators are uploaded to the GPU ONCE per generator
+(``to_device``); every later ``evaluate_`` only rewrites the coefficient list, which is what
+``qp_cheby_step`` / ``qp_arnoldi`` take per call.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import controls as _controls
+from . import _lib as L
+from .device import Context, DeviceGenerator, DeviceState
+
+__all__ = [
+    "Generator",
+    "Operator",
+    "ScaledOperator",
+    "hamiltonian",
+    "evaluate",
+    "evaluate_",
+    "get_controls",
+]
+
+
+def _is_number(x) -> bool:
+    return isinstance(x, (int, float, complex, np.number)) and not isinstance(x, bool)
+
+
+class _DeviceCache:
+    """ops -> DeviceGenerator, shared between a Generator and the Operators evaluated from it
+    (they share ``ops`` by reference, like the reference asserts in ``src/generators.jl:759``)."""
+
+    def __init__(self):
+        self.by_ctx = {}
+
+
+class Generator:
+    """``Generator(ops, amplitudes)`` (reference ``src/generators.jl:44-61``)."""
+
+    def __init__(self, ops, amplitudes):
+        ops, amplitudes = list(ops), list(amplitudes)
+        if len(amplitudes) > len(ops):
+            raise ValueError("The number of amplitudes cannot exceed the number of operators in a Generator")
+        if len(amplitudes) < 1:
+            raise ValueError("A Generator requires at least one amplitude")
+        self.ops = ops
+        self.amplitudes = amplitudes
+        self._cache = _DeviceCache()
+
+    @property
+    def shape(self):
+        return self.ops[0].shape
+
+    def __repr__(self):
+        return f"Generator with {len(self.ops)} ops and {len(self.amplitudes)} amplitudes"
+
+    def to_device(self, ctx: Context, fmt="auto") -> DeviceGenerator:
+        return _to_device(self, ctx, len(self.amplitudes), fmt)
+
+
+class Operator:
+    """``Operator(ops, coeffs)``: lazy sum Σ c_l H_l; with fewer coeffs than ops the leading
+    ops have c = 1 (reference ``src/generators.jl:111-125``)."""
+
+    def __init__(self, ops, coeffs, _cache=None):
+        coeffs = list(coeffs)
+        if len(coeffs) > len(ops):
+            raise ValueError("The number of coefficients cannot exceed the number of operators in an Operator")
+        self.ops = ops if isinstance(ops, list) else list(ops)
+        self.coeffs = coeffs
+        self._cache = _cache if _cache is not None else _DeviceCache()
+
+    @property
+    def shape(self):
+        return self.ops[0].shape
+
+    def __repr__(self):
+        return f"Operator with {len(self.ops)} ops and {len(self.coeffs)} coeffs"
+
+    def toarray(self) -> np.ndarray:
+        """``Array(O)``: dense sum on the host (small operators only; used by specrange :diag)."""
+        drift = len(self.ops) - len(self.coeffs)
+        out = np.zeros(self.shape, dtype=np.complex128)
+        for i, op in enumerate(self.ops):
+            c = self.coeffs[i - drift] if i >= drift else 1.0
+            out += c * (op.toarray() if sp.issparse(op) else np.asarray(op))
+        return out
+
+    def to_device(self, ctx: Context, fmt="auto") -> DeviceGenerator:
+        return _to_device(self, ctx, len(self.coeffs), fmt)
+
+    # -- operator verbs on device states (src/interfaces/operator.jl:21-44) ---------------
+    def mul(self, y: DeviceState, x: DeviceState, alpha=1.0, beta=0.0) -> DeviceState:
+        """``mul!(y, self, x, α, β)`` (reference ``src/generators.jl:634-645``)."""
+        return self.to_device(x.ctx).mul(y, x, self.coeffs, alpha, beta)
+
+    def dot(self, x: DeviceState, y: DeviceState):
+        """``dot(x, self, y)`` (reference ``src/generators.jl:648-660``)."""
+        return self.to_device(x.ctx).dot(x, y, self.coeffs)
+
+    def __matmul__(self, x: DeviceState) -> DeviceState:
+        """``self * x`` (reference ``src/generators.jl:671-684``)."""
+        return self.mul(x.similar(), x)
+
+    def __rmul__(self, alpha):
+        if not _is_number(alpha):
+            return NotImplemented
+        return ScaledOperator(alpha, self)
+
+    __mul__ = __rmul__
+
+
+class ScaledOperator:
+    """``ScaledOperator(α, Ĥ)`` (reference ``src/generators.jl:238-249``); α == 1 returns Ĥ."""
+
+    def __new__(cls, coeff, operator):
+        if coeff == 1.0:
+            return operator
+        self = super().__new__(cls)
+        self.coeff = coeff
+        self.operator = operator
+        return self
+
+    @property
+    def shape(self):
+        return self.operator.shape
+
+    def toarray(self):
+        return self.coeff * _toarray(self.operator)
+
+    def mul(self, y, x, alpha=1.0, beta=0.0):
+        """reference ``src/generators.jl:701-703``"""
+        return _as_operator(self.operator).mul(y, x, self.coeff * alpha, beta)
+
+    def dot(self, x, y):
+        """reference ``src/generators.jl:706-708``"""
+        return self.coeff * _as_operator(self.operator).dot(x, y)
+
+    def __matmul__(self, x):
+        return self.mul(x.similar(), x)
+
+    def __rmul__(self, alpha):
+        if not _is_number(alpha):
+            return NotImplemented
+        return ScaledOperator(alpha * self.coeff, self.operator)
+
+    __mul__ = __rmul__
+
+
+def _toarray(H):
+    if hasattr(H, "toarray"):
+        return np.asarray(H.toarray())
+    return np.asarray(H)
+
+
+def _as_operator(H) -> Operator:
+    """Wrap a bare matrix as a one-term lazy sum (all drift)."""
+    if isinstance(H, Operator):
+        return H
+    if isinstance(H, ScaledOperator):
+        raise TypeError("nested ScaledOperator")
+    cache = getattr(H, "_qp_cache", None)
+    op = Operator([H], [])
+    if cache is not None:
+        op._cache = cache
+    else:
+        try:
+            H._qp_cache = op._cache
+        except AttributeError:  # ndarray: no attribute slot; cache lives with the wrapper
+            pass
+    return op
+
+
+def _to_device(obj, ctx: Context, n_coeffs: int, fmt) -> DeviceGenerator:
+    key = (id(ctx), n_coeffs, fmt)
+    dev = obj._cache.by_ctx.get(key)
+    if dev is None:
+        dev = DeviceGenerator(ctx, obj.ops, n_coeffs, fmt)
+        obj._cache.by_ctx[key] = dev
+    return dev
+
+
+def hamiltonian(*terms, check=True):
+    """``hamiltonian(terms...)`` (reference ``src/generators.jl:388-469``): each term is an
+    operator (drift) or a pair ``(op, ampl)``.  Drift terms are summed into one operator,
+    terms with the same amplitude are merged; purely numeric amplitudes give an ``Operator``,
+    no amplitudes at all give the drift operator itself."""
+    drift, ops, amplitudes = [], [], []
+    for term in terms:
+        if isinstance(term, (tuple, list)):
+            if len(term) != 2:
+                raise ValueError("time-dependent term must be 2-tuple")
+            op, ampl = term
+            slot = next(
+                (j for j, a in enumerate(amplitudes) if a is ampl or (_is_number(a) and _is_number(ampl) and a == ampl)),
+                None,
+            )
+            if slot is None:
+                ops.append(op)
+                amplitudes.append(ampl)
+            else:
+                ops[slot] = ops[slot] + op
+        elif drift:
+            drift[0] = drift[0] + term
+        else:
+            drift.append(term)
+    if not amplitudes:
+        if not drift:
+            raise ValueError("Generator has no terms")
+        return drift[0]
+    if all(_is_number(a) for a in amplitudes):
+        return Operator(drift + ops, amplitudes)
+    return Generator(drift + ops, amplitudes)
+
+
+def canonical(generator):
+    """Tuple generators ``(H0, (H1, ϵ1), ...)`` are canonicalised through ``hamiltonian`` so
+    that nothing is materialised per step."""
+    if isinstance(generator, (tuple, list)):
+        return hamiltonian(*generator, check=False)
+    return generator
+
+
+def get_controls(generator):
+    """Unique controls of a generator in order of first appearance (reference
+    ``src/generators.jl:711-733``)."""
+    generator = canonical(generator)
+    if not isinstance(generator, Generator):
+        return ()
+    found = []
+    for ampl in generator.amplitudes:
+        for control in _controls.get_controls(ampl):
+            if not any(control is c for c in found):
+                found.append(control)
+    return tuple(found)
+
+
+def evaluate(generator, *args, vals_dict=None):
+    """``evaluate(generator, tlist, n; vals_dict)`` -> static ``Operator`` sharing the
+    generator's ops (reference ``src/generators.jl:740-754``); static objects evaluate to
+    themselves (``src/controls.jl:309-313``)."""
+    generator = canonical(generator)
+    if not isinstance(generator, Generator):
+        return generator
+    coeffs = []
+    for i, ampl in enumerate(generator.amplitudes):
+        c = _controls.evaluate(ampl, *args, vals_dict=vals_dict)
+        if not _is_number(c):
+            raise TypeError(f"In `evaluate`, the amplitude {i + 1} evaluates to {type(c)}, not a number")
+        coeffs.append(c)
+    return Operator(generator.ops, coeffs, _cache=generator._cache)
+
+
+def evaluate_(op, generator, *args, vals_dict=None):
+    """``evaluate!(op, generator, tlist, n; vals_dict)``: rewrites ``op.coeffs`` only
+    (reference ``src/generators.jl:757-766``)."""
+    if not isinstance(generator, Generator):
+        if op is generator:
+            return op
+        raise TypeError("typeof(op) = typeof(generator), but op ≢ generator")
+    if len(op.ops) != len(generator.ops) or any(a is not b for a, b in zip(op.ops, generator.ops)):
+        raise AssertionError("op was not evaluated from this generator")
+    for i, ampl in enumerate(generator.amplitudes):
+        c = _controls.evaluate(ampl, *args, vals_dict=vals_dict)
+        if not _is_number(c):
+            raise AssertionError("amplitude does not evaluate to a number")
+        op.coeffs[i] = c
+    return op

@@ -1,0 +1,384 @@
+"""The propagator protocol: ``init_prop`` / ``prop_step`` / ``set_state`` / ``set_t`` /
+``reinit_prop`` / ``propagate`` for ``method="cheby"`` and ``method="newton"``, backed by
+device-resident states.
+
+Host mirror of the reference's ``src/propagator.jl``, ``src/pwc_utils.jl``,
+``src/cheby_propagator.jl``, ``src/newton_propagator.jl`` and the step loop of
+``src/propagate.jl``; Julia's ``!`` functions drop the bang (``prop_step!`` -> ``prop_step``).
+Interval indices ``n`` are 1-based like the reference's.  A host (NumPy) initial state is
+uploaded once; ``propagator.state`` is always a :class:`DeviceState`, and ``prop_step``
+returns that same object (the identity the reference's ``check_propagator`` demands of
+in-place propagators, ``src/interfaces/propagator.jl:162-167``).
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import controls as _c
+from .cheby import ChebyWrk, cheby_
+from .controls import IdDict, discretize, discretize_on_midpoints
+from .device import Context, DeviceState, default_context
+from .generators import Generator, Operator, canonical, evaluate, evaluate_, get_controls, _as_operator
+from .newton import NewtonWrk, newton_
+from .specrad import specrange
+
+__all__ = [
+    "init_prop",
+    "prop_step",
+    "set_state",
+    "set_t",
+    "reinit_prop",
+    "propagate",
+    "ChebyPropagator",
+    "NewtonPropagator",
+    "PWCPropagator",
+]
+
+_PROTECTED = ("generator",)  # hidden like in the reference (src/propagator.jl:80-84)
+
+
+def _get_uniform_dt(tlist, tol=1e-12, warn=False):
+    """reference ``src/propagator.jl:267-280``"""
+    dt = float(tlist[1] - tlist[0])
+    for i in range(1, len(tlist) - 1):
+        dt_i = float(tlist[i + 1] - tlist[i])
+        if abs(dt_i - dt) > tol:
+            if warn:
+                warnings.warn(
+                    f"Non-uniform time grid: dt = {dt_i:.2e} in interval {i + 1} differs from the first "
+                    f"dt={dt:.2e} by Δ = {abs(dt_i - dt):.2e} > tol = {tol:.2e}"
+                )
+            return None
+    return dt
+
+
+def _process_parameters(parameters, controls, tlist):
+    """reference ``src/pwc_utils.jl:29-45``: control -> nt-1 midpoint values."""
+    if parameters is None:
+        return IdDict((c, discretize_on_midpoints(c, tlist)) for c in controls)
+    for c in controls:
+        amplitude = parameters[c]
+        if len(amplitude) != len(tlist) - 1:
+            raise AssertionError("parameters must hold one value per interval of tlist")
+    return parameters
+
+
+def _max_genop(generator, controls, tlist):
+    """reference ``src/pwc_utils.jl:74-83``"""
+    vals = IdDict((c, float(np.max(discretize(c, tlist)))) for c in controls)
+    return evaluate(generator, tlist, len(tlist) // 2, vals_dict=vals)
+
+
+def cheby_get_spectral_envelope(generator, tlist, control_ranges, method, ctx=None, **kwargs):
+    """Spectral range of the generator over all control values within ``control_ranges``:
+    union of the ranges at the all-minimum and all-maximum amplitudes (reference
+    ``src/cheby_propagator.jl:331-345``)."""
+    n = len(tlist) // 2
+    G_min = evaluate(generator, tlist, n, vals_dict=IdDict((c, r[0]) for c, r in control_ranges.items()))
+    G_max = evaluate(generator, tlist, n, vals_dict=IdDict((c, r[1]) for c, r in control_ranges.items()))
+    E_min, E_max = specrange(G_max, method, ctx=ctx, **kwargs)
+    lo, hi = specrange(G_min, method, ctx=ctx, **kwargs)
+    return min(lo, E_min), max(hi, E_max)
+
+
+class PWCPropagator:
+    """Common state of the piecewise-constant propagators (reference
+    ``src/propagator.jl:48-126``): public properties ``state, tlist, t, parameters, backward,
+    inplace``; ``generator`` is hidden."""
+
+    def __getattribute__(self, name):
+        if name in _PROTECTED:
+            raise AttributeError(f"`{name}` is a private field of the propagator")
+        return object.__getattribute__(self, name)
+
+    def propertynames(self):
+        return ("state", "tlist", "t", "parameters", "backward", "inplace")
+
+    # -- src/pwc_utils.jl -----------------------------------------------------------------
+    def _generator(self):
+        return object.__getattribute__(self, "generator")
+
+    def _coeffs_for(self, n):
+        """``_pwc_set_genop!`` (reference ``src/pwc_utils.jl:86-92``): evaluate the generator on
+        interval n with the *current* ``parameters`` (the caller may mutate them between steps)."""
+        vals = IdDict((c, self.parameters[c][n - 1]) for c in self.controls)
+        gen = self._generator()
+        if isinstance(gen, Generator):
+            evaluate_(self.genop, gen, self.tlist, n, vals_dict=vals)
+        return self.genop
+
+    def _advance_time(self):
+        """reference ``src/pwc_utils.jl:102-112``"""
+        n = self.n
+        if self.backward:
+            object.__setattr__(self, "t", float(self.tlist[n - 1]))
+            object.__setattr__(self, "n", n - 1)
+        else:
+            object.__setattr__(self, "t", float(self.tlist[n]))
+            object.__setattr__(self, "n", n + 1)
+
+    def _set_t(self, t):
+        """reference ``src/pwc_utils.jl:48-71``"""
+        tlist = self.tlist
+        N = len(tlist)
+        if t <= tlist[0]:
+            n = 1
+        elif t >= tlist[-1]:
+            n = N
+        else:
+            n = min(int(np.searchsorted(tlist, t, side="left")) + 1, N)
+        snapped = float(tlist[n - 1])
+        if abs(t - snapped) > 1.4901161193847656e-08 * max(abs(t), abs(snapped)):
+            warnings.warn(f"Snapping t={t} to time grid value {snapped}")
+        object.__setattr__(self, "n", n - 1 if self.backward else n)
+        object.__setattr__(self, "t", snapped)
+
+
+class ChebyPropagator(PWCPropagator):
+    """reference ``src/cheby_propagator.jl:9-27``"""
+
+
+class NewtonPropagator(PWCPropagator):
+    """reference ``src/newton_propagator.jl:9-26``"""
+
+
+def _method_name(method) -> str:
+    if isinstance(method, str):
+        return method.lstrip(":").lower()
+    name = getattr(method, "__name__", None)  # a module / class named Cheby or Newton
+    if name:
+        return name.rsplit(".", 1)[-1].lower()
+    raise ValueError(f"Unknown propagation `method`: {method!r}")
+
+
+def _as_device_state(state, ctx):
+    if isinstance(state, DeviceState):
+        return state, False
+    ctx = default_context() if ctx is None else ctx
+    return DeviceState.from_host(ctx, np.asarray(state)), True
+
+
+def init_prop(
+    state,
+    generator,
+    tlist,
+    method,
+    backward=False,
+    inplace=True,
+    verbose=False,
+    piecewise=None,
+    pwc=None,
+    parameters=None,
+    ctx: Context = None,
+    matrix_format="auto",
+    **kwargs,
+):
+    """``init_prop(state, generator, tlist; method, ...)`` (reference ``src/propagator.jl:208-264``,
+    ``src/cheby_propagator.jl:87-175``, ``src/newton_propagator.jl:62-113``).
+
+    ``state`` is a DeviceState or a NumPy vector / (N, B) batch (uploaded once); with
+    ``inplace=True`` the propagator works on its own copy, as the reference does.
+    Cheby keywords: control_ranges, specrange_method, specrange_buffer, cheby_coeffs_limit,
+    check_normalization, uniform_dt_tolerance + specrange kwargs (E_min, E_max, rng, ...).
+    Newton keywords: m_max, func, norm_min, relerr, max_restarts.
+    Engine keyword: matrix_format in {"auto", "csr", "sell"} (device storage of the operators).
+    """
+    name = _method_name(method)
+    if name not in ("cheby", "newton"):
+        raise ValueError(f"Unknown propagation `method`: {method}")
+    tlist = np.array(tlist, dtype=np.float64)
+    generator = canonical(generator)
+    controls = get_controls(generator)
+    dev_state, uploaded = _as_device_state(state, ctx)
+    ctx = dev_state.ctx
+    G = _max_genop(generator, controls, tlist)
+    if not isinstance(G, Operator):
+        G = _as_operator(G)  # static generator: one drift term, no coefficients
+
+    if name == "cheby":
+        p = ChebyPropagator()
+        control_ranges = kwargs.pop("control_ranges", None)
+        p.specrange_method = kwargs.pop("specrange_method", "auto")
+        p.specrange_buffer = kwargs.pop("specrange_buffer", 0.01)
+        limit = kwargs.pop("cheby_coeffs_limit", 1e-12)
+        p.check_normalization = kwargs.pop("check_normalization", False)
+        uniform_dt_tolerance = kwargs.pop("uniform_dt_tolerance", 1e-12)
+        p.specrange_options = dict(kwargs)
+        parameters = _process_parameters(parameters, controls, tlist)
+        if control_ranges is None:
+            control_ranges = IdDict()
+            for c in controls:
+                vals = discretize(c, tlist)
+                control_ranges[c] = (float(np.min(vals)), float(np.max(vals)))
+        else:
+            for c in controls:
+                if c not in control_ranges or not control_ranges[c][0] <= control_ranges[c][1]:
+                    raise AssertionError("control_ranges must map every control to (min, max)")
+        E_min, E_max = cheby_get_spectral_envelope(
+            generator, tlist, control_ranges, p.specrange_method, ctx=ctx, **p.specrange_options
+        )
+        Delta = E_max - E_min
+        if not Delta > 0.0:
+            raise AssertionError("spectral range must be positive")
+        delta = p.specrange_buffer * Delta
+        E_min -= delta / 2
+        Delta += delta
+        dt = _get_uniform_dt(tlist, tol=uniform_dt_tolerance, warn=True)
+        if dt is None:
+            raise RuntimeError("Chebychev propagation only works on a uniform time grid")
+        p.control_ranges = control_ranges
+        p.wrk = ChebyWrk(dev_state, G.to_device(ctx, matrix_format), Delta, E_min, dt, limit=limit)
+    else:
+        if not inplace:
+            raise RuntimeError("The Newton propagator is only implemented in-place")
+        p = NewtonPropagator()
+        parameters = _process_parameters(parameters, controls, tlist)
+        p.wrk = NewtonWrk(dev_state, G.to_device(ctx, matrix_format), m_max=kwargs.get("m_max", 10))
+        p.func = kwargs.get("func", None)
+        p.norm_min = kwargs.get("norm_min", 1e-14)
+        p.relerr = kwargs.get("relerr", 1e-12)
+        p.max_restarts = kwargs.get("max_restarts", 50)
+
+    object.__setattr__(p, "generator", generator)
+    # the reference copies the caller's state when in-place (src/cheby_propagator.jl:158);
+    # a state we just uploaded from the host is already private
+    p.state = dev_state.copy() if (inplace and not uploaded) else dev_state
+    p.tlist = tlist
+    p.parameters = parameters
+    p.controls = controls
+    p.genop = G
+    p.backward = bool(backward)
+    p.inplace = bool(inplace)
+    p.ctx = ctx
+    p.n = len(tlist) - 1 if backward else 1
+    p.t = float(tlist[-1]) if backward else float(tlist[0])
+    p._host_io = uploaded
+    if piecewise is True or pwc is True:
+        pass  # both methods are piecewise-constant propagators
+    return p
+
+
+def prop_step(p):
+    """``prop_step!(propagator)`` (reference ``src/cheby_propagator.jl:348-386``,
+    ``src/newton_propagator.jl:120-153``): one ``qp_cheby_step`` / one Newton restart loop.
+    Returns ``propagator.state``, or ``None`` once the time grid is exhausted."""
+    n = p.n
+    tlist = p.tlist
+    if not (0 < n < len(tlist)):
+        return None
+    H = p._coeffs_for(n)
+    if isinstance(p, ChebyPropagator):
+        dt = -p.wrk.dt if p.backward else p.wrk.dt
+        if p.inplace:
+            cheby_(p.state, H, dt, p.wrk, check_normalization=p.check_normalization)
+        else:
+            p.state = cheby_(p.state.copy(), H, dt, p.wrk, check_normalization=p.check_normalization)
+    else:
+        dt = float(tlist[n] - tlist[n - 1])
+        if p.backward:
+            dt = -dt
+        newton_(p.state, H, dt, p.wrk, func=p.func, norm_min=p.norm_min, relerr=p.relerr, max_restarts=p.max_restarts)
+    p._advance_time()
+    return p.state
+
+
+def set_state(p, state):
+    """``set_state!(propagator, state)`` (reference ``src/propagator.jl:367-377``)."""
+    if state is not p.state:
+        if p.inplace:
+            p.state.copyto(state)
+        else:
+            p.state = state if isinstance(state, DeviceState) else DeviceState.from_host(p.ctx, state)
+    return p.state
+
+
+def set_t(p, t):
+    """``set_t!(propagator, t)`` (reference ``src/cheby_propagator.jl:30`` -> ``_pwc_set_t!``)."""
+    p._set_t(float(t))
+
+
+def reinit_prop(p, state, transform_control_ranges=None, **_):
+    """``reinit_prop!(propagator, state; transform_control_ranges)`` (reference
+    ``src/cheby_propagator.jl:243-299``; default ``src/propagator.jl:298-312``).  For Cheby the
+    coefficients are recomputed -- and re-uploaded without touching the operators -- only when
+    the current amplitudes left the control ranges they were derived for."""
+    state = set_state(p, state)
+    tlist = p.tlist
+    if isinstance(p, ChebyPropagator):
+        transform = transform_control_ranges or (lambda c, lo, hi, check: (lo, hi))
+        current = IdDict(
+            (c, (float(np.min(p.parameters[c])), float(np.max(p.parameters[c])))) for c in p.controls
+        )
+        recalc = False
+        for c in p.controls:
+            lo, hi = transform(c, current[c][0], current[c][1], True)
+            if lo < p.control_ranges[c][0] or hi > p.control_ranges[c][1]:
+                recalc = True
+                break
+        if recalc:
+            for c in p.controls:
+                current[c] = transform(c, current[c][0], current[c][1], False)
+            E_min, E_max = cheby_get_spectral_envelope(
+                p._generator(), tlist, current, p.specrange_method, ctx=p.ctx, **p.specrange_options
+            )
+            Delta = E_max - E_min
+            if not Delta > 0.0:
+                raise AssertionError("spectral range must be positive")
+            delta = p.specrange_buffer * Delta
+            p.control_ranges = current
+            p.wrk.set_spectral_range(Delta + delta, E_min - delta / 2, float(tlist[1] - tlist[0]))
+    p.ctx.reset_timings()
+    p._set_t(float(tlist[-1] if p.backward else tlist[0]))
+
+
+def _observe(observables, state: DeviceState):
+    """Default observable: the state itself (downloaded copy); otherwise a tuple of callables
+    on the DeviceState (reference ``src/storage.jl:67-80``)."""
+    if observables is None:
+        return state.to_host()
+    return np.array([obs(state) for obs in observables])
+
+
+def propagate(
+    state,
+    generator=None,
+    tlist=None,
+    method=None,
+    storage=None,
+    observables=None,
+    callback=None,
+    show_progress=False,
+    **kwargs,
+):
+    """``propagate(state, generator, tlist; method, storage, observables, callback, ...)``
+    (reference ``src/propagate.jl:167-235, 283-344``), also ``propagate(propagator; ...)`` when
+    the first argument is an initialised propagator.
+
+    Returns the final state (a NumPy array if the initial state was one, else the
+    DeviceState), or the storage array when ``storage=True``.  With ``storage`` given, column i
+    holds the observables at ``tlist[i]`` (filled back to front when propagating backward)."""
+    if isinstance(state, PWCPropagator):
+        p = state
+    else:
+        p = init_prop(state, generator, tlist, method, **kwargs)
+    tlist = p.tlist
+    nt = len(tlist)
+    return_storage = storage is True
+    if storage is True:
+        first = _observe(observables, p.state)
+        storage = np.zeros(first.shape + (nt,), dtype=first.dtype)
+    if storage is not None:
+        storage[..., nt - 1 if p.backward else 0] = _observe(observables, p.state)
+    intervals = range(nt - 1, 0, -1) if p.backward else range(1, nt)
+    for i in intervals:
+        prop_step(p)
+        if callback is not None:
+            callback(p, observables)
+        if storage is not None:
+            storage[..., (i - 1) if p.backward else i] = _observe(observables, p.state)
+    if return_storage:
+        return storage
+    return p.state.to_host() if p._host_io else p.state

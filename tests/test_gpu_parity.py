@@ -1,0 +1,548 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance (north_star): relative ‖ψ_gpu − ψ_ref‖ ≤ 1e-10 after the full time
+grid; norm conservation 1e-12 per step for Hermitian generators.
+"""
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+import oracle as O
+from oracle.controls import IdDict as OIdDict
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+def rand_state(rng, n, B=None):
+    shape = (n,) if B is None else (n, B)
+    psi = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    return psi / np.linalg.norm(psi, axis=0)
+
+
+def rand_sparse(rng, n, density, hermitian=True):
+    A = sp.random(n, n, density=density, random_state=np.random.RandomState(rng.integers(1 << 30)), format="csr")
+    A = A + 1j * sp.random(n, n, density=density, random_state=np.random.RandomState(rng.integers(1 << 30)), format="csr")
+    if hermitian:
+        A = (A + A.conj().T) * 0.5
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+# ---------------------------------------------------------------------------------------
+# level-1 verbs (src/interfaces/state.jl:24-47)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,B", [(1, 1), (7, 1), (1000, 1), (4097, 1), (257, 3), (64, 40), (1 << 16, 1)])
+def test_state_verbs(qp, ctx, n, B):
+    rng = np.random.default_rng(n * 31 + B)
+    x = rand_state(rng, n, None if B == 1 else B)
+    y = rand_state(rng, n, None if B == 1 else B)
+    dx, dy = qp.DeviceState.from_host(ctx, x), qp.DeviceState.from_host(ctx, y)
+    np.testing.assert_array_equal(dx.to_host(), x)
+    assert np.allclose(dx.norm(), np.linalg.norm(x, axis=0), rtol=1e-14)
+    ref_dot = np.vdot(x, y) if B == 1 else np.einsum("ib,ib->b", x.conj(), y)
+    assert np.allclose(dx.dot(dy), ref_dot, rtol=1e-12, atol=1e-15)
+    a = 0.3 - 1.7j
+    dy.axpy(a, dx)
+    assert rel(dy.to_host(), y + a * x) < 1e-15
+    dx.lmul(a)
+    assert rel(dx.to_host(), a * x) < 1e-15
+    z = dx.zero()
+    assert np.all(z.to_host() == 0)
+    c = dx.copy()
+    assert c is not dx and np.array_equal(c.to_host(), dx.to_host())
+    s = (dx + dy) - dy
+    assert rel(s.to_host(), dx.to_host()) < 1e-14
+    dx.fill(2.0 + 1j)
+    assert np.all(dx.to_host() == 2.0 + 1j)
+    if B > 1:  # partial column transfer
+        sub = dy.download(1, B - 1)
+        np.testing.assert_array_equal(sub, dy.to_host()[:, 1:])
+
+
+# ---------------------------------------------------------------------------------------
+# the multi-operator mul! and 3-arg dot (test/test_operator_linalg.jl:30-64)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fmt", ["csr", "sell"])
+@pytest.mark.parametrize("layout", ["csr", "csc"])
+@pytest.mark.parametrize("n,density", [(5, 0.6), (100, 0.1), (1000, 0.01), (777, 0.2)])
+def test_operator_mul(qp, ctx, fmt, layout, n, density):
+    rng = np.random.default_rng(n)
+    H0 = rand_sparse(rng, n, density, hermitian=False)
+    H1 = rand_sparse(rng, n, density, hermitian=True)
+    H2 = sp.diags(rng.standard_normal(n) + 0j, 0, format="csr")
+    ops = [H0, H1, H2]
+    if layout == "csc":
+        ops = [A.tocsc() for A in ops]
+    coeffs = [0.7 - 0.2j, -1.3]
+    gen = qp.DeviceGenerator(ctx, ops, 2, fmt)
+    assert gen.format == fmt
+    dense = H0.toarray() + coeffs[0] * H1.toarray() + coeffs[1] * H2.toarray()
+    x = rand_state(rng, n)
+    y0 = rand_state(rng, n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    for alpha in (1.0, 2.0, 0.5 - 1j):
+        for beta in (0.0, 1.0, 2.0):
+            dy = qp.DeviceState.from_host(ctx, y0)
+            gen.mul(dy, dx, coeffs, alpha, beta)
+            assert rel(dy.to_host(), beta * y0 + alpha * (dense @ x)) < 1e-12
+    # beta == 0 must not read y (NaN-safe like BLAS)
+    dy = qp.DeviceState.from_host(ctx, np.full(n, np.nan + 0j))
+    gen.mul(dy, dx, coeffs, 1.0, 0.0)
+    assert rel(dy.to_host(), dense @ x) < 1e-12
+    dy0 = qp.DeviceState.from_host(ctx, y0)
+    assert abs(gen.dot(dy0, dx, coeffs) - np.vdot(y0, dense @ x)) < 1e-12 * n
+
+
+def test_operator_mul_batched(qp, ctx):
+    rng = np.random.default_rng(5)
+    n, B = 300, 6
+    H0 = rand_sparse(rng, n, 0.05)
+    H1 = rand_sparse(rng, n, 0.05)
+    gen = qp.DeviceGenerator(ctx, [H0, H1], 1)
+    X = rand_state(rng, n, B)
+    Y = rand_state(rng, n, B)
+    dx, dy = qp.DeviceState.from_host(ctx, X), qp.DeviceState.from_host(ctx, Y)
+    gen.mul(dy, dx, [0.4j], 2.0, -1.0)
+    dense = H0.toarray() + 0.4j * H1.toarray()
+    assert rel(dy.to_host(), -Y + 2.0 * dense @ X) < 1e-12
+
+
+def test_host_operator_verbs(qp, ctx):
+    """Operator / ScaledOperator objects on DeviceStates (src/generators.jl:634-708)."""
+    rng = np.random.default_rng(9)
+    n = 64
+    H0, H1 = rand_sparse(rng, n, 0.2), rand_sparse(rng, n, 0.2)
+    op = qp.Operator([H0, H1], [0.5])
+    x = rand_state(rng, n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    dense = H0.toarray() + 0.5 * H1.toarray()
+    assert rel((op @ dx).to_host(), dense @ x) < 1e-12
+    sop = 2.0j * op
+    assert isinstance(sop, qp.ScaledOperator)
+    assert rel((sop @ dx).to_host(), 2.0j * dense @ x) < 1e-12
+    assert abs(sop.dot(dx, dx) - 2.0j * np.vdot(x, dense @ x)) < 1e-12
+    assert (1.0 * op) is op
+
+
+# ---------------------------------------------------------------------------------------
+# Chebyshev
+# ---------------------------------------------------------------------------------------
+
+
+def _oracle_generator(ops, controls):
+    terms = [ops[0]] + [(op, c) for op, c in zip(ops[1:], controls)]
+    return O.hamiltonian(*terms)
+
+
+def _product_generator(qp, ops, controls):
+    terms = [ops[0]] + [(op, c) for op, c in zip(ops[1:], controls)]
+    return qp.hamiltonian(*terms)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "sell"])
+@pytest.mark.parametrize("backward", [False, True])
+def test_cheby_config1_vs_oracle(qp, ctx, fmt, backward):
+    """BASELINE config 1 shape (random sparse Hermitian + 1 control), reduced to N=300 / 60
+    steps so the oracle finishes in seconds; manual spectral range so both sides use the same
+    coefficient table."""
+    w = qp.workloads.config1_random(N=300, density=0.1, nt=61, T=1.2, seed=11)
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"], backward=backward)
+    ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "cheby", **kw)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, matrix_format=fmt, **kw)
+    assert p.wrk.gen.format == fmt
+    out = qp.propagate(p)
+    assert rel(out, ref) < RTOL
+    assert abs(np.linalg.norm(out) - 1) < 1e-11
+
+
+def test_cheby_single_step_norm_and_coeff_count(qp, ctx):
+    w = qp.workloads.config1_random(N=1000, density=0.1, seed=1000)
+    p = qp.init_prop(w["psi0"], _product_generator(qp, w["ops"], w["controls"]), w["tlist"], "cheby",
+                     ctx=ctx, E_min=w["E_min"], E_max=w["E_max"])
+    # test/test_specrad.jl:187-191: manual E=±10 -> E_min = -10.1, Δ = 20.2; n_coeffs = 9
+    assert abs(p.wrk.E_min + 10.1) < 1e-12 and abs(p.wrk.Delta - 20.2) < 1e-12
+    assert p.wrk.n_coeffs == 9
+    for _ in range(5):
+        st = qp.prop_step(p)
+        assert st is p.state
+        assert abs(st.norm() - 1.0) < 1e-12
+
+
+def test_cheby_tls_analytic(qp, ctx):
+    """test/test_propagate.jl:74-150: Rabi 3π/2 pulse, forward and back, 1e-12."""
+    H = np.array([[0, 0.5], [0.5, 0]], dtype=complex)
+    tlist = np.linspace(0, 1.5 * np.pi, 101)
+    psi0 = np.array([1, 0], dtype=complex)
+    out = qp.propagate(psi0, (H,), tlist, "cheby", ctx=ctx, inplace=False)
+    expected = np.array([-1 / np.sqrt(2), -1j / np.sqrt(2)])
+    assert np.linalg.norm(out - expected) < 1e-12
+    back = qp.propagate(out, (H,), tlist, "cheby", ctx=ctx, inplace=False, backward=True)
+    assert np.linalg.norm(back - psi0) < 1e-12
+
+
+@pytest.mark.parametrize("n_spins", [6, 10, 14])
+def test_cheby_tfim_vs_oracle_and_expm(qp, ctx, n_spins):
+    """BASELINE config 2 shape at reduced size: H0 + u1 ΣX + u2 ΣZ, both storage formats."""
+    from scipy.sparse.linalg import expm_multiply
+
+    w = qp.workloads.config2_tfim(n_spins, nt=11, dt=0.1)
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"])
+    ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "cheby", **kw)
+    for fmt in ("csr", "sell"):
+        gen = _product_generator(qp, w["ops"], w["controls"])
+        p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, matrix_format=fmt, **kw)
+        assert p.wrk.gen.format == fmt
+        out = qp.propagate(p)
+        assert rel(out, ref) < RTOL, fmt
+    # independent ground truth: exact PWC propagation with expm_multiply
+    psi = w["psi0"].copy()
+    tl = w["tlist"]
+    mids = O.get_tlist_midpoints(tl)
+    for k in range(len(tl) - 1):
+        Hk = w["ops"][0] + w["controls"][0](mids[k]) * w["ops"][1] + w["controls"][1](mids[k]) * w["ops"][2]
+        psi = expm_multiply(-1j * (tl[k + 1] - tl[k]) * Hk.tocsc(), psi)
+    assert rel(out, psi) < 1e-9
+
+
+def test_cheby_batched_per_trajectory(qp, ctx):
+    """Ensemble: B trajectories with their own control scale share one coefficient table."""
+    rng = np.random.default_rng(3)
+    w = qp.workloads.config3_transmon(n_sites=3, levels=3, B=5, nt=9, dt=0.5)
+    H0, H1, H2 = w["ops"]
+    B = 5
+    tl = w["tlist"]
+    dt = tl[1] - tl[0]
+    psi0 = rand_state(rng, H0.shape[0], B)
+    scales = w["scales"]
+    # common spectral envelope (Gershgorin bound over the whole ensemble)
+    bound = float((abs(H0) + 0.1 * abs(H1) + 0.1 * abs(H2)).sum(axis=1).max())
+    Delta, E_min = 2 * bound, -bound
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    st = qp.DeviceState.from_host(ctx, psi0)
+    wrk = qp.ChebyWrk(st, gen, Delta, E_min, dt)
+    mids = O.get_tlist_midpoints(tl)
+    ref = psi0.copy()
+    owrk = O.ChebyWrk(ref[:, 0].copy(), Delta, E_min, dt)
+    for k in range(len(tl) - 1):
+        u = np.array([[w["controls"][0](mids[k]) * s for s in scales], [w["controls"][1](mids[k]) * s for s in scales]])
+        qp.cheby_(st, None, dt, wrk, coeffs=u, per_trajectory=True)
+        for b in range(B):
+            Hb = O.Operator([H0, H1, H2], [u[0, b], u[1, b]])
+            col = ref[:, b].copy()
+            O.cheby_inplace(col, Hb, dt, owrk)
+            ref[:, b] = col
+    out = st.to_host()
+    for b in range(B):
+        assert rel(out[:, b], ref[:, b]) < RTOL
+
+
+def test_cheby_check_normalization_and_errors(qp, ctx):
+    rng = np.random.default_rng(4)
+    n = 200
+    H = rand_sparse(rng, n, 0.1)
+    ev = np.linalg.eigvalsh(H.toarray())
+    psi = rand_state(rng, n)
+    st = qp.DeviceState.from_host(ctx, psi)
+    gen = qp.DeviceGenerator(ctx, [H], 0)
+    good = qp.ChebyWrk(st, gen, (ev[-1] - ev[0]) * 1.01, ev[0] - 0.005 * (ev[-1] - ev[0]), 0.1)
+    qp.cheby_(st, None, 0.1, good, check_normalization=True, coeffs=[])
+    assert abs(st.norm() - 1) < 1e-12
+    # spectral radius underestimated by 3x: the reference asserts "Incorrect normalization"
+    bad = qp.ChebyWrk(st, gen, (ev[-1] - ev[0]) / 3, ev[0] / 3, 0.1)
+    with pytest.raises(qp.QPropError) as exc:
+        qp.cheby_(st, None, 0.1, bad, check_normalization=True, coeffs=[])
+    assert exc.value.status == -5 and "Incorrect normalization" in str(exc.value)
+    # wrong dt (src/cheby.jl:157)
+    with pytest.raises(qp.QPropError) as exc:
+        qp.cheby_(st, None, 0.2, good, coeffs=[])
+    assert exc.value.status == -1 and "initialized for dt" in str(exc.value)
+    # coefficient-count mismatch
+    with pytest.raises(ValueError):
+        qp.cheby_(st, None, 0.1, good, coeffs=[1.0])
+    # dimension mismatch
+    with pytest.raises(qp.QPropError):
+        qp.ChebyWrk(qp.DeviceState(ctx, n + 1), gen, 1.0, 0.0, 0.1)
+
+
+def test_cheby_dense_random_hermitian(qp, ctx):
+    """test/test_cheby.jl:6-49 at N=400: dense Hermitian, spectral range from eigvals, vs exp."""
+    rng = np.random.default_rng(6)
+    N = 400
+    X = rng.random((N, N)) + 1j * rng.random((N, N))
+    H = (X + X.conj().T) / 2
+    dt = 0.5
+    psi0 = rand_state(rng, N)
+    ev = np.linalg.eigvalsh(H)
+    expected = sla.expm(-1j * H * dt) @ psi0
+    st = qp.DeviceState.from_host(ctx, psi0)
+    gen = qp.DeviceGenerator(ctx, [H], 0)
+    assert gen.format == "dense"
+    wrk = qp.ChebyWrk(st, gen, ev[-1] - ev[0], ev[0], dt)
+    qp.cheby_(st, None, dt, wrk, coeffs=[])
+    assert np.linalg.norm(st.to_host() - expected) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------
+# Newton / Arnoldi / specrange
+# ---------------------------------------------------------------------------------------
+
+
+def test_arnoldi_matches_oracle(qp, ctx):
+    rng = np.random.default_rng(7)
+    n, m = 500, 12
+    A = rand_sparse(rng, n, 0.05, hermitian=False)
+    v = rand_state(rng, n)
+    Hess_ref = np.zeros((m + 1, m + 1), dtype=complex)
+    q = [np.empty(n, dtype=complex) for _ in range(m + 1)]
+    m_ref = O.arnoldi(Hess_ref, q, m, v, A, 0.3, extended=True)
+    st = qp.DeviceState.from_host(ctx, v)
+    K = qp.KrylovWrk(st, A, m)
+    Hess = np.zeros((m + 1, m + 1), dtype=complex)
+    m_gpu = qp.arnoldi_(Hess, K, m, st, A, 0.3, extended=True)
+    assert m_gpu == m_ref == m
+    assert np.linalg.norm(Hess - Hess_ref) < 1e-10 * np.linalg.norm(Hess_ref)
+    tmp = st.similar()
+    for i in range(m + 1):
+        assert rel(K.get(i, tmp).to_host(), q[i]) < 1e-9
+    # eigenvector start: Krylov dimension collapses to 1 (src/arnoldi.jl:91-95)
+    Hh = rand_sparse(rng, 50, 0.3)
+    w_, V = np.linalg.eigh(Hh.toarray())
+    st2 = qp.DeviceState.from_host(ctx, V[:, 3])
+    K2 = qp.KrylovWrk(st2, Hh, 5)
+    Hess2 = np.zeros((6, 6), dtype=complex)
+    assert qp.arnoldi_(Hess2, K2, 5, st2, Hh, 1.0, extended=True, norm_min=1e-10) == 1
+    assert abs(Hess2[0, 0] - w_[3]) < 1e-12
+
+
+def test_newton_optomech_vs_cheby_and_oracle(qp, ctx):
+    """test/test_propagate.jl:153-163: ‖Ψ_newton‖−1 < 1e-12, ‖Ψ_newton − Ψ_cheby‖ < 1e-10."""
+    H = qp.workloads.optomech()
+    psi0 = qp.workloads.optomech_ket(0, 2)
+    tlist = np.arange(0, 50 + 1e-9, 0.2)
+    p1 = qp.propagate(psi0, (H,), tlist, "newton", ctx=ctx)
+    p2 = qp.propagate(psi0, (H,), tlist, "cheby", ctx=ctx)
+    assert abs(np.linalg.norm(p1) - 1.0) < 1e-12
+    assert np.linalg.norm(p1 - p2) < 1e-10
+    ref = O.propagate(psi0, (H,), tlist, "newton")
+    assert rel(p1, ref) < RTOL
+
+
+@pytest.mark.parametrize("hermitian,m_max", [(True, 5), (False, 50)])
+def test_newton_random_vs_expm(qp, ctx, hermitian, m_max):
+    """test/test_newton.jl:7-127 at N=300: vs dense exp(-i H dt), 1e-10."""
+    rng = np.random.default_rng(8 + m_max)
+    N = 300
+    X = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    if hermitian:
+        X = (X + X.conj().T) / 2
+    X *= 10 / np.max(np.abs(np.linalg.eigvals(X)))
+    psi0 = rand_state(rng, N)
+    expected = sla.expm(-1j * X * 0.5) @ psi0
+    st = qp.DeviceState.from_host(ctx, psi0)
+    wrk = qp.NewtonWrk(st, X, m_max=m_max)
+    qp.newton_(st, X, 0.5, wrk, max_restarts=200, coeffs=[])
+    assert np.linalg.norm(st.to_host() - expected) < 1e-10
+    ref = psi0.copy()
+    O.newton_inplace(ref, X, 0.5, O.NewtonWrk(ref, m_max=m_max), max_restarts=200)
+    assert rel(st.to_host(), ref) < RTOL
+
+
+def test_newton_sparse_liouvillian_func_exp(qp, ctx):
+    """test/test_newton.jl:130-177: sparse non-Hermitian super-operator, func = exp(L dt)."""
+    rng = np.random.default_rng(12)
+    N = 16
+    Lm = rand_sparse(rng, N * N, 0.5, hermitian=False)
+    Lm = (Lm * (10 / np.max(np.abs(np.linalg.eigvals(Lm.toarray()))))).tocsr()
+    psi = rand_state(rng, N)
+    rho0 = np.outer(psi, psi.conj()).reshape(-1)
+    expected = sla.expm(Lm.toarray() * 0.5) @ rho0
+    st = qp.DeviceState.from_host(ctx, rho0)
+    wrk = qp.NewtonWrk(st, Lm, m_max=50)
+    qp.newton_(st, Lm, 0.5, wrk, func=np.exp, max_restarts=20, coeffs=[])
+    assert np.linalg.norm(st.to_host() - expected) < 1e-10
+
+
+def test_newton_config4_small_vs_oracle(qp, ctx):
+    """BASELINE config 4 shape at n_spins=4 (super-operator dimension 256), PWC control."""
+    w = qp.workloads.config4_liouvillian(n_spins=4, nt=6, dt=0.05)
+    ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "newton")
+    out = qp.propagate(w["psi0"], _product_generator(qp, w["ops"], w["controls"]), w["tlist"], "newton", ctx=ctx)
+    assert rel(out, ref) < RTOL
+    rho = out.reshape(16, 16, order="F")
+    assert abs(np.trace(rho) - 1) < 1e-10  # trace preserved by the Lindblad generator
+
+
+def test_newton_eigenstate_shortcut_and_max_restarts(qp, ctx):
+    rng = np.random.default_rng(13)
+    H = rand_sparse(rng, 40, 0.3)
+    w_, V = np.linalg.eigh(H.toarray())
+    st = qp.DeviceState.from_host(ctx, V[:, 0])
+    wrk = qp.NewtonWrk(st, H, m_max=5)
+    qp.newton_(st, H, 0.7, wrk, coeffs=[], norm_min=1e-10)
+    assert rel(st.to_host(), np.exp(-1j * w_[0] * 0.7) * V[:, 0]) < 1e-12
+    assert wrk.restarts == 0
+    big = rand_sparse(rng, 400, 0.2) * 200.0
+    st = qp.DeviceState.from_host(ctx, rand_state(rng, 400))
+    with pytest.raises(qp.QPropError) as exc:
+        qp.newton_(st, big, 1.0, qp.NewtonWrk(st, big, m_max=3), max_restarts=2, coeffs=[])
+    assert exc.value.status == -4
+    with pytest.raises(RuntimeError, match="only implemented in-place"):
+        qp.init_prop(V[:, 0], (H,), np.linspace(0, 1, 5), "newton", ctx=ctx, inplace=False)
+
+
+def test_specrange_arnoldi_brackets_spectrum(qp, ctx):
+    """test/test_specrad.jl:80-144: :arnoldi within 5% of Δ outside the true spectrum;
+    :diag exact; :manual / :auto dispatch."""
+    w = qp.workloads.config1_random(N=600, density=0.1, seed=77)
+    H = w["ops"][0]
+    ev = np.linalg.eigvalsh(H.toarray())
+    D = ev[-1] - ev[0]
+    E_min, E_max = qp.specrange(H, "arnoldi", ctx=ctx, prec=1e-4, rng=np.random.default_rng(1))
+    assert ev[0] - 0.05 * D <= E_min <= ev[0]
+    assert ev[-1] <= E_max < ev[-1] + 0.05 * D
+    lo, hi = qp.specrange(H, "diag")
+    assert abs(lo - ev[0]) < 1e-12 and abs(hi - ev[-1]) < 1e-12
+    assert qp.specrange(H, E_min=-10, E_max=10) == (-10.0, 10.0)
+    with pytest.raises(TypeError):
+        qp.specrange(H, "manual", E_min=-1.0)
+    # same start vector -> same Ritz values as the oracle
+    psi = O.random_state(H, rng=np.random.default_rng(5))
+    R_ref = O.ritzvals(H, psi, 25, 60, prec=1e-3)
+    R = qp.ritzvals(H, psi, 25, 60, prec=1e-3, ctx=ctx)
+    assert len(R) == len(R_ref)
+    assert abs(R[0] - R_ref[0]) < 1e-8 and abs(R[-1] - R_ref[-1]) < 1e-8
+
+
+def test_init_prop_spectral_arithmetic(qp, ctx):
+    """test/test_specrad.jl:147-223."""
+    w = qp.workloads.config1_random(N=200, density=0.1, seed=5, nt=21, T=1.0)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, E_min=-10, E_max=10,
+                     specrange_method="manual", specrange_buffer=0.1)
+    assert abs(p.wrk.E_min + 11.0) < 1e-12 and abs(p.wrk.Delta - 22.0) < 1e-12
+    u = w["controls"][0]
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, specrange_method="diag",
+                     specrange_buffer=0.0, control_ranges=qp.IdDict([(u, (-1, 1))]))
+    H0, H1 = w["ops"]
+    ev_m, ev_p = np.linalg.eigvalsh((H0 - H1).toarray()), np.linalg.eigvalsh((H0 + H1).toarray())
+    assert abs(p.wrk.E_min - min(ev_m[0], ev_p[0])) < 1e-10
+    assert abs(p.wrk.Delta - (max(ev_m[-1], ev_p[-1]) - p.wrk.E_min)) < 1e-10
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, rng=np.random.default_rng(0))  # :arnoldi
+    ev = [np.linalg.eigvalsh((H0 + s * H1).toarray()) for s in (-1, 1)]
+    assert p.wrk.E_min <= min(e[0] for e in ev) and p.wrk.E_min + p.wrk.Delta >= max(e[-1] for e in ev)
+
+
+# ---------------------------------------------------------------------------------------
+# the propagator protocol (src/interfaces/propagator.jl:55-338, test/test_prop_interfaces.jl)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("method", ["cheby", "newton"])
+@pytest.mark.parametrize("backward", [False, True])
+def test_propagator_protocol(qp, ctx, method, backward):
+    w = qp.workloads.config1_random(N=10, density=0.5, seed=21, nt=101, T=5.0)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"]) if method == "cheby" else {}
+    st0 = qp.DeviceState.from_host(ctx, w["psi0"])
+    p = qp.init_prop(st0, gen, w["tlist"], method, ctx=ctx, backward=backward, **kw)
+    tl = w["tlist"]
+    assert p.state is not st0  # in-place propagators work on a copy
+    assert p.t == (tl[-1] if backward else tl[0])
+    assert set(p.propertynames()) == {"state", "tlist", "t", "parameters", "backward", "inplace"}
+    with pytest.raises(AttributeError):
+        p.generator
+    s1 = qp.prop_step(p)
+    assert s1 is p.state
+    assert p.t == (tl[-2] if backward else tl[1])
+    assert abs(s1.norm() - 1) < 1e-12
+    # parameters: control -> nt-1 values, mutable between steps
+    u = w["controls"][0]
+    assert len(p.parameters[u]) == len(tl) - 1
+    # set_t! to the end: prop_step! returns nothing and leaves the propagator untouched
+    qp.set_t(p, tl[0] if backward else tl[-1])
+    before = p.state.to_host()
+    assert qp.prop_step(p) is None
+    assert np.array_equal(p.state.to_host(), before)
+    # set_state! overwrites in place and returns the same object
+    other = qp.DeviceState.from_host(ctx, np.roll(w["psi0"], 1))
+    held = p.state
+    assert qp.set_state(p, other) is held
+    assert np.array_equal(held.to_host(), other.to_host())
+    # reinit_prop! is idempotent
+    qp.reinit_prop(p, st0)
+    t0 = p.t
+    a = qp.prop_step(p).to_host()
+    qp.reinit_prop(p, st0)
+    assert p.t == t0
+    b = qp.prop_step(p).to_host()
+    assert np.array_equal(a, b)
+    with pytest.warns(UserWarning, match="Snapping"):
+        qp.set_t(p, 0.5 * (tl[3] + tl[4]) + 1e-3)
+
+
+def test_propagate_storage_and_parameters_mutation(qp, ctx):
+    w = qp.workloads.config1_random(N=50, density=0.2, seed=31, nt=21, T=1.0)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    ogen = _oracle_generator(w["ops"], w["controls"])
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"])
+    pops = [lambda s: float(abs(s.to_host()[0]) ** 2), lambda s: s.norm()]
+    store = qp.propagate(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, storage=True, observables=pops, **kw)
+    ref = O.propagate(w["psi0"], ogen, w["tlist"], "cheby", storage=True,
+                      observables=[lambda s: float(abs(s[0]) ** 2), lambda s: np.linalg.norm(s)], **kw)
+    assert store.shape == (2, 21) and np.allclose(store, ref, atol=1e-11)
+    full = qp.propagate(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, storage=True, **kw)
+    full_bw = qp.propagate(full[:, -1], gen, w["tlist"], "cheby", ctx=ctx, storage=True, backward=True, **kw)
+    assert np.linalg.norm(full - full_bw) < 1e-10  # stored back to front, same trajectory
+    # the caller may rewrite propagator.parameters between steps (src/propagator.jl:100-104)
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, control_ranges=qp.IdDict([(w["controls"][0], (-1, 1))]), **kw)
+    po = O.init_prop(w["psi0"], ogen, w["tlist"], "cheby", control_ranges=OIdDict([(w["controls"][0], (-1, 1))]), **kw)
+    u = w["controls"][0]
+    p.parameters[u][:] = 0.25
+    po.parameters[u][:] = 0.25
+    for _ in range(5):
+        qp.prop_step(p)
+        O.prop_step(po)
+    assert rel(p.state.to_host(), po.state) < RTOL
+
+
+def test_reinit_prop_recomputes_coefficients(qp, ctx):
+    """src/cheby_propagator.jl:243-299: larger amplitudes than the stored ranges -> new
+    coefficients, re-uploaded without touching the operators."""
+    w = qp.workloads.config1_random(N=80, density=0.2, seed=41, nt=11, T=1.0)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, specrange_method="diag")
+    n0, dev0 = p.wrk.n_coeffs, p.wrk.gen
+    u = w["controls"][0]
+    p.parameters[u] *= 5.0
+    qp.reinit_prop(p, p.state)
+    assert p.wrk.gen is dev0 and p.wrk.n_coeffs > n0
+    ogen = _oracle_generator(w["ops"], [5.0 * qp.discretize_on_midpoints(u, w["tlist"])])
+    ref = O.propagate(w["psi0"], ogen, w["tlist"], "cheby", specrange_method="diag")
+    for _ in range(10):
+        qp.prop_step(p)
+    assert rel(p.state.to_host(), ref) < 1e-9  # different (both valid) spectral envelopes
+
+
+def test_timings_labels(qp):
+    """test/test_timings.jl:8-39: > 200 "matrix-vector product" calls for 100 steps."""
+    c = qp.Context(0)
+    c.enable_timings()
+    w = qp.workloads.config1_random(N=100, density=0.2, seed=51, nt=101, T=5.0)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    qp.propagate(w["psi0"], gen, w["tlist"], "cheby", ctx=c, E_min=w["E_min"], E_max=w["E_max"])
+    n_step, t_step = c.timing("prop_step!")
+    n_mv, t_mv = c.timing("matrix-vector product")
+    assert n_step == 100 and n_mv > 200 and 0 < t_mv <= t_step
