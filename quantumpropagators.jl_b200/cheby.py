@@ -13,7 +13,7 @@ from scipy.special import jv
 
 from . import _lib as L
 from .device import DeviceGenerator, DeviceState
-from .generators import Operator, ScaledOperator, _as_operator
+from .generators import Generator, Operator, ScaledOperator, _as_operator
 
 __all__ = ["cheby_coeffs", "cheby_coeffs_", "ChebyWrk", "cheby_", "cheby"]
 
@@ -92,7 +92,7 @@ def _device_generator(H, ctx) -> DeviceGenerator:
         return H
     if isinstance(H, ScaledOperator):
         raise TypeError("Chebyshev propagation of a ScaledOperator is not supported; scale the coefficients")
-    if hasattr(H, "to_device"):
+    if isinstance(H, (Operator, Generator)):  # (not duck-typed: ndarray has its own to_device)
         return H.to_device(ctx)
     return _as_operator(H).to_device(ctx)
 
