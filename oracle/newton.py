@@ -181,8 +181,9 @@ def newton_inplace(
 
         # starting vector for the next restart :356-367
         R = (Hm @ R - wrk.leja[n_s + m - 1] * R) / wrk.radius
-        beta = float(np.linalg.norm(np.abs(R)))
-        R *= 1 / beta
+        beta = np.float64(np.linalg.norm(np.abs(R)))
+        with np.errstate(all="ignore"):  # Julia: 1/0.0 == Inf (exhausted Krylov space), no exception
+            R *= 1 / beta
         wrk.arnoldi_vecs[0][...] = wrk.v
         wrk.v *= R[0]
         for i in range(1, m + 1):

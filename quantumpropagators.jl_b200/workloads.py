@@ -79,8 +79,10 @@ def tfim_chain(n_spins, J=1.0, dtype=np.complex128):
     d2 = np.zeros(N)
     for i in range(n_spins):
         d2 += z[i]
-    H0 = sp.diags(d0.astype(dtype), 0, format="csr")
-    H2 = sp.diags(d2.astype(dtype), 0, format="csr")
+    # diagonal operators store all N entries (nnz = N), including exact zeros
+    ptr = np.arange(N + 1, dtype=np.int64)
+    H0 = sp.csr_matrix((d0.astype(dtype), idx.copy(), ptr), shape=(N, N))
+    H2 = sp.csr_matrix((d2.astype(dtype), idx.copy(), ptr.copy()), shape=(N, N))
     # H1: row r has columns r ^ (1<<i); build CSR directly with sorted columns
     cols = np.empty((N, n_spins), dtype=np.int64)
     for i in range(n_spins):

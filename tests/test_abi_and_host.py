@@ -1,0 +1,203 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports every
+symbol include/qprop.h declares (no compute calls without a GPU), compute calls fail loudly
+without a device, and the host-side mirror (controls, generators, coefficient / Leja tables)
+agrees with the oracle."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+import qprop_b200 as qp
+from qprop_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "qprop.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    names = _header_functions()
+    assert len(names) >= 40
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), f"libqprop_b200.so does not export {name}"
+    # the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.load().qp_version() == 100
+
+
+def test_header_cites_reference_and_has_plain_c_signatures():
+    text = open(os.path.join(ROOT, "include", "qprop.h")).read()
+    for cite in ("src/cheby.jl:150-213", "src/arnoldi.jl:60-100", "src/generators.jl:634-645", "src/newton.jl"):
+        assert cite in text
+    assert "torch" not in text.lower() and 'extern "C"' in text
+
+
+def test_status_strings():
+    lib = _lib.load()
+    assert lib.qp_status_string(0) == b"ok"
+    assert lib.qp_status_string(-5) == b"incorrect normalization"
+    assert lib.qp_status_string(-4) == b"not converged"
+
+
+def _no_gpu():
+    import torch
+
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device."""
+    with pytest.raises(qp.QPropError) as exc:
+        qp.Context(0)
+    assert exc.value.status == -2 and "no CPU fallback" in str(exc.value)
+    with pytest.raises(qp.QPropError):
+        qp.propagate(np.array([1, 0], dtype=complex), (np.eye(2, dtype=complex),), np.linspace(0, 1, 5), "cheby")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "quantumpropagators.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f
+
+
+# ---------------------------------------------------------------------------------------
+# host mirror vs oracle
+# ---------------------------------------------------------------------------------------
+
+
+def test_cheby_coeffs_host():
+    for Delta, dt in [(20.2, 0.02), (2.0, 1.0), (12.0, 1.0), (60.0, 1.0), (99.99, 0.1), (460.0, 1.0)]:
+        a, b = qp.cheby_coeffs(Delta, dt), O.cheby_coeffs(Delta, dt)
+        assert np.array_equal(a, b)
+        assert abs(a[-1]) <= 1e-12 < abs(a[-2])  # the first coefficient <= limit is kept
+    assert len(qp.cheby_coeffs(20.2, 0.02)) == 9 and len(qp.cheby_coeffs(2.0, 1.0)) == 13
+    n, buf = qp.cheby_coeffs_(np.zeros(4), 60.0, 1.0)
+    assert np.array_equal(buf[:n], O.cheby_coeffs(60.0, 1.0)) and len(buf) >= n
+
+
+def test_discretization_host():
+    assert np.array_equal(qp.get_tlist_midpoints([1, 3, 5, 6, 7]), [1, 4, 5.5, 7])
+    tlist = np.linspace(0, 3, 16)
+    f = lambda t: np.cos(3 * t)  # noqa: E731
+    assert np.array_equal(qp.discretize_on_midpoints(f, tlist), O.discretize_on_midpoints(f, tlist))
+    assert np.allclose(qp.discretize(f, tlist), O.discretize(f, tlist), atol=1e-15)
+    v = np.random.default_rng(0).standard_normal(16)
+    assert np.allclose(qp.discretize_on_midpoints(v, tlist), O.discretize_on_midpoints(v, tlist), atol=1e-14)
+    assert np.allclose(qp.discretize(v[:15], tlist), O.discretize(v[:15], tlist), atol=1e-15)
+    for n in (1, 2, 8, 15):
+        assert qp.t_mid(tlist, n) == O.t_mid(tlist, n)
+    with pytest.raises(ValueError):
+        qp.discretize(np.zeros(3), tlist)
+
+
+def test_generators_host():
+    rng = np.random.default_rng(1)
+    mats = [rng.standard_normal((6, 6)) + 0j for _ in range(4)]
+    e1 = lambda t: t  # noqa: E731
+    e2 = np.linspace(0, 1, 10)
+    gen = qp.hamiltonian(mats[0], (mats[1], e1), mats[2], (mats[3], e2))
+    assert isinstance(gen, qp.Generator) and len(gen.ops) == 3 and len(gen.amplitudes) == 2
+    assert np.array_equal(gen.ops[0], mats[0] + mats[2])  # drift terms are summed
+    ctrls = qp.get_controls(gen)
+    assert len(ctrls) == 2 and ctrls[0] is e1 and ctrls[1] is e2
+    tlist = np.linspace(0, 1, 11)
+    op = qp.evaluate(gen, tlist, 4)
+    assert isinstance(op, qp.Operator) and op.ops is gen.ops
+    assert np.allclose(op.toarray(), mats[0] + mats[2] + 0.35 * mats[1] + e2[3] * mats[3])
+    qp.evaluate_(op, gen, tlist, 1, vals_dict=qp.IdDict([(e1, 2.0), (e2, -1.0)]))
+    assert op.coeffs == [2.0, -1.0]
+    merged = qp.hamiltonian((mats[1], e1), (mats[2], e1))
+    assert len(merged.ops) == 1 and np.array_equal(merged.ops[0], mats[1] + mats[2])
+    assert isinstance(qp.hamiltonian(mats[0], (mats[1], 3.0)), qp.Operator)
+    assert qp.hamiltonian(mats[0]) is mats[0]
+    assert qp.get_controls((mats[0],)) == ()
+    with pytest.raises(ValueError):
+        qp.Operator(mats[:1], [1.0, 2.0])
+    with pytest.raises(ValueError):
+        qp.Generator(mats[:2], [])
+    with pytest.raises(AssertionError):
+        qp.evaluate_(qp.Operator([mats[0], mats[1]], [1.0]), gen, tlist, 1)
+
+
+def test_leja_and_newton_coeffs_host():
+    rng = np.random.default_rng(2)
+    func = lambda z: np.exp(-1j * z)  # noqa: E731
+    leja_a, leja_b = np.zeros(5, dtype=complex), np.zeros(5, dtype=complex)
+    a_a, a_b = np.zeros(3, dtype=complex), np.zeros(3, dtype=complex)
+    n_a = n_b = na_a = na_b = 0
+    radius = None
+    for restart in range(4):
+        cand = rng.standard_normal(15) + 0.1j * rng.standard_normal(15)
+        if restart == 1:
+            cand[3] = cand[7]  # duplicates: exercises the tie / zero-product path
+        if radius is None:
+            radius = qp.leja_radius(cand)
+            assert radius == O.leja_radius(cand)
+        n_a, leja_a = qp.extend_leja_(leja_a, n_a, cand.copy(), 5)
+        n_b, leja_b = O.extend_leja(leja_b, n_b, cand.copy(), 5)
+        assert n_a == n_b == 5 * (restart + 1)
+        assert np.array_equal(leja_a[:n_a], leja_b[:n_b])
+        na_a, a_a = qp.extend_newton_coeffs_(a_a, na_a, leja_a, func, n_a, radius)
+        na_b, a_b = O.extend_newton_coeffs(a_b, na_b, leja_b, func, n_b, radius)
+        assert na_a == na_b == n_a and np.array_equal(a_a[:na_a], a_b[:na_b])
+    # the Newton interpolant reproduces func at the Leja points
+    z = leja_a[:8]
+    for zi in z:
+        acc, prod = 0j, 1.0 + 0j
+        for k in range(8):
+            acc += a_a[k] * prod
+            prod *= (zi - leja_a[k]) / radius
+        assert abs(acc - func(zi)) < 1e-10
+
+
+def test_hessenberg_eigenvalues_host():
+    rng = np.random.default_rng(3)
+    Hs = np.triu(rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6)), -1)
+    for acc in (False, True):
+        assert np.allclose(qp.diagonalize_hessenberg_matrix(Hs, 5, accumulate=acc),
+                           O.diagonalize_hessenberg_matrix(Hs, 5, accumulate=acc))
+    two = qp.diagonalize_hessenberg_matrix(Hs, 2)
+    assert np.allclose(sorted(two, key=lambda z: (z.real, z.imag)),
+                       sorted(np.linalg.eigvals(Hs[:2, :2]), key=lambda z: (z.real, z.imag)))
+    assert len(qp.diagonalize_hessenberg_matrix(Hs, 4, accumulate=True)) == 10
+
+
+def test_workloads_shapes():
+    W = qp.workloads
+    H0, H1, H2 = W.tfim_chain(6)
+    assert H0.nnz == 64 and H1.nnz == 6 * 64 and H2.nnz == 64
+    dense = (H0 + 0.3 * H1 - 0.2 * H2).toarray()
+    assert np.allclose(dense, dense.conj().T)
+    w = W.config2_tfim(6)
+    ev = np.linalg.eigvalsh((H0 + 1.0 * H1 + 0.5 * H2).toarray())
+    assert w["E_min"] <= ev[0] and ev[-1] <= w["E_max"]
+    T0, T1, T2 = W.transmon_chain(3, 3)
+    for T in (T0, T1, T2):
+        assert abs(T - T.conj().T).max() < 1e-14
+    L = W.config4_liouvillian(n_spins=3, nt=4)
+    L0, L1 = L["ops"]
+    assert L0.shape == (64, 64)
+    # TDSE convention: d/dt vec(rho) = -i L vec(rho); trace preservation <=> vec(1)^T L = 0
+    one = np.eye(8).reshape(-1, order="F")
+    assert np.abs(one @ L0.toarray()).max() < 1e-13 and np.abs(one @ L1.toarray()).max() < 1e-13
+    # commutator part: -i L0 rho matches -i[H, rho] + D(rho) on a random density matrix
+    rng = np.random.default_rng(0)
+    psi = rng.standard_normal(8) + 1j * rng.standard_normal(8)
+    rho = np.outer(psi, psi.conj())
+    H0s, H1s, _ = W.tfim_chain(3)
+    lhs = (L1.toarray() @ rho.reshape(-1, order="F")).reshape(8, 8, order="F")
+    assert np.allclose(lhs, H1s.toarray() @ rho - rho @ H1s.toarray())
+    assert W.optomech().shape == (55, 55)
