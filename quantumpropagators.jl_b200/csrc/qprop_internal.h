@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,7 @@ struct qp_ctx_s {
   // small pinned staging area for per-step coefficient uploads
   qp_c128* h_stage = nullptr;
   size_t stage_elems = 0;
+  std::set<const void*> smem_configured;  // kernels already opted in to large dynamic smem
 };
 
 struct qp_op_s {
@@ -74,6 +76,8 @@ struct qp_gen_s {
   int64_t stored_entries = 0;  // entries stored in the chosen format (incl. padding)
   int64_t matrix_bytes = 0;    // algorithmic M of SURVEY.md §8
   int lanes = 8;               // CSR: lanes per row (power of two <= 32)
+  int sell_kernel = 1;         // SELL: 0 = LDG kernel, 1 = TMA-staged kernel (env QPROP_SELL_KERNEL)
+  int tma_cfg = 0;             // TMA kernel shape (env QPROP_TMA_CFG), see launch_epi
   // merged CSR (always built for sparse generators)
   uint32_t* d_mptr = nullptr;
   uint32_t* d_mcolop = nullptr;

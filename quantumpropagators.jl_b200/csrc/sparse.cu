@@ -417,6 +417,9 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     // small problems: trade lane efficiency for parallelism
     while (lanes < 32 && n * lanes < (int64_t)ctx->sm_count * 2048) lanes *= 2;
     g->lanes = lanes;
+    // SELL kernel selection (tuning knobs; defaults chosen from measurements on B200)
+    if (const char* k = getenv("QPROP_SELL_KERNEL")) g->sell_kernel = (strcmp(k, "ldg") == 0) ? 0 : 1;
+    if (const char* c = getenv("QPROP_TMA_CFG")) g->tma_cfg = atoi(c);
   }
 
   if (chosen == QP_FORMAT_SELL) {
@@ -504,6 +507,28 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
 // kernel dispatch
 // ---------------------------------------------------------------------------------------
 
+// TMA-staged SELL kernel: one CTA per SM (or a small multiple when a CTA's slice range would
+// exceed the staged offset table), dynamic shared memory = stages + barriers + slice offsets.
+template <int EPI, int WARPS, int STAGES, int CH>
+static int32_t launch_sell_tma(qp_gen_t gen, const MatView& m, const double2* x, const EpiArgs& e) {
+  qp_ctx_t ctx = gen->ctx;
+  auto kern = k_spmv_sell_tma<EPI, WARPS, STAGES, CH>;
+  int64_t ctas = ctx->sm_count;
+  while ((gen->n_slices + ctas - 1) / ctas > TMA_MAX_LOCAL_SLICES) ctas += ctx->sm_count;
+  if (ctas > gen->n_slices) ctas = gen->n_slices;
+  const int spc = (int)((gen->n_slices + ctas - 1) / ctas);
+  const size_t smem = sizeof(TmaStage<CH>) * WARPS * STAGES + sizeof(uint64_t) * WARPS * STAGES +
+                      sizeof(uint32_t) * (size_t)(spc + 1);
+  if (!ctx->smem_configured.count((const void*)kern)) {  // opt in to > 48 KB dynamic smem once per context
+    QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    ctx->smem_configured.insert((const void*)kern);
+  }
+  if (smem > 226 * 1024) return qp_fail(ctx, QP_ERR_INTERNAL, "TMA kernel needs %zu bytes of shared memory", smem);
+  kern<<<(unsigned)ctas, WARPS * 32, smem, ctx->stream>>>(m, gen->d_coef, gen->n_ops, x, e, spc);
+  QP_LAUNCHED(ctx);
+  return QP_OK;
+}
+
 template <int EPI>
 static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
@@ -526,9 +551,30 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};
-    // persistent-style grid: a multiple of the SM count, 8 CTAs of 256 threads per SM
+    if (gen->sell_kernel == 1) {
+      switch (gen->tma_cfg) {
+        case 1: return launch_sell_tma<EPI, 8, 3, 8>(gen, m, x, e);
+        case 2: return launch_sell_tma<EPI, 16, 2, 8>(gen, m, x, e);
+        case 3: return launch_sell_tma<EPI, 12, 3, 8>(gen, m, x, e);
+        case 4: return launch_sell_tma<EPI, 8, 6, 4>(gen, m, x, e);
+        case 5: return launch_sell_tma<EPI, 16, 3, 4>(gen, m, x, e);
+        case 6: return launch_sell_tma<EPI, 32, 2, 4>(gen, m, x, e);
+        case 7: return launch_sell_tma<EPI, 24, 2, 4>(gen, m, x, e);
+        case 8: return launch_sell_tma<EPI, 20, 2, 8>(gen, m, x, e);
+        case 9: return launch_sell_tma<EPI, 24, 3, 4>(gen, m, x, e);
+        case 10: return launch_sell_tma<EPI, 16, 4, 4>(gen, m, x, e);
+        default: return launch_sell_tma<EPI, 8, 4, 8>(gen, m, x, e);
+      }
+    }
+    // persistent grid: exactly the number of CTAs that are resident at once (SMs x occupancy),
+    // each striding over the slices -- no partial second wave
+    static int occ = 0;
+    if (occ == 0) {
+      QP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<EPI>, 256, 0));
+      if (occ < 1) occ = 1;
+    }
     int64_t blocks = (gen->n_slices + 7) / 8;
-    int64_t cap = (int64_t)ctx->sm_count * 8;
+    int64_t cap = (int64_t)ctx->sm_count * occ;
     if (blocks > cap) blocks = cap;
     k_spmv_sell<EPI><<<(unsigned)blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e);
     QP_LAUNCHED(ctx);

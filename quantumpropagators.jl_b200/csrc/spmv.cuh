@@ -58,26 +58,44 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
   return r;
 }
 
+// The epilogue is split in two so that kernels can request its operands (x_r, v_{k-1}[r],
+// acc[r]) at the START of a row block and consume them after the SpMV: their DRAM latency
+// is then hidden behind the matrix stream instead of being exposed once per block.
 template <int EPI>
-__device__ __forceinline__ void epilogue(const EpiArgs& e, int64_t idx, int64_t b, double2 hx,
-                                         double2 xr, double& chk_dr, double& chk_di, double& chk_n) {
+__device__ __forceinline__ void epi_load(const EpiArgs& e, const double2* __restrict__ x, int64_t xidx,
+                                         int64_t idx, double2& xr, double2& yv, double2& av) {
+  xr = yv = av = make_double2(0.0, 0.0);
+  if (EPI == EPI_MUL) {
+    if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = e.y[idx];  // beta == 0: y is not read (BLAS)
+    return;
+  }
+  xr = __ldg(x + xidx);
+  if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
+    yv = e.y[idx];
+    av = e.acc[idx];
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_apply(const EpiArgs& e, int64_t idx, double2 hx, double2 xr, double2 yv,
+                                          double2 av, double& chk_dr, double& chk_di, double& chk_n) {
   if (EPI == EPI_MUL) {
     double2 r = cmul2(e.alpha, hx);
     if (e.betac.x != 0.0 || e.betac.y != 0.0) {
-      double2 t = cmul2(e.betac, e.y[idx]);
+      const double2 t = cmul2(e.betac, yv);
       r.x += t.x;
       r.y += t.y;
     }
     e.y[idx] = r;
     return;
   }
-  double2 t = make_double2(hx.x - e.beta * xr.x, hx.y - e.beta * xr.y);
+  const double2 t = make_double2(hx.x - e.beta * xr.x, hx.y - e.beta * xr.y);
   double2 v = cmul2(e.c, t);  // c (Hx - beta x)
   if (EPI == EPI_CHEB_FIRST) {
     e.y[idx] = v;
     e.acc[idx] = make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y);
   } else if (EPI == EPI_CHEB_ONLY) {
-    double2 s = make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y);
+    const double2 s = make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y);
     e.acc[idx] = cmul2(e.phase, s);
   } else {
     if (e.chk != nullptr) {  // <v1|v2'> and |v1|^2, src/cheby.jl:194-200
@@ -85,19 +103,26 @@ __device__ __forceinline__ void epilogue(const EpiArgs& e, int64_t idx, int64_t 
       chk_di += xr.x * v.y - xr.y * v.x;
       chk_n += xr.x * xr.x + xr.y * xr.y;
     }
-    double2 p = e.y[idx];
-    v.x += p.x;
-    v.y += p.y;
-    double2 a = e.acc[idx];
-    a.x += e.ak * v.x;
-    a.y += e.ak * v.y;
+    v.x += yv.x;
+    v.y += yv.y;
+    av.x += e.ak * v.x;
+    av.y += e.ak * v.y;
     if (EPI == EPI_CHEB_MID) {
       e.y[idx] = v;
-      e.acc[idx] = a;
+      e.acc[idx] = av;
     } else {
-      e.acc[idx] = cmul2(e.phase, a);
+      e.acc[idx] = cmul2(e.phase, av);
     }
   }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue(const EpiArgs& e, const double2* __restrict__ x, int64_t xidx,
+                                         int64_t idx, double2 hx, double& chk_dr, double& chk_di,
+                                         double& chk_n) {
+  double2 xr, yv, av;
+  epi_load<EPI>(e, x, xidx, idx, xr, yv, av);
+  epi_apply<EPI>(e, idx, hx, xr, yv, av, chk_dr, chk_di, chk_n);
 }
 
 // warp-level flush of the normalization-check partial sums (debug option, atomics)
@@ -144,11 +169,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
     si += __shfl_xor_sync(0xffffffffu, si, o);
   }
   double dr = 0, di = 0, nn = 0;
-  if (active && lane == 0) {
-    double2 xr = make_double2(0.0, 0.0);
-    if (EPI != EPI_MUL) xr = __ldg(x + row);
-    epilogue<EPI>(e, row, 0, make_double2(sr, si), xr, dr, di, nn);
-  }
+  if (active && lane == 0) epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
   if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
@@ -178,6 +199,8 @@ k_spmv_sell(MatView m, const double2* __restrict__ coef, int n_ops, const double
        s += warps_total) {
     const int64_t row = s * QP_SELL_C + lane;
     const uint32_t p0 = m.ptr[s], p1 = m.ptr[s + 1];
+    double2 xr, yv, av;
+    if (row < m.n) epi_load<EPI>(e, x, row, row, xr, yv, av);  // consumed after the slice
     double sr = 0.0, si = 0.0;
 #pragma unroll 4
     for (uint32_t k = p0 + lane; k < p1; k += QP_SELL_C) {
@@ -190,11 +213,216 @@ k_spmv_sell(MatView m, const double2* __restrict__ coef, int n_ops, const double
       sr += u.x * tr - u.y * ti;
       si += u.x * ti + u.y * tr;
     }
-    if (row < m.n) {
-      double2 xr = make_double2(0.0, 0.0);
-      if (EPI != EPI_MUL) xr = __ldg(x + row);
-      epilogue<EPI>(e, row, 0, make_double2(sr, si), xr, dr, di, nn);
+    if (row < m.n) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
+  }
+  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) {
+      dr += __shfl_xor_sync(0xffffffffu, dr, o);
+      di += __shfl_xor_sync(0xffffffffu, di, o);
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
+    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SELL-32, batch == 1, TMA-staged: the matrix stream (values + packed columns of a slice
+// chunk) is brought into shared memory by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP)
+// completing on per-warp mbarriers, STAGES chunks deep, so the HBM stream stays in flight
+// independently of the registers; the threads only read shared memory, gather x (L1/L2) and
+// run the fused epilogue.  Each warp runs its own pipeline (lane 0 issues the copies for the
+// stage the warp has just drained), so no CTA-wide barrier sits in the loop.
+//
+// CTA c owns the contiguous slice range [c*spc, (c+1)*spc); warp w takes local slices
+// w, w+WARPS, ...  The slice offsets of the range are staged in shared memory once.
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier, with an L2
+// cache-policy hint (the matrix is streamed once per term: evict-first keeps L2 for vectors)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_hint(const double2* p, uint64_t policy) {
+  double2 r;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void st_hint(double2* p, double2 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy)
+               : "memory");
+}
+
+constexpr int TMA_MAX_LOCAL_SLICES = 2048;  // slice offsets staged per CTA
+
+template <int CH>
+struct __align__(128) TmaStage {
+  double2 val[CH * QP_SELL_C];
+  uint32_t col[CH * QP_SELL_C];
+};
+
+template <int EPI, int WARPS, int STAGES, int CH>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const double2* __restrict__ x,
+                EpiArgs e, int slices_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TmaStage<CH>* stages = reinterpret_cast<TmaStage<CH>*>(smem_raw);                       // [WARPS][STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(TmaStage<CH>) * WARPS * STAGES);  // [WARPS][STAGES]
+  uint32_t* s_ptr = reinterpret_cast<uint32_t*>(bars + WARPS * STAGES);                    // [slices_per_cta + 1]
+  __shared__ double2 s_coef[QP_MAX_OPS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
+  const int64_t s_begin = (int64_t)blockIdx.x * slices_per_cta;
+  int64_t s_end = s_begin + slices_per_cta;
+  if (s_end > n_slices) s_end = n_slices;
+  const int n_loc = s_end > s_begin ? (int)(s_end - s_begin) : 0;
+
+  if (threadIdx.x < n_ops) s_coef[threadIdx.x] = coef[threadIdx.x];
+  for (int i = threadIdx.x; i <= n_loc; i += WARPS * 32) s_ptr[i] = m.ptr[s_begin + i];
+  TmaStage<CH>* my_stage = stages + warp * STAGES;
+  uint64_t* my_bar = bars + warp * STAGES;
+  if (lane == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(my_bar + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (n_loc == 0) return;
+
+  const uint64_t pol_stream = policy_evict_first();
+  constexpr uint32_t CHUNK = CH * QP_SELL_C;  // entries per stage
+
+  // producer / consumer cursors (warp-uniform): local slice, entry offset, slice end
+  int p_ls = warp, c_ls = warp;
+  uint32_t p_off = 0, p_end = 0, c_off = 0, c_end = 0;
+  auto load_slice = [&](int& ls, uint32_t& off, uint32_t& end) {
+    while (ls < n_loc) {
+      off = s_ptr[ls];
+      end = s_ptr[ls + 1];
+      if (end > off) return;
+      ls += WARPS;  // empty slice (all rows empty): nothing to stream, epilogue handled below
+    }
+  };
+  // NOTE: slices whose rows are all empty still need their epilogue (Hx = 0); they are rare
+  // (never for a Hamiltonian with a diagonal) and are handled by the consumer loop below via
+  // c_ls stepping one slice at a time.
+  auto issue = [&](int stage) {
+    if (lane == 0) {
+      const uint32_t nent = min(CHUNK, p_end - p_off);
+      mbar_expect_tx(my_bar + stage, nent * 20u);
+      tma_load_1d(my_stage[stage].val, m.val + p_off, nent * 16u, my_bar + stage, pol_stream);
+      tma_load_1d(my_stage[stage].col, m.colop + p_off, nent * 4u, my_bar + stage, pol_stream);
+    }
+  };
+  auto p_advance = [&]() {
+    p_off += CHUNK;
+    if (p_off >= p_end) {
+      p_ls += WARPS;
+      load_slice(p_ls, p_off, p_end);
+    }
+  };
+
+  load_slice(p_ls, p_off, p_end);
+  // prologue: fill STAGES-1 stages
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (p_ls < n_loc) {
+      issue(s);
+      p_advance();
+    }
+  }
+
+  int stage = 0;
+  uint32_t parity = 0;
+  double dr = 0, di = 0, nn = 0;
+  for (; c_ls < n_loc; c_ls += WARPS) {
+    c_off = s_ptr[c_ls];
+    c_end = s_ptr[c_ls + 1];
+    const int64_t row = (s_begin + c_ls) * QP_SELL_C + lane;
+    const bool live = row < m.n;
+    // epilogue operands are requested now and consumed after the slice: latency fully hidden
+    double2 xr, yv, av;
+    if (live) epi_load<EPI>(e, x, row, row, xr, yv, av);
+    double sr = 0.0, si = 0.0;
+    while (c_off < c_end) {
+      // refill the stage drained in the previous iteration with the chunk STAGES-1 ahead
+      if (p_ls < n_loc) {
+        issue((stage + STAGES - 1) % STAGES);
+        p_advance();
+      }
+      mbar_wait(my_bar + stage, parity);
+      const uint32_t nj = min(CHUNK, c_end - c_off) / QP_SELL_C;
+      const TmaStage<CH>& sb = my_stage[stage];
+      if (nj == CH) {
+        uint32_t co[CH];
+        double2 xv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) co[j] = sb.col[j * QP_SELL_C + lane];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) xv[j] = __ldg(x + (co[j] & QP_COL_MASK));
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const double2 v = sb.val[j * QP_SELL_C + lane];
+          const double2 u = s_coef[co[j] >> QP_COL_BITS];
+          const double tr = v.x * xv[j].x - v.y * xv[j].y;
+          const double ti = v.x * xv[j].y + v.y * xv[j].x;
+          sr += u.x * tr - u.y * ti;
+          si += u.x * ti + u.y * tr;
+        }
+      } else {
+        for (uint32_t j = 0; j < nj; ++j) {
+          const uint32_t co = sb.col[j * QP_SELL_C + lane];
+          const double2 v = sb.val[j * QP_SELL_C + lane];
+          const double2 xv = __ldg(x + (co & QP_COL_MASK));
+          const double2 u = s_coef[co >> QP_COL_BITS];
+          const double tr = v.x * xv.x - v.y * xv.y;
+          const double ti = v.x * xv.y + v.y * xv.x;
+          sr += u.x * tr - u.y * ti;
+          si += u.x * ti + u.y * tr;
+        }
+      }
+      __syncwarp();  // every lane is done with this stage before lane 0 refills it
+      c_off += CHUNK;
+      stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+      if (stage == 0) parity ^= 1u;
+    }
+    if (live) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
   }
   if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -238,10 +466,8 @@ k_spmm_csr(MatView m, const double2* __restrict__ coef, int coef_stride, int64_t
     sr += u.x * tr - u.y * ti;
     si += u.x * ti + u.y * tr;
   }
-  double2 xr = make_double2(0.0, 0.0);
-  if (EPI != EPI_MUL) xr = __ldg(x + idx);
   double dr = 0, di = 0, nn = 0;
-  epilogue<EPI>(e, idx, b, make_double2(sr, si), xr, dr, di, nn);
+  epilogue<EPI>(e, x, idx, idx, make_double2(sr, si), dr, di, nn);
   if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) chk_flush(e, b, dr, di, nn);
 }
 
@@ -279,11 +505,7 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
     si += __shfl_xor_sync(0xffffffffu, si, o);
   }
   double dr = 0, di = 0, nn = 0;
-  if (row < n && lane == 0) {
-    double2 xr = make_double2(0.0, 0.0);
-    if (EPI != EPI_MUL) xr = __ldg(x + row);
-    epilogue<EPI>(e, row, 0, make_double2(sr, si), xr, dr, di, nn);
-  }
+  if (row < n && lane == 0) epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
   if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
