@@ -5,6 +5,7 @@
 // w2 accumulates psi; v_{k+1} overwrites v_{k-1}; at the end the state handle simply adopts
 // the accumulator buffer (pointer swap instead of a copy).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "spmv.cuh"
@@ -117,6 +118,10 @@ extern "C" int32_t qp_cheby_step(qp_cheby_t w, qp_state_t st, const qp_c128* op_
   double2* acc = w->w2;
   EpiArgs e;
   memset(&e, 0, sizeof(e));
+  {
+    static const int hint = getenv("QPROP_VEC_HINT") ? atoi(getenv("QPROP_VEC_HINT")) : 0;
+    e.vec_hint = hint;
+  }
   e.beta = beta;
   e.phase = phase;
   e.acc = acc;

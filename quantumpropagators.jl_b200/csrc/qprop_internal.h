@@ -77,7 +77,7 @@ struct qp_gen_s {
   int64_t matrix_bytes = 0;    // algorithmic M of SURVEY.md §8
   int lanes = 8;               // CSR: lanes per row (power of two <= 32)
   int sell_kernel = 1;         // SELL: 0 = LDG kernel, 1 = TMA-staged kernel (env QPROP_SELL_KERNEL)
-  int tma_cfg = 0;             // TMA kernel shape (env QPROP_TMA_CFG), see launch_epi
+  int tma_cfg = 2;             // TMA kernel shape (env QPROP_TMA_CFG), see launch_epi; 2 = 16 warps x 2 stages x 8 entries (best on B200, profiles/r1_variants.txt)
   // merged CSR (always built for sparse generators)
   uint32_t* d_mptr = nullptr;
   uint32_t* d_mcolop = nullptr;

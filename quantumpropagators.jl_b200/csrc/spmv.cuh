@@ -39,6 +39,7 @@ struct EpiArgs {
   double2* y;            // MUL: y;  FIRST: v1 out;  MID/LAST: v_{k-1} in, v_{k+1} out
   double2* acc;          // psi accumulator
   double* chk;           // normalization-check accumulators [batch][3] or nullptr
+  int vec_hint;          // 1: access the Chebyshev vectors with an L2 evict_last policy (TMA kernel)
 };
 
 __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
@@ -58,6 +59,42 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
   return r;
 }
 
+// L2 cache-policy helpers (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_hint(const double2* p, uint64_t policy) {
+  double2 r;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ double2 ld_nc_hint(const double2* p, uint64_t policy) {
+  double2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void st_hint(double2* p, double2 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ double2 vld(const double2* p, int hint) {
+  return hint ? ld_hint(p, policy_evict_last()) : *p;
+}
+__device__ __forceinline__ double2 vldg(const double2* p, int hint) {
+  return hint ? ld_nc_hint(p, policy_evict_last()) : __ldg(p);
+}
+__device__ __forceinline__ void vst(double2* p, double2 v, int hint) {
+  if (hint) st_hint(p, v, policy_evict_last());
+  else *p = v;
+}
+
 // The epilogue is split in two so that kernels can request its operands (x_r, v_{k-1}[r],
 // acc[r]) at the START of a row block and consume them after the SpMV: their DRAM latency
 // is then hidden behind the matrix stream instead of being exposed once per block.
@@ -69,10 +106,10 @@ __device__ __forceinline__ void epi_load(const EpiArgs& e, const double2* __rest
     if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = e.y[idx];  // beta == 0: y is not read (BLAS)
     return;
   }
-  xr = __ldg(x + xidx);
+  xr = vldg(x + xidx, e.vec_hint);
   if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
-    yv = e.y[idx];
-    av = e.acc[idx];
+    yv = vld(e.y + idx, e.vec_hint);
+    av = vld(e.acc + idx, e.vec_hint);
   }
 }
 
@@ -92,11 +129,11 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, int64_t idx, double2
   const double2 t = make_double2(hx.x - e.beta * xr.x, hx.y - e.beta * xr.y);
   double2 v = cmul2(e.c, t);  // c (Hx - beta x)
   if (EPI == EPI_CHEB_FIRST) {
-    e.y[idx] = v;
-    e.acc[idx] = make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y);
+    vst(e.y + idx, v, e.vec_hint);
+    vst(e.acc + idx, make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y), e.vec_hint);
   } else if (EPI == EPI_CHEB_ONLY) {
     const double2 s = make_double2(e.a0 * xr.x + e.ak * v.x, e.a0 * xr.y + e.ak * v.y);
-    e.acc[idx] = cmul2(e.phase, s);
+    vst(e.acc + idx, cmul2(e.phase, s), e.vec_hint);
   } else {
     if (e.chk != nullptr) {  // <v1|v2'> and |v1|^2, src/cheby.jl:194-200
       chk_dr += xr.x * v.x + xr.y * v.y;
@@ -108,10 +145,10 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, int64_t idx, double2
     av.x += e.ak * v.x;
     av.y += e.ak * v.y;
     if (EPI == EPI_CHEB_MID) {
-      e.y[idx] = v;
-      e.acc[idx] = av;
+      vst(e.y + idx, v, e.vec_hint);
+      vst(e.acc + idx, av, e.vec_hint);
     } else {
-      e.acc[idx] = cmul2(e.phase, av);
+      vst(e.acc + idx, cmul2(e.phase, av), e.vec_hint);
     }
   }
 }
@@ -269,26 +306,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ double2 ld_hint(const double2* p, uint64_t policy) {
-  double2 r;
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
-  return r;
-}
-__device__ __forceinline__ void st_hint(double2* p, double2 v, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy)
-               : "memory");
-}
-
 constexpr int TMA_MAX_LOCAL_SLICES = 2048;  // slice offsets staged per CTA
 
 template <int CH>
@@ -395,7 +412,7 @@ k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const do
 #pragma unroll
         for (int j = 0; j < CH; ++j) co[j] = sb.col[j * QP_SELL_C + lane];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) xv[j] = __ldg(x + (co[j] & QP_COL_MASK));
+        for (int j = 0; j < CH; ++j) xv[j] = vldg(x + (co[j] & QP_COL_MASK), e.vec_hint);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const double2 v = sb.val[j * QP_SELL_C + lane];
