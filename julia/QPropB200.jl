@@ -1,0 +1,411 @@
+# QPropB200.jl -- Julia host side of the B200 engine: the `ccall` bindings of
+# include/qprop.h and the method plugins `method=ChebyB200` / `method=NewtonB200` for
+# QuantumPropagators.jl.
+#
+# STATUS: written against QuantumPropagators v0.8.5 (`/root/reference`), NOT executed in the
+# build image (no Julia there).  The executed and tested host side is the Python mirror in
+# `quantumpropagators.jl_b200/`, which makes the same C-ABI calls in the same order; the
+# mapping is documented in INTEGRATION.md.
+#
+# Usage (unchanged user code, only the `method` differs):
+#
+#     using QuantumPropagators, QPropB200
+#     Ψ = propagate(Ψ₀, generator, tlist; method=ChebyB200, E_min=-10.0, E_max=10.0)
+#
+# Selection follows the reference's own plugin route: `init_prop(state, generator, tlist,
+# ::Val{:ChebyB200}; ...)` is found through `Val(nameof(method))`
+# (reference src/propagator.jl:255-258; precedent ext/QuantumPropagatorsExponentialUtilitiesExt.jl).
+
+module QPropB200
+
+using LinearAlgebra
+using SparseArrays
+using OffsetArrays
+import QuantumPropagators
+import QuantumPropagators: init_prop, prop_step!, set_t!, set_state!, reinit_prop!, PWCPropagator
+import QuantumPropagators: _pwc_get_max_genop, _pwc_process_parameters, _pwc_set_t!,
+    _pwc_set_genop!, _pwc_advance_time!, _get_uniform_dt, cheby_get_spectral_envelope
+import QuantumPropagators.Interfaces: supports_inplace
+using QuantumPropagators.Controls: get_controls, discretize
+using QuantumPropagators.Generators: Generator, Operator
+using QuantumPropagators.Cheby: cheby_coeffs
+using QuantumPropagators.Arnoldi: diagonalize_hessenberg_matrix
+using QuantumPropagators.Newton: extend_leja!, extend_newton_coeffs!, leja_radius
+
+export ChebyB200, NewtonB200, DeviceState, to_device, to_host
+
+const libqprop = get(ENV, "QPROP_B200_LIB", joinpath(@__DIR__, "..", "quantumpropagators.jl_b200",
+                                                      "csrc", "libqprop_b200.so"))
+
+# `method=ChebyB200` / `method=NewtonB200`: modules, like `QuantumPropagators.Cheby`
+module ChebyB200 end
+module NewtonB200 end
+
+const QP_LAYOUT_CSC = Int32(0)
+const QP_FORMAT_AUTO = Int32(0)
+
+# ---------------------------------------------------------------------------------------
+# status -> exception (reference error conventions, SURVEY.md §5)
+# ---------------------------------------------------------------------------------------
+function check(status::Int32, ctx::Ptr{Cvoid}=C_NULL)
+    status == 0 && return
+    msg = unsafe_string(ccall((:qp_last_error, libqprop), Cstring, (Ptr{Cvoid},), ctx))
+    status == -1 && throw(ArgumentError(msg))
+    status == -3 && throw(OutOfMemoryError())
+    (status == -4 || status == -5) && throw(AssertionError(msg))  # src/newton.jl:375, src/cheby.jl:196
+    error("libqprop_b200 [$status]: $msg")
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qp_ctx_create, libqprop), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h))
+        ctx = new(h[])
+        finalizer(c -> ccall((:qp_ctx_destroy, libqprop), Int32, (Ptr{Cvoid},), c.handle), ctx)
+    end
+end
+
+const _default_ctx = Ref{Union{Nothing,Context}}(nothing)
+default_context() = something(_default_ctx[], (_default_ctx[] = Context(0)))
+
+# ---------------------------------------------------------------------------------------
+# DeviceState: satisfies check_state (reference src/interfaces/state.jl:24-47) without being
+# an AbstractVector, so supports_vector_interface stays false (SURVEY.md §8b)
+# ---------------------------------------------------------------------------------------
+mutable struct DeviceState
+    ctx::Context
+    handle::Ptr{Cvoid}
+    n::Int64
+    function DeviceState(ctx::Context, n::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qp_state_create, libqprop), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    ctx.handle, n, 1, h), ctx.handle)
+        st = new(ctx, h[], n)
+        finalizer(s -> ccall((:qp_state_destroy, libqprop), Int32, (Ptr{Cvoid},), s.handle), st)
+    end
+end
+
+function to_device(Ψ::Vector{ComplexF64}; ctx=default_context())
+    st = DeviceState(ctx, length(Ψ))
+    check(ccall((:qp_state_upload, libqprop), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64, Int64),
+                st.handle, Ψ, 0, 1), ctx.handle)
+    return st
+end
+
+function to_host(st::DeviceState)
+    Ψ = Vector{ComplexF64}(undef, st.n)
+    check(ccall((:qp_state_download, libqprop), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64, Int64),
+                st.handle, Ψ, 0, 1), st.ctx.handle)
+    return Ψ
+end
+
+supports_inplace(::Type{DeviceState}) = true
+Base.length(st::DeviceState) = st.n
+Base.similar(st::DeviceState) = DeviceState(st.ctx, st.n)
+Base.copy(st::DeviceState) = copyto!(similar(st), st)
+Base.zero(st::DeviceState) = fill!(similar(st), 0)
+function Base.copyto!(dst::DeviceState, src::DeviceState)
+    check(ccall((:qp_copy, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), dst.handle, src.handle), dst.ctx.handle)
+    return dst
+end
+function Base.fill!(st::DeviceState, v)
+    check(ccall((:qp_fill, libqprop), Int32, (Ptr{Cvoid}, ComplexF64), st.handle, ComplexF64(v)), st.ctx.handle)
+    return st
+end
+function LinearAlgebra.lmul!(α::Number, st::DeviceState)
+    check(ccall((:qp_scal, libqprop), Int32, (Ptr{Cvoid}, ComplexF64), st.handle, ComplexF64(α)), st.ctx.handle)
+    return st
+end
+function LinearAlgebra.axpy!(α::Number, x::DeviceState, y::DeviceState)
+    check(ccall((:qp_axpy, libqprop), Int32, (ComplexF64, Ptr{Cvoid}, Ptr{Cvoid}), ComplexF64(α), x.handle, y.handle),
+          y.ctx.handle)
+    return y
+end
+function LinearAlgebra.dot(x::DeviceState, y::DeviceState)
+    out = Ref{ComplexF64}(0)
+    check(ccall((:qp_dot, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{ComplexF64}), x.handle, y.handle, out),
+          x.ctx.handle)
+    return out[]
+end
+function LinearAlgebra.norm(x::DeviceState)
+    out = Ref{Float64}(0)
+    check(ccall((:qp_norm, libqprop), Int32, (Ptr{Cvoid}, Ref{Float64}), x.handle, out), x.ctx.handle)
+    return out[]
+end
+Base.:+(a::DeviceState, b::DeviceState) = axpy!(1, b, copy(a))
+Base.:-(a::DeviceState, b::DeviceState) = axpy!(-1, b, copy(a))
+Base.:*(α::Number, a::DeviceState) = lmul!(α, copy(a))
+Base.:*(a::DeviceState, α::Number) = α * a
+
+# ---------------------------------------------------------------------------------------
+# operators / generators: Julia's native SparseMatrixCSC{ComplexF64,Int64} (1-based CSC) and
+# Matrix{ComplexF64} are passed as they are; the library transposes CSC -> CSR and narrows to
+# Int32 (SURVEY.md §7 hard part 1)
+# ---------------------------------------------------------------------------------------
+mutable struct DeviceGenerator
+    ctx::Context
+    handle::Ptr{Cvoid}
+    ops::Vector{Ptr{Cvoid}}
+    n_coeffs::Int
+end
+
+function upload_op(ctx::Context, A::SparseMatrixCSC{ComplexF64,Int64})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_op_upload_sparse, libqprop), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Int32, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(A, 1), size(A, 2), nnz(A), A.colptr, A.rowval, A.nzval, QP_LAYOUT_CSC, 1, h),
+          ctx.handle)
+    return h[]
+end
+
+function upload_op(ctx::Context, A::Matrix{ComplexF64})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_op_upload_dense, libqprop), Int32, (Ptr{Cvoid}, Int64, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                ctx.handle, size(A, 1), A, h), ctx.handle)
+    return h[]
+end
+
+upload_op(ctx::Context, A::AbstractSparseMatrix) = upload_op(ctx, SparseMatrixCSC{ComplexF64,Int64}(A))
+upload_op(ctx::Context, A::AbstractMatrix) = upload_op(ctx, Matrix{ComplexF64}(A))
+
+"""Device form of a static `Operator` (ops shared with the `Generator` it was evaluated from)."""
+function DeviceGenerator(ctx::Context, G::Operator)
+    ops = [upload_op(ctx, A) for A in G.ops]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_gen_create, libqprop), Int32, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Int32, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, length(ops), ops, length(G.coeffs), QP_FORMAT_AUTO, h), ctx.handle)
+    gen = DeviceGenerator(ctx, h[], ops, length(G.coeffs))
+    finalizer(gen) do g
+        ccall((:qp_gen_destroy, libqprop), Int32, (Ptr{Cvoid},), g.handle)
+        foreach(o -> ccall((:qp_op_destroy, libqprop), Int32, (Ptr{Cvoid},), o), g.ops)
+    end
+end
+DeviceGenerator(ctx::Context, A::AbstractMatrix) = DeviceGenerator(ctx, Operator([A], Float64[]))
+
+_coeffs(G::Operator) = ComplexF64[c for c in G.coeffs]
+_coeffs(::AbstractMatrix) = ComplexF64[]
+
+# ---------------------------------------------------------------------------------------
+# method = ChebyB200   (mirrors reference src/cheby_propagator.jl:9-27, 87-175, 243-299, 348-386)
+# ---------------------------------------------------------------------------------------
+mutable struct ChebyB200Propagator{GT,OT} <: PWCPropagator
+    const generator::GT
+    state::DeviceState
+    t::Float64
+    n::Int64
+    const tlist::Vector{Float64}
+    parameters::AbstractDict
+    controls
+    control_ranges::AbstractDict
+    genop::OT
+    devgen::DeviceGenerator
+    wrk::Ptr{Cvoid}              # qp_cheby_t
+    coeffs::Vector{Float64}
+    Δ::Float64
+    E_min::Float64
+    dt::Float64
+    limit::Float64
+    backward::Bool
+    inplace::Bool
+    specrange_method::Symbol
+    specrange_buffer::Float64
+    check_normalization::Bool
+    specrange_options::Dict{Symbol,Any}
+end
+
+set_t!(p::ChebyB200Propagator, t) = _pwc_set_t!(p, t)
+
+function _set_spectral_range!(p, Δ, E_min, dt)
+    p.coeffs = cheby_coeffs(Δ, dt; limit=p.limit)              # host: Bessel functions, src/cheby.jl:25-39
+    p.Δ, p.E_min, p.dt = Δ, E_min, dt
+    check(ccall((:qp_cheby_set_coeffs, libqprop), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Float64, Float64, Float64),
+                p.wrk, p.coeffs, length(p.coeffs), Δ, E_min, abs(dt), p.limit), p.state.ctx.handle)
+end
+
+function init_prop(state, generator, tlist, ::Val{:ChebyB200};
+                   inplace=true, backward=false, verbose=false, parameters=nothing,
+                   control_ranges=nothing, specrange_method=:auto, specrange_buffer=0.01,
+                   cheby_coeffs_limit=1e-12, check_normalization=false, uniform_dt_tolerance=1e-12,
+                   specrange_kwargs...)
+    tlist = convert(Vector{Float64}, tlist)
+    controls = get_controls(generator)
+    controlvals = [discretize(c, tlist) for c in controls]
+    G = _pwc_get_max_genop(generator, controls, tlist)
+    parameters = _pwc_process_parameters(parameters, controls, tlist)
+    if isnothing(control_ranges)
+        control_ranges = IdDict(c => (minimum(controlvals[i]), maximum(controlvals[i]))
+                                for (i, c) in enumerate(controls))
+    end
+    # spectral envelope exactly as the reference (specrange on host operators; :arnoldi can be
+    # redirected to the device by passing DeviceState start vectors)
+    E_min, E_max = cheby_get_spectral_envelope(generator, tlist, control_ranges, specrange_method;
+                                               specrange_kwargs...)
+    Δ = E_max - E_min
+    @assert Δ > 0.0
+    δ = specrange_buffer * Δ
+    E_min -= δ / 2
+    Δ += δ
+    dt = _get_uniform_dt(tlist; tol=uniform_dt_tolerance, warn=true)
+    isnothing(dt) && error("Chebychev propagation only works on a uniform time grid")
+    dstate = state isa DeviceState ? (inplace ? copy(state) : state) : to_device(Vector{ComplexF64}(state))
+    ctx = dstate.ctx
+    devgen = DeviceGenerator(ctx, G)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_cheby_create, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                devgen.handle, dstate.handle, h), ctx.handle)
+    n, t = backward ? (length(tlist) - 1, tlist[end]) : (1, tlist[1])
+    p = ChebyB200Propagator{typeof(generator),typeof(G)}(
+        generator, dstate, t, n, tlist, parameters, controls, control_ranges, G, devgen, h[],
+        Float64[], Δ, E_min, dt, cheby_coeffs_limit, backward, inplace, specrange_method,
+        specrange_buffer, check_normalization, Dict{Symbol,Any}(specrange_kwargs))
+    finalizer(q -> ccall((:qp_cheby_destroy, libqprop), Int32, (Ptr{Cvoid},), q.wrk), p)
+    _set_spectral_range!(p, Δ, E_min, dt)
+    return p
+end
+
+function prop_step!(p::ChebyB200Propagator)
+    n = p.n
+    tlist = getfield(p, :tlist)
+    (0 < n < length(tlist)) || return nothing
+    dt = p.backward ? -p.dt : p.dt
+    H = _pwc_set_genop!(p, n)                                   # host: rewrites H.coeffs only
+    Ψ = p.inplace ? p.state : copy(p.state)
+    check(ccall((:qp_cheby_step, libqprop), Int32,                # ONE ccall per prop_step!
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Float64, Int32),
+                p.wrk, Ψ.handle, _coeffs(H), 0, dt, p.check_normalization), Ψ.ctx.handle)
+    p.inplace || setfield!(p, :state, Ψ)
+    _pwc_advance_time!(p)
+    return p.state
+end
+
+function reinit_prop!(p::ChebyB200Propagator, state; transform_control_ranges=(c, lo, hi, check) -> (lo, hi), _...)
+    set_state!(p, state isa DeviceState ? state : to_device(Vector{ComplexF64}(state); ctx=p.state.ctx))
+    ranges = IdDict(c => (minimum(p.parameters[c]), maximum(p.parameters[c])) for c in p.controls)
+    recalc = any(p.controls) do c
+        lo, hi = transform_control_ranges(c, ranges[c]..., true)
+        lo < p.control_ranges[c][1] || hi > p.control_ranges[c][2]
+    end
+    if recalc
+        for c in p.controls
+            ranges[c] = transform_control_ranges(c, ranges[c]..., false)
+        end
+        E_min, E_max = cheby_get_spectral_envelope(getfield(p, :generator), p.tlist, ranges,
+                                                   p.specrange_method; p.specrange_options...)
+        Δ = E_max - E_min
+        δ = p.specrange_buffer * Δ
+        p.control_ranges = ranges
+        # new coefficient table only -- the operators stay on the device (SURVEY.md §3.4)
+        _set_spectral_range!(p, Δ + δ, E_min - δ / 2, float(p.tlist[2] - p.tlist[1]))
+    end
+    _pwc_set_t!(p, float(p.backward ? p.tlist[end] : p.tlist[1]))
+end
+
+# ---------------------------------------------------------------------------------------
+# method = NewtonB200   (mirrors reference src/newton_propagator.jl and src/newton.jl:246-385)
+# vectors on the device, Hessenberg / Leja / divided differences on the host
+# ---------------------------------------------------------------------------------------
+mutable struct NewtonB200Propagator{GT,OT} <: PWCPropagator
+    const generator::GT
+    state::DeviceState
+    t::Float64
+    n::Int64
+    const tlist::Vector{Float64}
+    parameters::AbstractDict
+    controls
+    genop::OT
+    devgen::DeviceGenerator
+    krylov::Ptr{Cvoid}           # qp_krylov_t
+    v::DeviceState
+    m_max::Int64
+    backward::Bool
+    inplace::Bool
+    func::Function
+    norm_min::Float64
+    relerr::Float64
+    max_restarts::Int64
+end
+
+set_t!(p::NewtonB200Propagator, t) = _pwc_set_t!(p, t)
+
+function init_prop(state, generator, tlist, ::Val{:NewtonB200};
+                   inplace=true, backward=false, verbose=false, parameters=nothing, m_max=10,
+                   func=(z -> exp(-1im * z)), norm_min=1e-14, relerr=1e-12, max_restarts=50, _...)
+    inplace || error("The Newton propagator is only implemented in-place")
+    tlist = convert(Vector{Float64}, tlist)
+    controls = get_controls(generator)
+    G = _pwc_get_max_genop(generator, controls, tlist)
+    parameters = _pwc_process_parameters(parameters, controls, tlist)
+    dstate = state isa DeviceState ? copy(state) : to_device(Vector{ComplexF64}(state))
+    m_max = min(m_max, length(dstate) - 1)
+    m_max > 2 || error("Newton propagation requires m_max > 2")
+    devgen = DeviceGenerator(dstate.ctx, G)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_krylov_create, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}),
+                devgen.handle, dstate.handle, m_max, h), dstate.ctx.handle)
+    n, t = backward ? (length(tlist) - 1, tlist[end]) : (1, tlist[1])
+    p = NewtonB200Propagator{typeof(generator),typeof(G)}(
+        generator, dstate, t, n, tlist, parameters, controls, G, devgen, h[], similar(dstate), m_max,
+        backward, inplace, func, norm_min, relerr, max_restarts)
+    finalizer(q -> ccall((:qp_krylov_destroy, libqprop), Int32, (Ptr{Cvoid},), q.krylov), p)
+end
+
+function _combine!(p, w::Vector{ComplexF64}, st::DeviceState, accumulate::Bool)
+    check(ccall((:qp_krylov_combine, libqprop), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Int32, Ptr{Cvoid}, Int32),
+                p.krylov, w, 0, length(w), st.handle, accumulate), st.ctx.handle)
+end
+
+function prop_step!(p::NewtonB200Propagator)
+    n = p.n
+    tlist = getfield(p, :tlist)
+    (0 < n < length(tlist)) || return nothing
+    dt = tlist[n+1] - tlist[n]
+    p.backward && (dt = -dt)
+    H = _pwc_set_genop!(p, n)
+    Ψ, ctx, func = p.state, p.state.ctx, p.func
+    m = p.m_max
+    a = OffsetVector(zeros(ComplexF64, 10 * m + 1), 0:(10*m))
+    leja = OffsetVector(zeros(ComplexF64, 10 * m + 1), 0:(10*m))
+    Hess = zeros(ComplexF64, m + 1, m + 1)
+    n_a = n_leja = s = 0
+    radius = 0.0
+    copyto!(p.v, Ψ)
+    β = norm(p.v)
+    lmul!(1 / β, p.v)
+    while true
+        m_out = Ref{Int32}(0)
+        check(ccall((:qp_arnoldi, libqprop), Int32,            # Arnoldi sweep on the device
+                    (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Int32, Float64, Int32, Float64, Ptr{ComplexF64}, Int32, Ref{Int32}),
+                    p.krylov, _coeffs(H), p.v.handle, m, dt, true, p.norm_min, Hess, size(Hess, 1), m_out), ctx.handle)
+        m = Int(m_out[])
+        if m == 1 && s == 0
+            lmul!(func(β * Hess[1, 1]), Ψ)
+            break
+        end
+        ritz = diagonalize_hessenberg_matrix(Hess, m, accumulate=true)        # host, src/arnoldi.jl:143
+        s == 0 && (radius = leja_radius(ritz))
+        n_s = n_leja
+        n_leja = extend_leja!(leja, n_leja, OffsetVector(ritz, 0:(length(ritz)-1)), m)   # host
+        n_a = extend_newton_coeffs!(a, n_a, leja, func, n_leja, radius)                  # host
+        R = zeros(ComplexF64, m + 1)
+        R[1] = β
+        P = a[n_s] * R
+        Hm = @view Hess[1:(m+1), 1:(m+1)]
+        for k = 1:(m-1)
+            R = (Hm * R - leja[n_s+k-1] * R) / radius
+            P += a[n_s+k] * R
+        end
+        _combine!(p, P[1:m], Ψ, s > 0)                         # Ψ (+)= Σ P_i q_i on the device
+        R = (Hm * R - leja[n_s+m-1] * R) / radius
+        β = norm(R)
+        _combine!(p, R / β, p.v, false)                        # restart vector on the device
+        (β * abs(a[n_a-1]) / (1 + norm(Ψ)) < p.relerr) && break
+        s += 1
+        @assert s <= p.max_restarts
+    end
+    _pwc_advance_time!(p)
+    return p.state
+end
+
+end # module
