@@ -286,3 +286,26 @@ def test_tfim_golden_fixture():
     assert np.linalg.norm(out - gold["exact"]) < 1e-10
     out_n = O.propagate(w["psi0"], O.hamiltonian(*terms), w["tlist"], "newton")
     assert np.linalg.norm(out_n - gold["exact"]) < 1e-10
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/cheby_ref.c (the timed CPU baseline of bench.py): both the faithful single-thread
+    CSC form and the OpenMP CSR variant equal the NumPy oracle to rounding."""
+    from oracle import cref
+
+    if not cref.available():
+        pytest.skip("oracle/libcheby_ref.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    w = W.config2_tfim(n_spins=10, nt=6, dt=0.1)
+    Delta = 1.01 * (w["E_max"] - w["E_min"])
+    E_min = w["E_min"] - 0.005 * (w["E_max"] - w["E_min"])
+    a = O.cheby_coeffs(Delta, 0.1)
+    ref_c = cref.ChebyRef(w["ops"], 2)
+    for dt in (0.1, -0.1):
+        for coeffs in ([0.3, -0.2], [1.0 + 0.5j, 0.0]):
+            expect = w["psi0"].copy()
+            O.cheby_inplace(expect, O.Operator(list(w["ops"]), coeffs), dt, O.ChebyWrk(expect, Delta, E_min, 0.1))
+            for threads in (0, 2):
+                psi = w["psi0"].copy()
+                n_mv = ref_c.step(psi, coeffs, a, Delta, E_min, dt, threads=threads)
+                assert n_mv == len(a) - 1
+                assert np.linalg.norm(psi - expect) < 1e-13
