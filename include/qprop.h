@@ -51,6 +51,9 @@ extern "C" {
 #define QP_FORMAT_CSR 1   /* merged multi-operator CSR, sub-warp per row        */
 #define QP_FORMAT_SELL 2  /* merged sliced-ELL (C = 32), thread per row           */
 #define QP_FORMAT_DENSE 3 /* dense row-major ComplexF64 operators                 */
+#define QP_FORMAT_SELLD 4 /* dictionary-compressed sliced-ELL: one 8/16-bit code per entry
+                             indexing a table of distinct (operator, value, column-row)
+                             triples; chosen when the table has < 4096 entries            */
 
 typedef struct qp_ctx_s* qp_ctx_t;
 typedef struct qp_op_s* qp_op_t;
@@ -110,6 +113,12 @@ int32_t qp_gen_destroy(qp_gen_t gen);
  * (sum_ops 20*nnz + 4*(N+1), or 16 N^2 per dense operator) */
 int32_t qp_gen_info(qp_gen_t gen, int32_t* format, int64_t* n, int64_t* stored_entries,
                     int64_t* matrix_bytes);
+/* what one application of the generator actually streams from memory for the matrix:
+ * bytes of the chosen device format (incl. padding); n_dict / code_bytes: entries of the
+ * dictionary of distinct (operator, value, offset) triples and the code width, when one could
+ * be built (used by QP_FORMAT_SELLD and by the trajectory-batched kernel; 0 otherwise).  No reference counterpart:
+ * the reference stores SparseMatrixCSC{ComplexF64,Int64} (24 B per entry). */
+int32_t qp_gen_storage(qp_gen_t gen, int64_t* stored_bytes, int32_t* n_dict, int32_t* code_bytes);
 
 /* ------------------------------------------------------------------ states
  * Replaces: Vector{ComplexF64} states and the level-1 verbs the reference's kernels use

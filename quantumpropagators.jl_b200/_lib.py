@@ -31,7 +31,8 @@ QP_FORMAT_AUTO = 0
 QP_FORMAT_CSR = 1
 QP_FORMAT_SELL = 2
 QP_FORMAT_DENSE = 3
-FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense"}
+QP_FORMAT_SELLD = 4
+FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense", 4: "selld"}
 
 
 class QPropLibraryError(RuntimeError):
@@ -82,6 +83,7 @@ SIGNATURES = {
     "qp_gen_create": (_i32, [_vp, _i32, _P(_vp), _i32, _i32, _P(_vp)]),
     "qp_gen_destroy": (_i32, [_vp]),
     "qp_gen_info": (_i32, [_vp, _P(_i32), _P(_i64), _P(_i64), _P(_i64)]),
+    "qp_gen_storage": (_i32, [_vp, _P(_i64), _P(_i32), _P(_i32)]),
     "qp_state_create": (_i32, [_vp, _i64, _i64, _P(_vp)]),
     "qp_state_destroy": (_i32, [_vp]),
     "qp_state_info": (_i32, [_vp, _P(_i64), _P(_i64)]),

@@ -252,7 +252,13 @@ static int32_t state_xfer(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb, 
              (long long)(b0 + nb), (long long)st->batch);
   // device row pitch = batch elements, host row pitch = nb elements
   const size_t el = sizeof(double2);
-  if (upload) {
+  if (nb == st->batch) {
+    // full width: one contiguous transfer at link speed (a pitched copy with 16-byte rows is
+    // an order of magnitude slower)
+    const size_t bytes = el * (size_t)st->n * (size_t)st->batch;
+    if (upload) QP_CUDA(ctx, cudaMemcpyAsync(st->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else QP_CUDA(ctx, cudaMemcpyAsync(host, st->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else if (upload) {
     QP_CUDA(ctx, cudaMemcpy2DAsync(st->d + b0, st->batch * el, host, nb * el, nb * el, st->n,
                                    cudaMemcpyHostToDevice, ctx->stream));
   } else {

@@ -66,6 +66,29 @@ struct MatView {
   int64_t n;             // rows
 };
 
+// device view of a dictionary-compressed SELL-32 matrix (QP_FORMAT_SELLD): every stored entry
+// is an 8- or 16-bit code into a table of distinct (operator, value, column - row) triples;
+// code 0 is the padding entry (value 0, offset 0).  A slice holds `width` chunks; chunk c of
+// lane l is the 16-byte word codes[off + c*32 + l] carrying 16 (8-bit) or 8 (16-bit) codes.
+struct DictView {
+  const uint32_t* sptr;   // slice offsets [n_slices+1] in 16-byte words (unused when uniform_words > 0)
+  const uint4* codes;
+  const double2* dval;    // [n_dict]
+  const int32_t* ddelta;  // [n_dict] column - row
+  const uint8_t* dop;     // [n_dict] operator index
+  int n_dict;
+  uint32_t uniform_words; // > 0: every slice has this many words (offset = slice * uniform_words)
+  int64_t n;
+  // operators whose main diagonal has too many distinct values for the table keep it as an
+  // explicit vector diag[i*n + row] (their diagonal entries are padding codes in the stream)
+  const double2* diag;
+  int n_diag;
+  unsigned long long diag_ops;  // operator index of vector i in bits [4i, 4i+4)
+};
+
+constexpr int QP_DICT_MAX = 4096;       // table entries incl. the padding entry
+constexpr int QP_DICT_HASH_CAP = 16384; // open-addressing capacity used while building
+
 struct qp_gen_s {
   qp_ctx_t ctx = nullptr;
   int n_ops = 0, n_coeffs = 0, drift = 0;
@@ -87,6 +110,20 @@ struct qp_gen_s {
   uint32_t* d_scolop = nullptr;
   double2* d_sval = nullptr;
   int64_t n_slices = 0;
+  // SELL-D (built when the dictionary of distinct entries is small enough)
+  uint32_t* d_dptr = nullptr;
+  uint4* d_dcodes = nullptr;
+  double2* d_dval = nullptr;
+  int32_t* d_ddelta = nullptr;
+  uint8_t* d_dop = nullptr;
+  double2* d_diag = nullptr;  // explicit diagonals [n_diag][n] (see DictView)
+  int n_diag = 0;
+  uint8_t diag_op[QP_MAX_OPS] = {0};
+  int n_dict = 0;          // 0: no dictionary
+  int code_bytes = 0;      // 1 or 2
+  uint32_t uniform_words = 0;
+  int64_t dict_words = 0;  // 16-byte words stored
+  int64_t stored_bytes = 0;  // bytes of the matrix stream actually read per application
   // dense: pointers to the row-major operators
   const double2** d_dense_ops = nullptr;
   // device copy of the effective per-operator coefficients (drift ops = 1), [n_ops][B]

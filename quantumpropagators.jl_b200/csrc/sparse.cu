@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "spmv.cuh"
+#include "dense_mma.cuh"
 
 // ---------------------------------------------------------------------------------------
 // operator upload
@@ -248,6 +249,186 @@ __global__ void k_sell_fill(const uint32_t* __restrict__ mptr, const uint32_t* _
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// dictionary compression (QP_FORMAT_SELLD)
+//
+// Hamiltonians assembled from tensor products of few-level operators have very few distinct
+// (operator, value, column - row) triples (TFIM n = 20: 81; transmon chain: a few hundred),
+// so an entry can be stored as one small code instead of 16 B value + 4 B column.  The table
+// is built on the device with an exact-match open-addressing hash (no lossy fingerprints),
+// compacted and ordered on the host (deterministic code numbering), and the codes are laid
+// out slice by slice in 16-byte words so that a warp-wide load is one 512 B segment.
+// ---------------------------------------------------------------------------------------
+
+constexpr uint16_t QP_DICT_DIAG_SLOT = 0xfffeu;  // slot_of marker: entry lives in an explicit diagonal
+
+struct DictSlot {
+  unsigned long long a, b, c;  // (op << 32 | uint32(col - row)), bits of re, bits of im
+  unsigned int tag;            // 0 empty, 1 being written, 2 ready
+  unsigned int pad;
+};
+
+__device__ __forceinline__ unsigned long long dict_mix(unsigned long long a, unsigned long long b,
+                                                       unsigned long long c) {
+  unsigned long long h = a * 0x9E3779B97F4A7C15ull;
+  h ^= (b + 0xBF58476D1CE4E5B9ull + (h << 6) + (h >> 2));
+  h *= 0x94D049BB133111EBull;
+  h ^= (c + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+
+// returns the slot of the key, inserting it if absent; 0xffffffff after overflow
+__device__ uint32_t dict_find_or_insert(DictSlot* tab, unsigned long long a, unsigned long long b,
+                                        unsigned long long c, unsigned int* ctl /*[0]=count,[1]=overflow*/,
+                                        unsigned int max_count) {
+  const uint32_t mask = QP_DICT_HASH_CAP - 1;
+  uint32_t s = (uint32_t)dict_mix(a, b, c) & mask;
+  for (uint32_t probe = 0; probe < (uint32_t)QP_DICT_HASH_CAP; ++probe) {
+    if (*(volatile unsigned int*)(ctl + 1)) return 0xffffffffu;
+    volatile unsigned int* tag = &tab[s].tag;
+    unsigned int t = *tag;
+    if (t == 0u) {
+      t = atomicCAS(&tab[s].tag, 0u, 1u);
+      if (t == 0u) {  // slot claimed
+        if (atomicAdd(ctl, 1u) >= max_count) atomicExch(ctl + 1, 1u);
+        tab[s].a = a;
+        tab[s].b = b;
+        tab[s].c = c;
+        __threadfence();
+        atomicExch(&tab[s].tag, 2u);
+        return s;
+      }
+    }
+    while (t == 1u) {  // another thread is publishing this slot
+      if (*(volatile unsigned int*)(ctl + 1)) return 0xffffffffu;
+      t = *tag;
+    }
+    __threadfence();
+    const volatile DictSlot* q = tab + s;
+    if (q->a == a && q->b == b && q->c == c) return s;
+    s = (s + 1) & mask;
+  }
+  atomicExch(ctl + 1, 1u);
+  return 0xffffffffu;
+}
+
+// warp per row of the merged CSR matrix; slot_of[k] = hash slot of entry k
+__global__ void k_dict_scan(const uint32_t* __restrict__ mptr, const uint32_t* __restrict__ mcolop,
+                            const double2* __restrict__ mval, int64_t n, DictSlot* tab, unsigned int* ctl,
+                            unsigned int max_count, uint16_t* __restrict__ slot_of, int skip_diag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    if (*(volatile unsigned int*)(ctl + 1)) return;
+    const uint32_t p0 = mptr[r], p1 = mptr[r + 1];
+    for (uint32_t k0 = p0; k0 < p1; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      bool have = k < p1;
+      unsigned long long a = 0, b = 0, c = 0;
+      if (have) {
+        const uint32_t co = mcolop[k];
+        const double2 v = mval[k];
+        const int32_t delta = (int32_t)((int64_t)(co & QP_COL_MASK) - r);
+        if (skip_diag && delta == 0) {  // kept as an explicit diagonal vector instead
+          slot_of[k] = QP_DICT_DIAG_SLOT;
+          have = false;
+        }
+        a = ((unsigned long long)(co >> QP_COL_BITS) << 32) | (unsigned long long)(uint32_t)delta;
+        b = (unsigned long long)__double_as_longlong(v.x);
+        c = (unsigned long long)__double_as_longlong(v.y);
+      }
+      // one insertion per distinct key of the warp (cuts contention on the few hot slots)
+      const unsigned act = __ballot_sync(0xffffffffu, have);
+      if (have) {
+        const unsigned long long h = dict_mix(a, b, c);
+        const unsigned peers = __match_any_sync(act, h);
+        const int leader = __ffs(peers) - 1;
+        uint32_t slot = 0;
+        if (lane == leader) slot = dict_find_or_insert(tab, a, b, c, ctl, max_count);
+        slot = __shfl_sync(peers, slot, leader);
+        // same 64-bit mix but a different key (vanishingly rare): look it up individually
+        const unsigned long long la = __shfl_sync(peers, a, leader), lb = __shfl_sync(peers, b, leader),
+                                 lc = __shfl_sync(peers, c, leader);
+        if (la != a || lb != b || lc != c) slot = dict_find_or_insert(tab, a, b, c, ctl, max_count);
+        slot_of[k] = (uint16_t)(slot & 0xffffu);
+      }
+    }
+  }
+}
+
+// which operators have entries on the main diagonal (flags[op] = 1)
+__global__ void k_diag_flags(const uint32_t* __restrict__ mptr, const uint32_t* __restrict__ mcolop, int64_t n,
+                             int* __restrict__ flags) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    for (uint32_t k = mptr[r]; k < mptr[r + 1]; ++k) {
+      const uint32_t co = mcolop[k];
+      if ((int64_t)(co & QP_COL_MASK) == r && flags[co >> QP_COL_BITS] == 0) flags[co >> QP_COL_BITS] = 1;
+    }
+}
+
+// diag[index_of[op] * n + r] = sum of operator op's entries at (r, r)
+__global__ void k_diag_extract(const uint32_t* __restrict__ mptr, const uint32_t* __restrict__ mcolop,
+                               const double2* __restrict__ mval, int64_t n, const int* __restrict__ index_of,
+                               double2* __restrict__ diag) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    for (uint32_t k = mptr[r]; k < mptr[r + 1]; ++k) {
+      const uint32_t co = mcolop[k];
+      if ((int64_t)(co & QP_COL_MASK) != r) continue;
+      double2* d = diag + (int64_t)index_of[co >> QP_COL_BITS] * n + r;
+      const double2 v = mval[k];
+      d->x += v.x;
+      d->y += v.y;
+    }
+}
+
+// 16-byte words per slice: ceil(longest row / codes per word) * 32
+__global__ void k_selld_widths(const uint32_t* __restrict__ mptr, int64_t n, int64_t n_slices, int cpw,
+                               uint32_t* __restrict__ slice_words) {
+  int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= n_slices) return;
+  int64_t r = s * QP_SELL_C + lane;
+  uint32_t len = r < n ? mptr[r + 1] - mptr[r] : 0u;
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) slice_words[s] = ((len + cpw - 1) / cpw) * QP_SELL_C;
+}
+
+template <int CB>
+__global__ void k_selld_fill(const uint32_t* __restrict__ mptr, const uint16_t* __restrict__ slot_of,
+                             const uint16_t* __restrict__ remap, int64_t n, int64_t n_slices,
+                             const uint32_t* __restrict__ dptr, uint4* __restrict__ codes) {
+  constexpr int CPW = 16 / CB;
+  int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= n_slices) return;
+  int64_t r = s * QP_SELL_C + lane;
+  const uint32_t base = dptr[s];
+  const uint32_t chunks = (dptr[s + 1] - base) / QP_SELL_C;
+  uint32_t p0 = 0, len = 0;
+  if (r < n) {
+    p0 = mptr[r];
+    len = mptr[r + 1] - p0;
+  }
+  for (uint32_t ch = 0; ch < chunks; ++ch) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < CPW; ++t) {
+      const uint32_t j = ch * CPW + t;
+      uint32_t code = 0u;  // 0 = padding (also stands in for entries kept in the explicit diagonals)
+      if (j < len) {
+        const uint16_t slot = slot_of[p0 + j];
+        if (slot != QP_DICT_DIAG_SLOT) code = remap[slot];
+      }
+      if (CB == 1) w[t >> 2] |= code << (8 * (t & 3));
+      else w[t >> 1] |= code << (16 * (t & 1));
+    }
+    codes[base + ch * QP_SELL_C + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 static int32_t exclusive_scan_u32(qp_ctx_t ctx, const uint32_t* d_in, uint32_t* d_out, int64_t count) {
   void* d_temp = nullptr;
   size_t temp_bytes = 0;
@@ -274,9 +455,199 @@ static void gen_free(qp_gen_t g) {
   cudaFree(g->d_sptr);
   cudaFree(g->d_scolop);
   cudaFree(g->d_sval);
+  cudaFree(g->d_dptr);
+  cudaFree(g->d_dcodes);
+  cudaFree(g->d_dval);
+  cudaFree(g->d_ddelta);
+  cudaFree(g->d_dop);
+  cudaFree(g->d_diag);
   cudaFree((void*)g->d_dense_ops);
   cudaFree(g->d_coef);
   delete g;
+}
+
+// Builds the SELL-D storage of a generator from its merged CSR arrays.  *ok = false (and
+// nothing allocated) when the matrix has more than QP_DICT_MAX-1 distinct entries.
+static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
+  *ok = false;
+  const int64_t n = g->n, nnz = g->nnz_total, n_slices = g->n_slices;
+  if (nnz == 0) return QP_OK;
+  DictSlot* d_tab = nullptr;
+  unsigned int* d_ctl = nullptr;
+  uint16_t* d_slot_of = nullptr;
+  uint16_t* d_remap = nullptr;
+  uint32_t* d_words = nullptr;
+  auto release = [&]() {
+    cudaFree(d_tab);
+    cudaFree(d_ctl);
+    cudaFree(d_slot_of);
+    cudaFree(d_remap);
+    cudaFree(d_words);
+  };
+  auto drop = [&]() {
+    cudaFree(g->d_dptr);
+    cudaFree(g->d_dcodes);
+    cudaFree(g->d_dval);
+    cudaFree(g->d_ddelta);
+    cudaFree(g->d_dop);
+    cudaFree(g->d_diag);
+    g->d_dptr = nullptr;
+    g->d_dcodes = nullptr;
+    g->d_dval = nullptr;
+    g->d_ddelta = nullptr;
+    g->d_dop = nullptr;
+    g->d_diag = nullptr;
+    g->n_diag = 0;
+    g->n_dict = 0;
+  };
+#define D_CUDA(call)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      cudaGetLastError();                                                                         \
+      release();                                                                                  \
+      drop();                                                                                     \
+      return qp_fail(ctx, e__ == cudaErrorMemoryAllocation ? QP_ERR_OOM : QP_ERR_CUDA,            \
+                     "qp_gen_create (dictionary): %s failed: %s", #call, cudaGetErrorString(e__)); \
+    }                                                                                             \
+  } while (0)
+
+  D_CUDA(cudaMalloc(&d_tab, sizeof(DictSlot) * QP_DICT_HASH_CAP));
+  D_CUDA(cudaMalloc(&d_ctl, sizeof(unsigned int) * 2));
+  D_CUDA(cudaMalloc(&d_slot_of, sizeof(uint16_t) * (size_t)nnz));
+  D_CUDA(cudaMemsetAsync(d_tab, 0, sizeof(DictSlot) * QP_DICT_HASH_CAP, ctx->stream));
+  D_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(unsigned int) * 2, ctx->stream));
+  {
+    int64_t blocks = std::min<int64_t>((n * 32 + 255) / 256, (int64_t)ctx->sm_count * 8);
+    k_dict_scan<<<(unsigned)blocks, 256, 0, ctx->stream>>>(g->d_mptr, g->d_mcolop, g->d_mval, n, d_tab, d_ctl,
+                                                             (unsigned)(QP_DICT_MAX - 1), d_slot_of, skip_diag ? 1 : 0);
+    ctx->launches++;
+    D_CUDA(cudaGetLastError());
+  }
+  unsigned int h_ctl[2] = {0, 0};
+  D_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, ctx->stream));
+  D_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_ctl[1] != 0 || h_ctl[0] > (unsigned)(QP_DICT_MAX - 1)) {  // too many distinct entries
+    release();
+    return QP_OK;
+  }
+
+  // compact + order the table on the host: codes are deterministic (sorted by operator,
+  // offset, value bits) although the hash slots are not
+  std::vector<DictSlot> h_tab(QP_DICT_HASH_CAP);
+  D_CUDA(cudaMemcpy(h_tab.data(), d_tab, sizeof(DictSlot) * QP_DICT_HASH_CAP, cudaMemcpyDeviceToHost));
+  std::vector<int> used;
+  for (int i = 0; i < QP_DICT_HASH_CAP; ++i)
+    if (h_tab[i].tag == 2u) used.push_back(i);
+  std::sort(used.begin(), used.end(), [&](int x, int y) {
+    const DictSlot &p = h_tab[x], &q = h_tab[y];
+    if (p.a != q.a) return p.a < q.a;
+    if (p.b != q.b) return p.b < q.b;
+    return p.c < q.c;
+  });
+  const int n_dict = (int)used.size() + 1;
+  std::vector<uint16_t> h_remap(QP_DICT_HASH_CAP, 0);
+  std::vector<double2> h_val(n_dict, make_double2(0.0, 0.0));
+  std::vector<int32_t> h_delta(n_dict, 0);
+  std::vector<uint8_t> h_op(n_dict, 0);
+  for (int i = 0; i < (int)used.size(); ++i) {
+    const DictSlot& p = h_tab[used[i]];
+    h_remap[used[i]] = (uint16_t)(i + 1);
+    double re, im;
+    memcpy(&re, &p.b, 8);
+    memcpy(&im, &p.c, 8);
+    h_val[i + 1] = make_double2(re, im);
+    h_delta[i + 1] = (int32_t)(uint32_t)(p.a & 0xffffffffull);
+    h_op[i + 1] = (uint8_t)(p.a >> 32);
+  }
+  const int cb = n_dict <= 256 ? 1 : 2;
+  const int cpw = 16 / cb;
+
+  D_CUDA(cudaMalloc(&d_remap, sizeof(uint16_t) * QP_DICT_HASH_CAP));
+  D_CUDA(cudaMemcpy(d_remap, h_remap.data(), sizeof(uint16_t) * QP_DICT_HASH_CAP, cudaMemcpyHostToDevice));
+  D_CUDA(cudaMalloc(&g->d_dval, sizeof(double2) * n_dict));
+  D_CUDA(cudaMalloc(&g->d_ddelta, sizeof(int32_t) * n_dict));
+  D_CUDA(cudaMalloc(&g->d_dop, sizeof(uint8_t) * n_dict));
+  D_CUDA(cudaMemcpy(g->d_dval, h_val.data(), sizeof(double2) * n_dict, cudaMemcpyHostToDevice));
+  D_CUDA(cudaMemcpy(g->d_ddelta, h_delta.data(), sizeof(int32_t) * n_dict, cudaMemcpyHostToDevice));
+  D_CUDA(cudaMemcpy(g->d_dop, h_op.data(), sizeof(uint8_t) * n_dict, cudaMemcpyHostToDevice));
+
+  // slice widths in 16-byte words
+  D_CUDA(cudaMalloc(&d_words, sizeof(uint32_t) * (n_slices + 1)));
+  D_CUDA(cudaMemsetAsync(d_words, 0, sizeof(uint32_t) * (n_slices + 1), ctx->stream));
+  k_selld_widths<<<(unsigned)((n_slices * 32 + 255) / 256), 256, 0, ctx->stream>>>(g->d_mptr, n, n_slices, cpw, d_words);
+  ctx->launches++;
+  D_CUDA(cudaGetLastError());
+  std::vector<uint32_t> h_words((size_t)n_slices);
+  D_CUDA(cudaMemcpyAsync(h_words.data(), d_words, sizeof(uint32_t) * n_slices, cudaMemcpyDeviceToHost, ctx->stream));
+  D_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint64_t total_words = 0;
+  bool uniform = true;
+  for (uint32_t v : h_words) {
+    total_words += v;
+    uniform &= (v == h_words[0]);
+  }
+  if (total_words >= (uint64_t(1) << 32)) {  // offsets are 32-bit
+    release();
+    drop();
+    return QP_OK;
+  }
+  D_CUDA(cudaMalloc(&g->d_dptr, sizeof(uint32_t) * (n_slices + 1)));
+  {
+    int32_t rc = exclusive_scan_u32(ctx, d_words, g->d_dptr, n_slices + 1);
+    if (rc != QP_OK) {
+      release();
+      drop();
+      return rc;
+    }
+  }
+  D_CUDA(cudaMalloc(&g->d_dcodes, sizeof(uint4) * std::max<uint64_t>(total_words, 1)));
+  if (cb == 1)
+    k_selld_fill<1><<<(unsigned)((n_slices * 32 + 255) / 256), 256, 0, ctx->stream>>>(g->d_mptr, d_slot_of, d_remap, n, n_slices, g->d_dptr, g->d_dcodes);
+  else
+    k_selld_fill<2><<<(unsigned)((n_slices * 32 + 255) / 256), 256, 0, ctx->stream>>>(g->d_mptr, d_slot_of, d_remap, n, n_slices, g->d_dptr, g->d_dcodes);
+  ctx->launches++;
+  D_CUDA(cudaGetLastError());
+  if (skip_diag) {
+    int* d_flags = nullptr;  // [0..15] has-diagonal flags, [16..31] index of the operator's vector
+    D_CUDA(cudaMalloc(&d_flags, sizeof(int) * 2 * QP_MAX_OPS));
+    cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * QP_MAX_OPS, ctx->stream);
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_diag_flags<<<blocks, 256, 0, ctx->stream>>>(g->d_mptr, g->d_mcolop, n, d_flags);
+    ctx->launches++;
+    int h_flags[2 * QP_MAX_OPS] = {0};
+    cudaError_t e1 = cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * QP_MAX_OPS, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+    g->n_diag = 0;
+    for (int l = 0; l < g->n_ops && e1 == cudaSuccess; ++l)
+      if (h_flags[l]) {
+        h_flags[QP_MAX_OPS + l] = g->n_diag;
+        g->diag_op[g->n_diag++] = (uint8_t)l;
+      }
+    if (e1 == cudaSuccess && g->n_diag > 0) {
+      e1 = cudaMalloc(&g->d_diag, sizeof(double2) * (size_t)g->n_diag * (size_t)n);
+      if (e1 == cudaSuccess) e1 = cudaMemsetAsync(g->d_diag, 0, sizeof(double2) * (size_t)g->n_diag * (size_t)n, ctx->stream);
+      if (e1 == cudaSuccess)
+        e1 = cudaMemcpyAsync(d_flags + QP_MAX_OPS, h_flags + QP_MAX_OPS, sizeof(int) * QP_MAX_OPS, cudaMemcpyHostToDevice, ctx->stream);
+      if (e1 == cudaSuccess) {
+        k_diag_extract<<<blocks, 256, 0, ctx->stream>>>(g->d_mptr, g->d_mcolop, g->d_mval, n, d_flags + QP_MAX_OPS, g->d_diag);
+        ctx->launches++;
+        e1 = cudaGetLastError();
+      }
+    }
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_flags);
+    D_CUDA(e1);
+  }
+  D_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef D_CUDA
+  release();
+  g->n_dict = n_dict;
+  g->code_bytes = cb;
+  g->uniform_words = uniform && n_slices > 0 ? h_words[0] : 0u;
+  g->dict_words = (int64_t)total_words;
+  *ok = true;
+  return QP_OK;
 }
 
 extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops, int32_t n_coeffs,
@@ -290,7 +661,7 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   // "The number of coefficients cannot exceed the number of operators" src/generators.jl:116-121
   QP_REQUIRE(ctx, n_coeffs >= 0 && n_coeffs <= n_ops,
              "qp_gen_create: the number of coefficients (%d) cannot exceed the number of operators (%d)", n_coeffs, n_ops);
-  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_DENSE, "qp_gen_create: bad format %d", format);
+  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_SELLD, "qp_gen_create: bad format %d", format);
   bool any_dense = false, all_dense = true;
   for (int l = 0; l < n_ops; ++l) {
     QP_REQUIRE(ctx, ops[l] != nullptr, "qp_gen_create: operator %d is null", l);
@@ -400,16 +771,37 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   const double mean_len = (double)nnz_total / (double)n;
   const double pad = nnz_total > 0 ? (double)sell_entries / (double)nnz_total : 1.0;
   int chosen = format;
+  // thread-per-row needs enough rows to fill the machine; otherwise use sub-warps per row
+  const bool rows_ok = n >= (int64_t)ctx->sm_count * 1024;
+  bool dict_ok = false;
+  // attempted for every AUTO generator: besides the B = 1 SELL-D kernel (large N only) the
+  // dictionary also serves the trajectory-batched kernel at any N
+  if ((format == QP_FORMAT_AUTO && !getenv("QPROP_NO_DICT")) || format == QP_FORMAT_SELLD) {
+    int32_t rc = build_dict(ctx, g, &dict_ok, false);
+    // typical second chance: a diagonal drift term with thousands of distinct energies on top of
+    // couplings with a handful of values -- keep the diagonals as explicit vectors
+    if (rc == QP_OK && !dict_ok) rc = build_dict(ctx, g, &dict_ok, true);
+    if (rc != QP_OK) {
+      cudaFree(d_len);
+      cudaFree(d_slice_entries);
+      return bail(rc);
+    }
+    if (format == QP_FORMAT_SELLD && !dict_ok) {
+      cudaFree(d_len);
+      cudaFree(d_slice_entries);
+      return bail(qp_fail(ctx, QP_ERR_UNSUPPORTED,
+                          "qp_gen_create: QP_FORMAT_SELLD needs fewer than %d distinct (operator, value, offset) entries",
+                          QP_DICT_MAX));
+    }
+  }
   if (chosen == QP_FORMAT_AUTO) {
-    // thread-per-row needs enough rows to fill the machine; otherwise use sub-warps per row
-    const bool sell_ok = n >= (int64_t)ctx->sm_count * 1024 && pad <= 1.25 && sell_entries < (uint64_t(1) << 32);
-    chosen = sell_ok ? QP_FORMAT_SELL : QP_FORMAT_CSR;
+    const bool sell_ok = rows_ok && pad <= 1.25 && sell_entries < (uint64_t(1) << 32);
+    // padded code slots per true nonzero (the code stream is 1-2 B/entry, so padding is cheap in
+    // bytes; the bound limits wasted lookups)
+    const double dpad = dict_ok ? (double)g->dict_words * (16 / g->code_bytes) / (double)nnz_total : 1e30;
+    chosen = (dict_ok && rows_ok && dpad <= 2.0) ? QP_FORMAT_SELLD : sell_ok ? QP_FORMAT_SELL : QP_FORMAT_CSR;
   }
-  if (chosen == QP_FORMAT_SELL && sell_entries >= (uint64_t(1) << 32)) {
-    cudaFree(d_len);
-    cudaFree(d_slice_entries);
-    return bail(qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: SELL storage exceeds 2^32 entries"));
-  }
+  if (chosen == QP_FORMAT_AUTO) chosen = QP_FORMAT_CSR;
   g->format = chosen;
   {
     int lanes = pow2_floor((int64_t)std::max(1.0, mean_len / 2.0));
@@ -441,6 +833,12 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     g->d_sptr = nullptr;
     g->stored_entries = nnz_total;
   }
+  if (chosen == QP_FORMAT_SELLD) {
+    g->stored_entries = g->dict_words * (16 / g->code_bytes);
+    g->stored_bytes = g->dict_words * 16 + (g->uniform_words ? 0 : 4 * (n_slices + 1)) + 16 * (int64_t)g->n_diag * n;
+  } else {
+    g->stored_bytes = 20 * g->stored_entries + 4 * ((chosen == QP_FORMAT_SELL ? n_slices : n) + 1);
+  }
   G_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_len);
   cudaFree(d_slice_entries);
@@ -464,6 +862,14 @@ extern "C" int32_t qp_gen_info(qp_gen_t gen, int32_t* format, int64_t* n, int64_
   if (n) *n = gen->n;
   if (stored_entries) *stored_entries = gen->stored_entries;
   if (matrix_bytes) *matrix_bytes = gen->matrix_bytes;
+  return QP_OK;
+}
+
+extern "C" int32_t qp_gen_storage(qp_gen_t gen, int64_t* stored_bytes, int32_t* n_dict, int32_t* code_bytes) {
+  if (!gen) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_gen_storage: null generator");
+  if (stored_bytes) *stored_bytes = gen->format == QP_FORMAT_DENSE ? gen->matrix_bytes : gen->stored_bytes;
+  if (n_dict) *n_dict = gen->n_dict;
+  if (code_bytes) *code_bytes = gen->n_dict > 0 ? gen->code_bytes : 0;
   return QP_OK;
 }
 
@@ -529,15 +935,76 @@ static int32_t launch_sell_tma(qp_gen_t gen, const MatView& m, const double2* x,
   return QP_OK;
 }
 
+static DictView make_dict_view(qp_gen_t gen) {
+  DictView m{gen->d_dptr, gen->d_dcodes, gen->d_dval, gen->d_ddelta, gen->d_dop, gen->n_dict, gen->uniform_words,
+             gen->n,      gen->d_diag,   gen->n_diag, 0ull};
+  for (int i = 0; i < gen->n_diag; ++i) m.diag_ops |= (unsigned long long)(gen->diag_op[i] & 15) << (4 * i);
+  return m;
+}
+
+// SELL-D kernel: CTAs = SMs x resident CTAs per SM (or fewer for small matrices), each owning a
+// contiguous slice range; dynamic shared memory = the coefficient-scaled table.
+template <int EPI, int CB>
+static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, const EpiArgs& e) {
+  qp_ctx_t ctx = gen->ctx;
+  auto kern = k_spmv_selld<EPI, CB>;
+  const size_t smem = (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
+  if (!ctx->smem_configured.count((const void*)kern)) {
+    QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ctx->smem_configured.insert((const void*)kern);
+  }
+  const int threads = 256;
+  static const int per_sm = getenv("QPROP_SELLD_CTAS") ? atoi(getenv("QPROP_SELLD_CTAS")) : 0;
+  int occ = per_sm;
+  if (occ <= 0) {
+    QP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+  }
+  const int wpc = threads / 32;
+  int64_t ctas = (int64_t)ctx->sm_count * occ;
+  int64_t spc = (gen->n_slices + ctas - 1) / ctas;
+  spc = (spc + wpc - 1) / wpc * wpc;  // whole rounds of the CTA's warps
+  // alternative: small aligned tiles handed out by the hardware block scheduler
+  static const int spc_env = getenv("QPROP_SELLD_SPC") ? atoi(getenv("QPROP_SELLD_SPC")) : 0;
+  if (spc_env > 0) spc = spc_env;
+  ctas = (gen->n_slices + spc - 1) / spc;
+  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc);
+  QP_LAUNCHED(ctx);
+  return QP_OK;
+}
+
 template <int EPI>
 static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
   const int64_t n = gen->n;
   cudaStream_t st = ctx->stream;
   if (gen->format == QP_FORMAT_DENSE) {
-    if (batch != 1)
-      return qp_fail(ctx, QP_ERR_UNSUPPORTED, "dense generators with batch > 1 are not supported yet");
+    if (batch != 1) return launch_dense_batched<EPI>(gen, coef_stride, x, batch, e);  // FP64 tensor cores
     k_gemv_dense<EPI><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e);
+    QP_LAUNCHED(ctx);
+    return QP_OK;
+  }
+  if (batch >= 16 && gen->n_dict > 0) {  // dictionary available: warp per (row, 32 trajectories)
+    const DictView m = make_dict_view(gen);
+    const int64_t chunks = (batch + 31) / 32;
+    if (chunks > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "batch too large for one launch");
+    const size_t smem = ((size_t)gen->n_dict * 21 + 15) / 16 * 16;
+    dim3 grid((unsigned)gen->n_slices, (unsigned)chunks);
+    if (gen->code_bytes == 1) {
+      auto kern = k_spmm_selld<EPI, 1>;
+      if (!ctx->smem_configured.count((const void*)kern)) {
+        QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ctx->smem_configured.insert((const void*)kern);
+      }
+      kern<<<grid, 256, smem, st>>>(m, gen->d_coef, coef_stride, batch, x, e, gen->n_ops);
+    } else {
+      auto kern = k_spmm_selld<EPI, 2>;
+      if (!ctx->smem_configured.count((const void*)kern)) {
+        QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ctx->smem_configured.insert((const void*)kern);
+      }
+      kern<<<grid, 256, smem, st>>>(m, gen->d_coef, coef_stride, batch, x, e, gen->n_ops);
+    }
     QP_LAUNCHED(ctx);
     return QP_OK;
   }
@@ -548,6 +1015,12 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     k_spmm_csr<EPI><<<(unsigned)blocks, 256, 0, st>>>(m, gen->d_coef, coef_stride, batch, x, e);
     QP_LAUNCHED(ctx);
     return QP_OK;
+  }
+  if (gen->format == QP_FORMAT_SELLD) {
+    const DictView m = make_dict_view(gen);
+    // compiled for 2 resident CTAs of 256 threads per SM (<= 128 registers): measured best on
+    // B200 against 3 / 4 CTAs and a 16-gather variant (profiles/r1_variants.txt)
+    return gen->code_bytes == 1 ? launch_selld<EPI, 1>(gen, m, x, e) : launch_selld<EPI, 2>(gen, m, x, e);
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};

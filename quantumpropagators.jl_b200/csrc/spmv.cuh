@@ -452,6 +452,170 @@ k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const do
 }
 
 // ---------------------------------------------------------------------------------------
+// SELL-D (dictionary-compressed SELL-32), batch == 1: thread per row, warp per slice.
+// The matrix stream shrinks from 20 B to 1-2 B per entry, so the kernel is bounded by the
+// five vector streams (80 B/row) and the x gathers (L1/L2), not by the matrix.  The table,
+// pre-multiplied by this step's operator coefficients (u_l * value), lives in shared memory:
+// per entry one code extract, two shared-memory lookups (offset, value), one gather, 4 DFMA.
+// CTA c owns a contiguous slice range (keeps the near gathers of neighbouring slices in L1).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// streaming vector accesses of the SELL-D kernel: v_{k-1}[row], psi[row] are touched exactly once
+// per launch, so they must not displace the x lines that neighbouring slices gather from L1
+__device__ __forceinline__ double2 ld_noalloc(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// NG groups of 8 codes taken from the 32-bit words w[]: all 8*NG gathers are issued before the
+// first one is consumed
+template <int CB, int NG>
+__device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* __restrict__ s_val,
+                                             const int32_t* __restrict__ s_delta,
+                                             const double2* __restrict__ xbase, double& sr, double& si) {
+  constexpr int NC = 8 * NG;
+  uint32_t code[NC];
+  double2 xv[NC];
+#pragma unroll
+  for (int t = 0; t < NC; ++t)
+    code[t] = CB == 1 ? (w[t >> 2] >> (8 * (t & 3))) & 0xffu : (w[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+#pragma unroll
+  for (int t = 0; t < NC; ++t) xv[t] = __ldg(xbase + s_delta[code[t]]);
+#pragma unroll
+  for (int t = 0; t < NC; ++t) {
+    const double2 v = s_val[code[t]];
+    sr += v.x * xv[t].x - v.y * xv[t].y;
+    si += v.x * xv[t].y + v.y * xv[t].x;
+  }
+}
+
+// one 16-byte word of codes: 8 gathers in flight at a time (16 at once was slower on B200:
+// the extra registers cost more latency hiding than the deeper queue buys)
+template <int CB>
+__device__ __forceinline__ void selld_word(const uint4& c, const double2* __restrict__ s_val,
+                                           const int32_t* __restrict__ s_delta,
+                                           const double2* __restrict__ xbase, double& sr, double& si) {
+  const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+  if (CB == 1) {
+    selld_groups<1, 1>(w, s_val, s_delta, xbase, sr, si);
+    if ((w[2] | w[3]) != 0u) selld_groups<1, 1>(w + 2, s_val, s_delta, xbase, sr, si);  // not all padding
+  } else {
+    selld_groups<2, 1>(w, s_val, s_delta, xbase, sr, si);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* __restrict__ x, int64_t row,
+                                               double2& xr, double2& yv, double2& av) {
+  xr = yv = av = make_double2(0.0, 0.0);
+  if (EPI == EPI_MUL) {
+    if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + row);
+    return;
+  }
+  xr = __ldg(x + row);  // allocates in L1: neighbouring rows gather it
+  if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
+    yv = ld_noalloc(e.y + row);
+    av = ld_noalloc(e.acc + row);
+  }
+}
+
+template <int EPI, int CB>
+__global__ void __launch_bounds__(256, 2)
+k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
+             int slices_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* s_val = reinterpret_cast<double2*>(smem_raw);
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
+  for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
+    s_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
+    s_delta[j] = m.ddelta[j];
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
+  const int64_t s_begin = (int64_t)blockIdx.x * slices_per_cta;
+  int64_t s_end = s_begin + slices_per_cta;
+  if (s_end > n_slices) s_end = n_slices;
+  double dr = 0, di = 0, nn = 0;
+
+  // software pipeline over the warp's slices: the first code word and the epilogue operands of
+  // the NEXT slice are requested before the current slice's gathers are consumed
+  uint32_t n_off0 = 0, n_off1 = 0;
+  uint4 n_c = make_uint4(0u, 0u, 0u, 0u);
+  double2 n_xr, n_yv, n_av;
+  n_xr = n_yv = n_av = make_double2(0.0, 0.0);
+  auto prefetch = [&](int64_t s) {
+    if (m.uniform_words) {
+      n_off0 = (uint32_t)s * m.uniform_words;
+      n_off1 = n_off0 + m.uniform_words;
+    } else {
+      n_off0 = m.sptr[s];
+      n_off1 = m.sptr[s + 1];
+    }
+    if (n_off0 < n_off1) n_c = ld_stream(m.codes + n_off0 + lane);
+    const int64_t row = s * QP_SELL_C + lane;
+    if (row < m.n) selld_epi_load<EPI>(e, x, row, n_xr, n_yv, n_av);
+  };
+  int64_t s = s_begin + warp;
+  if (s < s_end) prefetch(s);
+  while (s < s_end) {
+    const int64_t row = s * QP_SELL_C + lane;
+    const bool live = row < m.n;
+    const double2* xbase = x + (live ? row : m.n - 1);  // dead lanes hold padding codes only
+    uint32_t off = n_off0 + lane;
+    const uint32_t off1 = n_off1;
+    uint4 c = n_c;
+    const double2 xr = n_xr, yv = n_yv, av = n_av;
+    const bool any = n_off0 < n_off1;
+    const int64_t s_next = s + nwarps;
+    if (s_next < s_end) prefetch(s_next);
+    double sr = 0.0, si = 0.0;
+    if (any) {
+      for (;;) {
+        const uint32_t off_n = off + QP_SELL_C;
+        const bool more = off_n < off1;
+        uint4 c_n = c;
+        if (more) c_n = ld_stream(m.codes + off_n);  // look one word ahead
+        selld_word<CB>(c, s_val, s_delta, xbase, sr, si);
+        if (!more) break;
+        c = c_n;
+        off = off_n;
+      }
+    }
+    if (m.n_diag > 0 && live) {  // explicit diagonals: hx += sum_i u_i d_i[row] x[row]
+      const double2 xs = EPI == EPI_MUL ? __ldg(x + row) : xr;
+      double2 d = make_double2(0.0, 0.0);
+      for (int i = 0; i < m.n_diag; ++i) {
+        const double2 t = cmul2(coef[(m.diag_ops >> (4 * i)) & 15ull], ld_stream(m.diag + (int64_t)i * m.n + row));
+        d.x += t.x;
+        d.y += t.y;
+      }
+      sr += d.x * xs.x - d.y * xs.y;
+      si += d.x * xs.y + d.y * xs.x;
+    }
+    if (live) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
+    s = s_next;
+  }
+  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) {
+      dr += __shfl_xor_sync(0xffffffffu, dr, o);
+      di += __shfl_xor_sync(0xffffffffu, di, o);
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // merged CSR, trajectory-batched: thread per (row, b); state layout [N][B]
 // coef layout [n_ops][coef_stride ? B : 1]
 // ---------------------------------------------------------------------------------------
@@ -486,6 +650,123 @@ k_spmm_csr(MatView m, const double2* __restrict__ coef, int coef_stride, int64_t
   double dr = 0, di = 0, nn = 0;
   epilogue<EPI>(e, x, idx, idx, make_double2(sr, si), dr, di, nn);
   if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) chk_flush(e, b, dr, di, nn);
+}
+
+// ---------------------------------------------------------------------------------------
+// SELL-D, trajectory-batched: warp per (row, chunk of 32 trajectories); state layout [N][B].
+// Every lane of a warp works on the same matrix row, so the code stream, the table lookups,
+// the operator changes and the real/imaginary/complex kind of an entry are all warp-uniform:
+// the gathers are 512 B contiguous, a purely real or imaginary entry costs 2 DFMA instead of
+// 4, and the per-trajectory coefficient u_l^(b) is applied once per operator and row (entries
+// of a row are stored operator by operator).  The grid runs all row blocks of one trajectory
+// chunk before the next chunk (blockIdx.x = row block), so the chunk's slice of x
+// (N x 32 x 16 B) stays in L2 while the rows sweep over it and every gather after the first
+// is an L2 hit -- HBM traffic stays at the algorithmic 80 B per (row, trajectory).
+// CTA = one slice of 32 rows; warp w takes rows w, w+8, w+16, w+24.
+// ---------------------------------------------------------------------------------------
+template <int EPI, int CB>
+__global__ void __launch_bounds__(256, 2)
+k_spmm_selld(DictView m, const double2* __restrict__ coef, int coef_stride, int64_t batch,
+             const double2* __restrict__ x, EpiArgs e, int n_ops) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* s_val = reinterpret_cast<double2*>(smem_raw);
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
+  uint8_t* s_op = reinterpret_cast<uint8_t*>(s_delta + m.n_dict);
+  for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
+    s_val[j] = m.dval[j];
+    s_delta[j] = m.ddelta[j];
+    s_op[j] = m.dop[j];
+  }
+  __syncthreads();
+
+  constexpr int CPW = 16 / CB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t slice = blockIdx.x;
+  const int64_t b = (int64_t)blockIdx.y * 32 + lane;
+  const bool blive = b < batch;
+  const int64_t bb = blive ? b : batch - 1;
+  uint32_t off0, off1;
+  if (m.uniform_words) {
+    off0 = (uint32_t)slice * m.uniform_words;
+    off1 = off0 + m.uniform_words;
+  } else {
+    off0 = m.sptr[slice];
+    off1 = m.sptr[slice + 1];
+  }
+  // this trajectory's coefficients (n_ops <= 16 would cost 32 registers: keep them in L1/L2)
+  const double2* __restrict__ ucol = coef + (coef_stride ? bb : 0);
+  const int64_t ustride = coef_stride ? batch : 1;
+
+  double dr = 0, di = 0, nn = 0;
+  for (int rl = warp; rl < QP_SELL_C; rl += 8) {
+    const int64_t row = slice * QP_SELL_C + rl;
+    if (row >= m.n) break;
+    const int64_t idx = row * batch + bb;
+    double2 xr, yv, av;
+    epi_load<EPI>(e, x, idx, idx, xr, yv, av);
+    const double2* __restrict__ xb = x + idx;  // x[(row + delta) * batch + b] = xb[delta * batch]
+    double tr = 0.0, ti = 0.0;                 // sum over all operators
+    double pr = 0.0, pi = 0.0;                 // partial sum of the current operator
+    int cur_op = -1;
+    for (uint32_t off = off0 + rl; off < off1; off += QP_SELL_C) {
+      const uint4 c = __ldg(m.codes + off);    // same word for all lanes: one broadcast load
+      const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int h = 0; h < CPW; h += 8) {
+        uint32_t code[8];
+        double2 xv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int tt = h + t;
+          code[t] = CB == 1 ? (w[tt >> 2] >> (8 * (tt & 3))) & 0xffu : (w[tt >> 1] >> (16 * (tt & 1))) & 0xffffu;
+        }
+        if (CB == 1 && h == 8 && (w[2] | w[3]) == 0u) break;  // all padding (warp-uniform)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xv[t] = __ldg(xb + (int64_t)s_delta[code[t]] * batch);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (code[t] == 0u) continue;  // padding
+          const int op = s_op[code[t]];
+          if (op != cur_op) {           // warp-uniform: fold the finished operator
+            if (cur_op >= 0) {
+              const double2 u = __ldg(ucol + cur_op * ustride);
+              tr += u.x * pr - u.y * pi;
+              ti += u.x * pi + u.y * pr;
+            }
+            cur_op = op;
+            pr = pi = 0.0;
+          }
+          const double2 v = s_val[code[t]];
+          if (v.y == 0.0) {             // real entry: 2 DFMA
+            pr += v.x * xv[t].x;
+            pi += v.x * xv[t].y;
+          } else if (v.x == 0.0) {      // imaginary entry: 2 DFMA
+            pr -= v.y * xv[t].y;
+            pi += v.y * xv[t].x;
+          } else {
+            pr += v.x * xv[t].x - v.y * xv[t].y;
+            pi += v.x * xv[t].y + v.y * xv[t].x;
+          }
+        }
+      }
+    }
+    if (cur_op >= 0) {
+      const double2 u = __ldg(ucol + cur_op * ustride);
+      tr += u.x * pr - u.y * pi;
+      ti += u.x * pi + u.y * pr;
+    }
+    if (m.n_diag > 0) {  // explicit diagonals (warp-uniform matrix element, per-trajectory u)
+      const double2 xs = EPI == EPI_MUL ? __ldg(x + idx) : xr;
+      for (int i = 0; i < m.n_diag; ++i) {
+        const double2 u = __ldg(ucol + (int64_t)((m.diag_ops >> (4 * i)) & 15ull) * ustride);
+        const double2 t = cmul2(u, __ldg(m.diag + (int64_t)i * m.n + row));
+        tr += t.x * xs.x - t.y * xs.y;
+        ti += t.x * xs.y + t.y * xs.x;
+      }
+    }
+    if (blive) epi_apply<EPI>(e, idx, make_double2(tr, ti), xr, yv, av, dr, di, nn);
+  }
+  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr && blive) chk_flush(e, b, dr, di, nn);
 }
 
 // ---------------------------------------------------------------------------------------

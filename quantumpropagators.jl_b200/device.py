@@ -128,6 +128,11 @@ class DeviceGenerator:
         self.stored_entries = stored.value
         self.matrix_bytes = mbytes.value
         self.shape = (self.n, self.n)
+        sb, nd, cb = C.c_int64(), C.c_int32(), C.c_int32()
+        L.check(lib.qp_gen_storage(h, C.byref(sb), C.byref(nd), C.byref(cb)), ctx.handle)
+        self.stored_bytes = sb.value  # matrix bytes one application actually streams
+        self.n_dict = nd.value  # SELL-D: table entries (0 otherwise)
+        self.code_bytes = cb.value
 
     def _coeffs(self, coeffs):
         c = L.as_c128_array(coeffs if coeffs is not None else [])

@@ -105,6 +105,101 @@ def test_operator_mul(qp, ctx, fmt, layout, n, density):
     assert abs(gen.dot(dy0, dx, coeffs) - np.vdot(y0, dense @ x)) < 1e-12 * n
 
 
+def _structured_ops(rng, n, n_vals, offsets):
+    """Operators with few distinct (value, column - row) pairs: band matrices whose entries are
+    drawn from a table of `n_vals` complex values -- the structure SELL-D compresses."""
+    table = rng.standard_normal(n_vals) + 1j * rng.standard_normal(n_vals)
+    ops = []
+    for offs in offsets:
+        rows, cols, vals = [], [], []
+        for d in offs:
+            r = np.arange(max(0, -d), min(n, n - d))
+            keep = rng.random(r.size) < 0.8  # ragged rows, some rows empty
+            r = r[keep]
+            rows.append(r)
+            cols.append(r + d)
+            vals.append(table[rng.integers(0, n_vals, r.size)])
+        A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+        A.sort_indices()
+        ops.append(A)
+    return ops
+
+
+@pytest.mark.parametrize("n,n_vals", [(33, 3), (1000, 20), (4099, 200), (5000, 400)])
+def test_operator_mul_selld(qp, ctx, n, n_vals):
+    """Dictionary-compressed storage: 8-bit (< 256 entries) and 16-bit codes, ragged and empty
+    rows, N not a multiple of the slice height; exact same mul! as the uncompressed formats."""
+    rng = np.random.default_rng(n + n_vals)
+    offsets = [[0], [-7, 1, 2, 64], [-n // 2, -1, 3, n // 3]]
+    ops = _structured_ops(rng, n, n_vals, offsets)
+    coeffs = [0.7 - 0.2j, -1.3]
+    gen = qp.DeviceGenerator(ctx, ops, 2, "selld")
+    assert gen.format == "selld"
+    ref_gen = qp.DeviceGenerator(ctx, ops, 2, "csr")
+    dense = ops[0].toarray() + coeffs[0] * ops[1].toarray() + coeffs[1] * ops[2].toarray()
+    x, y0 = rand_state(rng, n), rand_state(rng, n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+        dy = qp.DeviceState.from_host(ctx, y0)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), beta * y0 + alpha * (dense @ x)) < 1e-13
+        dz = qp.DeviceState.from_host(ctx, y0)
+        ref_gen.mul(dz, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), dz.to_host()) < 1e-14
+
+
+@pytest.mark.parametrize("B", [1, 33])
+def test_selld_explicit_diagonal(qp, ctx, B):
+    """A diagonal drift with thousands of distinct energies on top of few-valued couplings (the
+    transmon-chain shape): the diagonals are kept as explicit vectors, everything else is coded."""
+    rng = np.random.default_rng(77 + B)
+    n = 6000
+    D0 = sp.diags(rng.standard_normal(n) + 0j, 0, format="csr")          # n distinct values
+    D2 = sp.diags(rng.standard_normal(n) * (1 + 0.5j), 0, format="csr")   # controlled op with a diagonal too
+    band = _structured_ops(rng, n, 6, [[-9, -1, 1, 9, 500]])[0]
+    ops = [D0 + band, band.conj().T.tocsr(), D2]
+    coeffs = [0.3 + 0.1j, -0.8]
+    gen = qp.DeviceGenerator(ctx, ops, 2, "selld" if B == 1 else "auto")
+    assert gen.n_dict > 0
+    dense = sum(c * A for c, A in zip([1.0] + coeffs, ops)).tocsr()
+    X, Y = rand_state(rng, n, None if B == 1 else B), rand_state(rng, n, None if B == 1 else B)
+    dx = qp.DeviceState.from_host(ctx, X)
+    for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+        dy = qp.DeviceState.from_host(ctx, Y)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), beta * Y + alpha * (dense @ X)) < 1e-13
+
+
+def test_selld_refuses_incompressible(qp, ctx):
+    """More than 4095 distinct entries: forcing the format is an error, AUTO falls back."""
+    rng = np.random.default_rng(8)
+    A = rand_sparse(rng, 2000, 0.01)
+    with pytest.raises(qp.QPropError, match="distinct"):
+        qp.DeviceGenerator(ctx, [A], 0, "selld")
+    assert qp.DeviceGenerator(ctx, [A], 0).format == "csr"
+
+
+@pytest.mark.parametrize("n,n_vals,B", [(100, 5, 16), (1000, 300, 33), (333, 40, 70)])
+def test_operator_mul_batched_selld(qp, ctx, n, n_vals, B):
+    """Trajectory-batched dictionary kernel (B >= 16, AUTO format): real, imaginary and complex
+    entries, 8- and 16-bit codes, partial trajectory chunks."""
+    rng = np.random.default_rng(n + B)
+    offsets = [[0], [-7, 1, 2, 64], [-n // 2, -1, 3, n // 3]]
+    ops = _structured_ops(rng, n, n_vals, offsets)
+    ops[0] = sp.csr_matrix(ops[0].real.astype(complex))   # purely real operator
+    ops[1] = sp.csr_matrix(1j * ops[1].imag)              # purely imaginary operator
+    coeffs = [0.7 - 0.2j, -1.3]
+    gen = qp.DeviceGenerator(ctx, ops, 2)
+    assert gen.n_dict > 0
+    dense = ops[0].toarray() + coeffs[0] * ops[1].toarray() + coeffs[1] * ops[2].toarray()
+    X, Y = rand_state(rng, n, B), rand_state(rng, n, B)
+    dx = qp.DeviceState.from_host(ctx, X)
+    for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+        dy = qp.DeviceState.from_host(ctx, Y)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), beta * Y + alpha * (dense @ X)) < 1e-13
+
+
 def test_operator_mul_batched(qp, ctx):
     rng = np.random.default_rng(5)
     n, B = 300, 6
@@ -201,7 +296,7 @@ def test_cheby_tfim_vs_oracle_and_expm(qp, ctx, n_spins):
     w = qp.workloads.config2_tfim(n_spins, nt=11, dt=0.1)
     kw = dict(E_min=w["E_min"], E_max=w["E_max"])
     ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "cheby", **kw)
-    for fmt in ("csr", "sell"):
+    for fmt in ("csr", "sell", "selld"):
         gen = _product_generator(qp, w["ops"], w["controls"])
         p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, matrix_format=fmt, **kw)
         assert p.wrk.gen.format == fmt
@@ -217,12 +312,13 @@ def test_cheby_tfim_vs_oracle_and_expm(qp, ctx, n_spins):
     assert rel(out, psi) < 1e-9
 
 
-def test_cheby_batched_per_trajectory(qp, ctx):
-    """Ensemble: B trajectories with their own control scale share one coefficient table."""
+@pytest.mark.parametrize("B", [5, 40])
+def test_cheby_batched_per_trajectory(qp, ctx, B):
+    """Ensemble: B trajectories with their own control scale share one coefficient table
+    (B = 5: merged-CSR SpMM kernel, B = 40: dictionary SpMM kernel)."""
     rng = np.random.default_rng(3)
-    w = qp.workloads.config3_transmon(n_sites=3, levels=3, B=5, nt=9, dt=0.5)
+    w = qp.workloads.config3_transmon(n_sites=3, levels=3, B=B, nt=9, dt=0.5)
     H0, H1, H2 = w["ops"]
-    B = 5
     tl = w["tlist"]
     dt = tl[1] - tl[0]
     psi0 = rand_state(rng, H0.shape[0], B)
@@ -293,6 +389,54 @@ def test_cheby_dense_random_hermitian(qp, ctx):
     wrk = qp.ChebyWrk(st, gen, ev[-1] - ev[0], ev[0], dt)
     qp.cheby_(st, None, dt, wrk, coeffs=[])
     assert np.linalg.norm(st.to_host() - expected) < 1e-10
+
+
+@pytest.mark.parametrize("N,B", [(64, 2), (203, 5), (203, 9), (130, 17), (301, 40), (97, 70), (256, 64)])
+def test_dense_batched_dmma_mul(qp, ctx, N, B):
+    """Dense generators on a batch of states (FP64 tensor-core kernel): mul! with two operators,
+    shared coefficients; N and B not multiples of the tile sizes."""
+    rng = np.random.default_rng(N * 7 + B)
+    H0 = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    H1 = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    gen = qp.DeviceGenerator(ctx, [H0, H1], 1)
+    assert gen.format == "dense"
+    X, Y = rand_state(rng, N, B), rand_state(rng, N, B)
+    dx = qp.DeviceState.from_host(ctx, X)
+    for alpha, beta in ((1.0, 0.0), (0.3 - 2j, -1.5)):
+        dy = qp.DeviceState.from_host(ctx, Y)
+        gen.mul(dy, dx, [0.4 - 0.9j], alpha, beta)
+        ref = beta * Y + alpha * ((H0 + (0.4 - 0.9j) * H1) @ X)
+        assert rel(dy.to_host(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("B", [3, 16, 33])
+def test_cheby_dense_batched_per_trajectory(qp, ctx, B):
+    """BASELINE config 5 shape at reduced size: dense Hermitian H0 + u_b H1 on B states, each
+    trajectory with its own control amplitude; every column against the oracle's cheby!."""
+    rng = np.random.default_rng(60 + B)
+    N = 150
+    A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    C = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    H0, H1 = (A + A.conj().T) / 2, (C + C.conj().T) / 2
+    u = rng.uniform(-1, 1, (1, B))
+    bound = np.linalg.norm(H0, 2) + np.linalg.norm(H1, 2)
+    Delta, E_min, dt = 2 * bound, -bound, 0.05
+    psi0 = rand_state(rng, N, B)
+    st = qp.DeviceState.from_host(ctx, psi0)
+    gen = qp.DeviceGenerator(ctx, [H0, H1], 1)
+    wrk = qp.ChebyWrk(st, gen, Delta, E_min, dt)
+    owrk = O.ChebyWrk(psi0[:, 0].copy(), Delta, E_min, dt)
+    ref = psi0.copy()
+    for _ in range(3):
+        qp.cheby_(st, None, dt, wrk, coeffs=u, per_trajectory=True, check_normalization=True)
+        for b in range(B):
+            col = ref[:, b].copy()
+            O.cheby_inplace(col, O.Operator([H0, H1], [u[0, b]]), dt, owrk)
+            ref[:, b] = col
+    out = st.to_host()
+    for b in range(B):
+        assert rel(out[:, b], ref[:, b]) < RTOL
+        assert abs(np.linalg.norm(out[:, b]) - 1) < 1e-12
 
 
 # ---------------------------------------------------------------------------------------
