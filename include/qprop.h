@@ -149,6 +149,10 @@ int32_t qp_gen_mul(qp_gen_t gen, const qp_c128* coeffs, qp_c128 alpha, qp_c128 b
 int32_t qp_gen_dot(qp_gen_t gen, const qp_c128* coeffs, qp_state_t x, qp_state_t y,
                    qp_c128* out /*[batch]*/);
 
+/* out[b] = <x_b| sum_l c_l H_l |x_b> in one fused pass (no temporary, no stored H x):
+ * expectation values of matrix observables, src/storage.jl:100-123 */
+int32_t qp_gen_expval(qp_gen_t gen, const qp_c128* coeffs, qp_state_t x, qp_c128* out /*[batch]*/);
+
 /* ------------------------------------------------------------------ Chebyshev
  * Replaces: ChebyWrk (src/cheby.jl:87-124) and cheby! (src/cheby.jl:150-213).  The
  * coefficient table a_k comes from the host (cheby_coeffs, src/cheby.jl:25-39). */
@@ -167,6 +171,20 @@ int32_t qp_cheby_set_coeffs(qp_cheby_t wrk, const double* a, int32_t n_a, double
  *   check_normalization: src/cheby.jl:194-200; failing returns QP_ERR_NORMALIZATION. */
 int32_t qp_cheby_step(qp_cheby_t wrk, qp_state_t st, const qp_c128* op_coeffs,
                       int32_t coeffs_per_traj, double dt_signed, int32_t check_normalization);
+/* The step loop of propagate (src/propagate.jl:283-344) in ONE call: n_steps consecutive
+ * prop_step!s with the amplitudes of every interval given up front (the caller opts in to
+ * this: nothing can change `parameters` between the steps of one propagate call without a
+ * callback), and -- instead of downloading the state for storage -- the expectation values
+ * <psi|O_k|psi> of n_obs observables (generators without free coefficients; matrix
+ * observables, src/storage.jl:100-123) and the norms recorded on the device before the first
+ * and after every step.
+ *   coeff_table: [n_steps][n_coeffs] (coeffs_per_traj == 0) or [n_steps][n_coeffs][batch]
+ *   expvals:     [n_steps + 1][n_obs][batch] or NULL when n_obs == 0
+ *   norms:       [n_steps + 1][batch] or NULL
+ * No host synchronisation happens between the steps. */
+int32_t qp_cheby_propagate(qp_cheby_t wrk, qp_state_t st, const qp_c128* coeff_table,
+                           int32_t coeffs_per_traj, int32_t n_steps, double dt_signed, int32_t n_obs,
+                           const qp_gen_t* observables, qp_c128* expvals, double* norms);
 /* algorithmic bytes of one prop_step! as defined in SURVEY.md §8d:
  * (n_a - 1) * (M + 80 N B) */
 int32_t qp_cheby_step_bytes(qp_cheby_t wrk, int64_t* bytes);

@@ -27,7 +27,7 @@ from .generators import (  # noqa: F401
     evaluate_,
     get_controls,
 )
-from .cheby import cheby_coeffs, cheby_coeffs_, ChebyWrk, cheby_, cheby  # noqa: F401
+from .cheby import cheby_coeffs, cheby_coeffs_, ChebyWrk, cheby_, cheby, cheby_propagate_  # noqa: F401
 from .newton import (  # noqa: F401
     KrylovWrk,
     NewtonWrk,

@@ -102,6 +102,8 @@ SIGNATURES = {
     "qp_cheby_destroy": (_i32, [_vp]),
     "qp_cheby_set_coeffs": (_i32, [_vp, _vp, _i32, _f64, _f64, _f64, _f64]),
     "qp_cheby_step": (_i32, [_vp, _vp, _vp, _i32, _f64, _i32]),
+    "qp_cheby_propagate": (_i32, [_vp, _vp, _vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp]),
+    "qp_gen_expval": (_i32, [_vp, _vp, _vp, _vp]),
     "qp_cheby_step_bytes": (_i32, [_vp, _P(_i64)]),
     "qp_krylov_create": (_i32, [_vp, _vp, _i32, _P(_vp)]),
     "qp_krylov_destroy": (_i32, [_vp]),

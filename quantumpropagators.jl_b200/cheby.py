@@ -15,7 +15,7 @@ from . import _lib as L
 from .device import DeviceGenerator, DeviceState
 from .generators import Generator, Operator, ScaledOperator, _as_operator
 
-__all__ = ["cheby_coeffs", "cheby_coeffs_", "ChebyWrk", "cheby_", "cheby"]
+__all__ = ["cheby_propagate_", "cheby_coeffs", "cheby_coeffs_", "ChebyWrk", "cheby_", "cheby"]
 
 
 def cheby_coeffs(Delta, dt, limit=1e-12) -> np.ndarray:
@@ -121,6 +121,42 @@ def cheby_(Psi: DeviceState, H, dt, wrk: ChebyWrk, check_normalization=False, co
         wrk.ctx.handle,
     )
     return Psi
+
+
+def cheby_propagate_(Psi: DeviceState, wrk: ChebyWrk, coeff_table, dt, observables=(), norms=False,
+                     per_trajectory=False):
+    """The step loop of ``propagate`` (reference ``src/propagate.jl:283-344``) in one library
+    call (``qp_cheby_propagate``): ``coeff_table[s]`` holds the operator coefficients of step
+    ``s`` (shape ``[n_steps][n_coeffs]``, or ``[n_steps][n_coeffs][B]`` with ``per_trajectory``).
+    ``observables`` are :class:`DeviceGenerator` objects without free coefficients whose
+    expectation values are recorded on the device before the first and after every step.
+
+    Returns ``(expvals, norms)``: ``expvals[s, k(, b)]`` complex, ``norms[s(, b)]`` float (``None``
+    when not requested)."""
+    n_c = wrk.gen.n_coeffs
+    B = Psi.batch
+    tbl = L.as_c128_array(coeff_table)
+    n_steps = tbl.shape[0] if tbl.ndim > 1 or n_c > 0 else int(tbl.size)
+    want = (n_steps, n_c, B) if per_trajectory else (n_steps, n_c)
+    if n_c == 0:
+        tbl = np.zeros(want, dtype=np.complex128)
+    if tbl.shape != want:
+        raise ValueError(f"coefficient table must have shape {want}, got {tbl.shape}")
+    obs = list(observables)
+    arr = (C.c_void_p * max(len(obs), 1))(*[o.handle for o in obs])
+    ev = np.zeros((n_steps + 1, len(obs), B), dtype=np.complex128) if obs else None
+    nr = np.zeros((n_steps + 1, B), dtype=np.float64) if norms else None
+    L.check(
+        wrk.ctx._lib.qp_cheby_propagate(
+            wrk.handle, Psi.handle, L.ptr(tbl), 1 if per_trajectory else 0, int(n_steps), float(dt), len(obs),
+            arr if obs else None, L.ptr(ev) if obs else None, L.ptr(nr) if norms else None,
+        ),
+        wrk.ctx.handle,
+    )
+    if B == 1:
+        ev = ev[:, :, 0] if ev is not None else None
+        nr = nr[:, 0] if nr is not None else None
+    return ev, nr
 
 
 def cheby(Psi: DeviceState, H, dt, wrk: ChebyWrk, **kwargs) -> DeviceState:

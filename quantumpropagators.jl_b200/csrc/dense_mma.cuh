@@ -15,6 +15,9 @@
 // (8 trajectories); K tile: 16 complex per stage, STAGES-deep cp.async pipeline running
 // seamlessly across the operators of the lazy sum (the coefficient u_l -- per trajectory in
 // ensemble mode -- is applied to the X fragment, so one accumulator set serves all operators).
+// KS warp groups split every K tile between them (same output tile, partial sums added through
+// shared memory at the end): the DMMA pipe needs ~4 warps per scheduler to stay busy, and the
+// row count of the operator (8192 / 148 SMs = 56 rows per CTA) leaves no other way to get them.
 #pragma once
 
 #include "spmv.cuh"
@@ -39,10 +42,10 @@ constexpr int DM_KC = 16;       // complex K elements per stage
 constexpr int DM_STAGES = 3;
 constexpr int DM_A_STRIDE = 40;  // doubles per staged A row (32 + 8: rows 64 B apart mod 128 B)
 
-template <int WM, int WN, int MT>
+template <int WM, int WN, int MT, int NQ>
 struct DenseTile {
   static constexpr int ROWS = WM * MT * 8;
-  static constexpr int TRAJ = WN * 8;
+  static constexpr int TRAJ = WN * NQ * 4;
   static constexpr int X_STRIDE = TRAJ + 1;  // complex per staged X row (rows 16 B apart mod 128 B)
   static constexpr size_t A_BYTES = (size_t)ROWS * DM_A_STRIDE * sizeof(double);
   static constexpr size_t X_BYTES = (size_t)DM_KC * X_STRIDE * sizeof(double2);
@@ -50,16 +53,17 @@ struct DenseTile {
   static constexpr size_t SMEM = STAGE_BYTES * DM_STAGES + sizeof(double2) * QP_MAX_OPS * TRAJ;
 };
 
-template <int EPI, int WM, int WN, int MT>
-__global__ void __launch_bounds__(WM * WN * 32, 1)
+template <int EPI, int WM, int WN, int MT, int NQ, int KS>
+__global__ void __launch_bounds__(WM * WN * KS * 32, 1)
 k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const double2* __restrict__ coef,
              int coef_stride, int64_t batch, const double2* __restrict__ x, EpiArgs e) {
-  using T = DenseTile<WM, WN, MT>;
-  constexpr int THREADS = WM * WN * 32;
+  using T = DenseTile<WM, WN, MT, NQ>;
+  constexpr int THREADS = WM * WN * KS * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_coef = reinterpret_cast<double2*>(smem_raw + T::STAGE_BYTES * DM_STAGES);  // [n_ops][TRAJ]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ks = (tid >> 5) / (WM * WN), warp = (tid >> 5) % (WM * WN);  // K group, warp within the tile
   const int wm = warp / WN, wn = warp % WN;
   const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)blockIdx.x * T::ROWS;
@@ -102,18 +106,20 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
     cp_async_commit();
   };
 
-  double acc[MT][2][2];
+  double acc[MT][NQ][2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+    for (int q = 0; q < NQ; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < DM_STAGES - 1; ++s) load_stage(s, s);
 
   const int cpar = g & 1;              // this lane's B column is the (re | im) part of its trajectory
-  const int bt = wn * 8 + (g >> 1);    // B-side trajectory of n8-tile 0 (tile 1: +4)
-  double2 u[2] = {make_double2(1.0, 0.0), make_double2(1.0, 0.0)};
+  const int bt = wn * NQ * 4 + (g >> 1);  // B-side trajectory of n8-tile 0 (tile q: +4q)
+  double2 u[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) u[q] = make_double2(1.0, 0.0);
   int cur_op = -1;
 
   for (int it = 0; it < total_it; ++it) {
@@ -124,20 +130,20 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
     const int l = it / KT;
     if (l != cur_op) {
       cur_op = l;
-      u[0] = s_coef[l * T::TRAJ + bt];
-      u[1] = s_coef[l * T::TRAJ + bt + 4];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) u[q] = s_coef[l * T::TRAJ + bt + 4 * q];
     }
     const double* As = stage_A(it % DM_STAGES) + (wm * MT * 8 + g) * DM_A_STRIDE + 2 * t;
     const double2* Xs = stage_X(it % DM_STAGES) + t * T::X_STRIDE + bt;
 #pragma unroll
-    for (int jp = 0; jp < DM_KC / 4; ++jp) {
+    for (int jp = ks; jp < DM_KC / 4; jp += KS) {
       double2 a[MT];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
         a[i] = *reinterpret_cast<const double2*>(As + i * 8 * DM_A_STRIDE + 8 * jp);
-      double be[2], bo[2];
+      double be[NQ], bo[NQ];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         const double2 z = cmul2(u[q], Xs[jp * 4 * T::X_STRIDE + q * 4]);
         be[q] = cpar ? z.y : z.x;   // K = real part of H:  [Xr | Xi]
         bo[q] = cpar ? z.x : -z.y;  // K = imag part of H:  [-Xi | Xr]
@@ -145,54 +151,83 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          dmma884(acc[i][q][0], acc[i][q][1], a[i].x, be[q]);
-          dmma884(acc[i][q][0], acc[i][q][1], a[i].y, bo[q]);
-        }
+        for (int q = 0; q < NQ; ++q) dmma884(acc[i][q][0], acc[i][q][1], a[i].x, be[q]);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) dmma884(acc[i][q][0], acc[i][q][1], a[i].y, bo[q]);
     }
   }
   cp_async_wait<0>();
+  if (KS > 1) {  // add the K groups' partial sums through shared memory (the stages are drained)
+    double2* red = reinterpret_cast<double2*>(smem_raw);
+    for (int k = KS - 1; k >= 1; --k) {
+      __syncthreads();
+      if (ks == k) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            red[((warp * MT + i) * NQ + q) * 32 + lane] = make_double2(acc[i][q][0], acc[i][q][1]);
+      }
+      __syncthreads();
+      if (ks == 0) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const double2 p = red[((warp * MT + i) * NQ + q) * 32 + lane];
+            acc[i][q][0] += p.x;
+            acc[i][q][1] += p.y;
+          }
+      }
+    }
+    if (ks != 0) return;
+  }
 
   // fused epilogue: accumulator pair = (re, im) of (row, trajectory)
-  double dr[2] = {0, 0}, di[2] = {0, 0}, nn[2] = {0, 0};
+  double dr[NQ], di[NQ], nn[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) dr[q] = di[q] = nn[q] = 0.0;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     const int64_t row = row0 + (wm * MT + i) * 8 + g;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int64_t b = b0 + wn * 8 + q * 4 + t;
+    for (int q = 0; q < NQ; ++q) {
+      const int64_t b = b0 + wn * NQ * 4 + q * 4 + t;
       if (row < n && b < batch) {
         const int64_t idx = row * batch + b;
         epilogue<EPI>(e, x, idx, idx, make_double2(acc[i][q][0], acc[i][q][1]), dr[q], di[q], nn[q]);
       }
     }
   }
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       // lanes with equal t hold the same trajectory: reduce over g
       for (int o = 4; o < 32; o <<= 1) {
         dr[q] += __shfl_xor_sync(0xffffffffu, dr[q], o);
         di[q] += __shfl_xor_sync(0xffffffffu, di[q], o);
         nn[q] += __shfl_xor_sync(0xffffffffu, nn[q], o);
       }
-      const int64_t b = b0 + wn * 8 + q * 4 + t;
+      const int64_t b = b0 + wn * NQ * 4 + q * 4 + t;
       if (g == 0 && b < batch) chk_flush(e, b, dr[q], di[q], nn[q]);
     }
   }
 }
 
-template <int EPI, int WM, int WN, int MT>
+template <int EPI, int WM, int WN, int MT, int NQ, int KS>
 static int32_t launch_gemm_dense(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
-  using T = DenseTile<WM, WN, MT>;
+  using T = DenseTile<WM, WN, MT, NQ>;
   qp_ctx_t ctx = gen->ctx;
-  auto kern = k_gemm_dense<EPI, WM, WN, MT>;
+  static_assert(sizeof(double2) * WM * WN * MT * NQ * 32 <= T::STAGE_BYTES * DM_STAGES, "reduction buffer");
+  auto kern = k_gemm_dense<EPI, WM, WN, MT, NQ, KS>;
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     ctx->smem_configured.insert((const void*)kern);
   }
   dim3 grid((unsigned)((gen->n + T::ROWS - 1) / T::ROWS), (unsigned)((batch + T::TRAJ - 1) / T::TRAJ));
-  kern<<<grid, WM * WN * 32, T::SMEM, ctx->stream>>>(gen->d_dense_ops, gen->n_ops, gen->n, gen->d_coef, coef_stride,
+  kern<<<grid, WM * WN * KS * 32, T::SMEM, ctx->stream>>>(gen->d_dense_ops, gen->n_ops, gen->n, gen->d_coef, coef_stride,
                                                       batch, x, e);
   QP_LAUNCHED(ctx);
   return QP_OK;
@@ -202,8 +237,14 @@ static int32_t launch_gemm_dense(qp_gen_t gen, int coef_stride, const double2* x
 // every operator element is read from HBM once per application
 template <int EPI>
 static int32_t launch_dense_batched(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
-  if (batch > 32) return launch_gemm_dense<EPI, 1, 8, 7>(gen, coef_stride, x, batch, e);   // 56 rows x 64 traj
-  if (batch > 16) return launch_gemm_dense<EPI, 2, 4, 4>(gen, coef_stride, x, batch, e);   // 64 rows x 32 traj
-  if (batch > 8) return launch_gemm_dense<EPI, 4, 2, 2>(gen, coef_stride, x, batch, e);    // 64 rows x 16 traj
-  return launch_gemm_dense<EPI, 8, 1, 1>(gen, coef_stride, x, batch, e);                   // 64 rows x 8 traj
+  static const int variant = getenv("QPROP_DMMA_VARIANT") ? atoi(getenv("QPROP_DMMA_VARIANT")) : 0;
+  if (batch > 32) {
+    if (variant == 1) return launch_gemm_dense<EPI, 1, 16, 7, 1, 1>(gen, coef_stride, x, batch, e);  // 56 x 64, 16 warps, 7 acc/warp
+    if (variant == 2) return launch_gemm_dense<EPI, 2, 8, 4, 2, 1>(gen, coef_stride, x, batch, e);   // 64 x 64, 16 warps, 8 acc/warp
+    if (variant == 3) return launch_gemm_dense<EPI, 1, 8, 7, 2, 1>(gen, coef_stride, x, batch, e);   // 56 x 64, 8 warps, 14 acc/warp
+    return launch_gemm_dense<EPI, 1, 8, 7, 2, 2>(gen, coef_stride, x, batch, e);                     // 56 x 64, 2 x 8 warps (K split)
+  }
+  if (batch > 16) return launch_gemm_dense<EPI, 2, 4, 4, 2, 2>(gen, coef_stride, x, batch, e);   // 64 rows x 32 traj, 16 warps
+  if (batch > 8) return launch_gemm_dense<EPI, 4, 2, 2, 2, 2>(gen, coef_stride, x, batch, e);    // 64 rows x 16 traj, 16 warps
+  return launch_gemm_dense<EPI, 8, 1, 1, 2, 2>(gen, coef_stride, x, batch, e);                   // 64 rows x 8 traj, 16 warps
 }

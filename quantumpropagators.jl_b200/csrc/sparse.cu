@@ -461,6 +461,7 @@ static void gen_free(qp_gen_t g) {
   cudaFree(g->d_ddelta);
   cudaFree(g->d_dop);
   cudaFree(g->d_diag);
+  cudaFree(g->d_dvalr);
   cudaFree((void*)g->d_dense_ops);
   cudaFree(g->d_coef);
   delete g;
@@ -491,6 +492,8 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
     cudaFree(g->d_ddelta);
     cudaFree(g->d_dop);
     cudaFree(g->d_diag);
+    cudaFree(g->d_dvalr);
+    g->d_dvalr = nullptr;
     g->d_dptr = nullptr;
     g->d_dcodes = nullptr;
     g->d_dval = nullptr;
@@ -562,6 +565,16 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
   }
   const int cb = n_dict <= 256 ? 1 : 2;
   const int cpw = 16 / cb;
+  // operator kinds: purely real / purely imaginary operators let the batched kernel store one
+  // real number per entry (the factor i moves into the coefficient)
+  unsigned has_re = 0, has_im = 0;
+  for (int i = 1; i < n_dict; ++i) {
+    if (h_val[i].x != 0.0) has_re |= 1u << h_op[i];
+    if (h_val[i].y != 0.0) has_im |= 1u << h_op[i];
+  }
+  const bool realv = (has_re & has_im) == 0u;
+  std::vector<double> h_valr(n_dict, 0.0);
+  for (int i = 1; i < n_dict; ++i) h_valr[i] = ((has_im >> h_op[i]) & 1u) ? h_val[i].y : h_val[i].x;
 
   D_CUDA(cudaMalloc(&d_remap, sizeof(uint16_t) * QP_DICT_HASH_CAP));
   D_CUDA(cudaMemcpy(d_remap, h_remap.data(), sizeof(uint16_t) * QP_DICT_HASH_CAP, cudaMemcpyHostToDevice));
@@ -571,6 +584,13 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
   D_CUDA(cudaMemcpy(g->d_dval, h_val.data(), sizeof(double2) * n_dict, cudaMemcpyHostToDevice));
   D_CUDA(cudaMemcpy(g->d_ddelta, h_delta.data(), sizeof(int32_t) * n_dict, cudaMemcpyHostToDevice));
   D_CUDA(cudaMemcpy(g->d_dop, h_op.data(), sizeof(uint8_t) * n_dict, cudaMemcpyHostToDevice));
+  D_CUDA(cudaMalloc(&g->d_dvalr, sizeof(double) * n_dict));
+  D_CUDA(cudaMemcpy(g->d_dvalr, h_valr.data(), sizeof(double) * n_dict, cudaMemcpyHostToDevice));
+  g->dict_realv = realv;
+  g->imag_ops = realv ? has_im : 0u;
+  g->h_dval = h_val;
+  g->h_ddelta = h_delta;
+  g->h_dop = h_op;
 
   // slice widths in 16-byte words
   D_CUDA(cudaMalloc(&d_words, sizeof(uint32_t) * (n_slices + 1)));
@@ -905,6 +925,12 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
     }
   QP_CUDA(ctx, cudaMemcpyAsync(gen->d_coef, h, sizeof(double2) * elems, cudaMemcpyHostToDevice, ctx->stream));
   QP_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
+  // host copy for launchers that fold the coefficients into kernel parameters
+  gen->h_coef = nullptr;
+  if (!per_traj) {
+    for (int l = 0; l < gen->n_ops; ++l) gen->h_coef_buf[l] = make_double2(h[l].re, h[l].im);
+    gen->h_coef = gen->h_coef_buf;
+  }
   if (coef_stride_out) *coef_stride_out = per_traj ? 1 : 0;
   return QP_OK;
 }
@@ -944,11 +970,11 @@ static DictView make_dict_view(qp_gen_t gen) {
 
 // SELL-D kernel: CTAs = SMs x resident CTAs per SM (or fewer for small matrices), each owning a
 // contiguous slice range; dynamic shared memory = the coefficient-scaled table.
-template <int EPI, int CB>
+template <int EPI, int CB, int TC>
 static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
-  auto kern = k_spmv_selld<EPI, CB>;
-  const size_t smem = (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
+  auto kern = k_spmv_selld<EPI, CB, TC>;
+  const size_t smem = TC ? 0 : (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ctx->smem_configured.insert((const void*)kern);
@@ -968,9 +994,48 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   static const int spc_env = getenv("QPROP_SELLD_SPC") ? atoi(getenv("QPROP_SELLD_SPC")) : 0;
   if (spc_env > 0) spc = spc_env;
   ctas = (gen->n_slices + spc - 1) / spc;
-  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc);
+  DictConst tc;
+  if (TC) {  // pre-multiply the table by this step's coefficients on the host (<= 128 entries)
+    for (int j = 0; j < gen->n_dict; ++j) {
+      const double2 u = gen->h_coef[gen->h_dop[j]], v = gen->h_dval[j];
+      tc.val[j] = make_double2(u.x * v.x - u.y * v.y, u.x * v.y + u.y * v.x);
+      tc.delta[j] = gen->h_ddelta[j];
+    }
+  }
+  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc, tc);
   QP_LAUNCHED(ctx);
   return QP_OK;
+}
+
+template <int EPI, int CB, int REALV, int T, int G>
+static int32_t launch_spmm_selld_t(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
+  qp_ctx_t ctx = gen->ctx;
+  const DictView m = make_dict_view(gen);
+  const int64_t chunks = (batch + 32 * T - 1) / (32 * T);
+  if (chunks > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "batch too large for one launch");
+  const size_t smem = ((size_t)gen->n_dict * ((REALV ? 8 : 16) + sizeof(DeltaOp)) + 127) / 128 * 128;
+  auto kern = k_spmm_selld<EPI, CB, REALV, T, G>;
+  if (!ctx->smem_configured.count((const void*)kern)) {
+    QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ctx->smem_configured.insert((const void*)kern);
+  }
+  dim3 grid((unsigned)gen->n_slices, (unsigned)chunks);
+  kern<<<grid, 256, smem, ctx->stream>>>(m, gen->d_dvalr, gen->imag_ops, gen->d_coef, coef_stride, batch, x, e);
+  QP_LAUNCHED(ctx);
+  return QP_OK;
+}
+
+template <int EPI>
+static int32_t launch_spmm_selld(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
+  // two trajectory chunks per lane amortise the row decode (QPROP_SPMM_T=1 forces one)
+  static const int t_env = getenv("QPROP_SPMM_T") ? atoi(getenv("QPROP_SPMM_T")) : 0;
+  const bool two = t_env ? t_env == 2 : batch > 32;
+#define QP_SPMM(CB, RV) \
+  (two ? launch_spmm_selld_t<EPI, CB, RV, 2, 4>(gen, coef_stride, x, batch, e) \
+       : launch_spmm_selld_t<EPI, CB, RV, 1, 8>(gen, coef_stride, x, batch, e))
+  if (gen->code_bytes == 1) return gen->dict_realv ? QP_SPMM(1, 1) : QP_SPMM(1, 0);
+  return gen->dict_realv ? QP_SPMM(2, 1) : QP_SPMM(2, 0);
+#undef QP_SPMM
 }
 
 template <int EPI>
@@ -984,30 +1049,8 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     QP_LAUNCHED(ctx);
     return QP_OK;
   }
-  if (batch >= 16 && gen->n_dict > 0) {  // dictionary available: warp per (row, 32 trajectories)
-    const DictView m = make_dict_view(gen);
-    const int64_t chunks = (batch + 31) / 32;
-    if (chunks > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "batch too large for one launch");
-    const size_t smem = ((size_t)gen->n_dict * 21 + 15) / 16 * 16;
-    dim3 grid((unsigned)gen->n_slices, (unsigned)chunks);
-    if (gen->code_bytes == 1) {
-      auto kern = k_spmm_selld<EPI, 1>;
-      if (!ctx->smem_configured.count((const void*)kern)) {
-        QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ctx->smem_configured.insert((const void*)kern);
-      }
-      kern<<<grid, 256, smem, st>>>(m, gen->d_coef, coef_stride, batch, x, e, gen->n_ops);
-    } else {
-      auto kern = k_spmm_selld<EPI, 2>;
-      if (!ctx->smem_configured.count((const void*)kern)) {
-        QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ctx->smem_configured.insert((const void*)kern);
-      }
-      kern<<<grid, 256, smem, st>>>(m, gen->d_coef, coef_stride, batch, x, e, gen->n_ops);
-    }
-    QP_LAUNCHED(ctx);
-    return QP_OK;
-  }
+  if (batch >= 16 && gen->n_dict > 0)  // dictionary available: warp per (row, 32 T trajectories)
+    return launch_spmm_selld<EPI>(gen, coef_stride, x, batch, e);
   if (batch > 1) {
     MatView m{gen->d_mptr, gen->d_mcolop, gen->d_mval, n};
     int64_t blocks = (n * batch + 255) / 256;
@@ -1020,7 +1063,10 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     const DictView m = make_dict_view(gen);
     // compiled for 2 resident CTAs of 256 threads per SM (<= 128 registers): measured best on
     // B200 against 3 / 4 CTAs and a 16-gather variant (profiles/r1_variants.txt)
-    return gen->code_bytes == 1 ? launch_selld<EPI, 1>(gen, m, x, e) : launch_selld<EPI, 2>(gen, m, x, e);
+    static const bool no_tc = getenv("QPROP_SELLD_NO_CONST") != nullptr;
+    if (gen->code_bytes == 1 && gen->n_dict <= QP_DICT_CONST && gen->h_coef != nullptr && !no_tc)
+      return launch_selld<EPI, 1, 1>(gen, m, x, e);
+    return gen->code_bytes == 1 ? launch_selld<EPI, 1, 0>(gen, m, x, e) : launch_selld<EPI, 2, 0>(gen, m, x, e);
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};
@@ -1077,6 +1123,7 @@ int32_t qp_launch_fused(qp_gen_t gen, int epi, int coef_stride, const double2* x
     case EPI_CHEB_MID: return launch_epi<EPI_CHEB_MID>(gen, coef_stride, x, batch, e);
     case EPI_CHEB_LAST: return launch_epi<EPI_CHEB_LAST>(gen, coef_stride, x, batch, e);
     case EPI_CHEB_ONLY: return launch_epi<EPI_CHEB_ONLY>(gen, coef_stride, x, batch, e);
+    case EPI_DOT: return launch_epi<EPI_DOT>(gen, coef_stride, x, batch, e);
   }
   return qp_fail(gen->ctx, QP_ERR_INTERNAL, "bad epilogue %d", epi);
 }
@@ -1128,4 +1175,24 @@ extern "C" int32_t qp_gen_dot(qp_gen_t gen, const qp_c128* coeffs, qp_state_t x,
   cudaStreamSynchronize(ctx->stream);
   cudaFree(tmp);
   return rc;
+}
+
+extern "C" int32_t qp_gen_expval(qp_gen_t gen, const qp_c128* coeffs, qp_state_t x, qp_c128* out) {
+  QP_CHECK(check_gen_state(gen, x, x, "qp_gen_expval"));
+  qp_ctx_t ctx = gen->ctx;
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, out != nullptr, "qp_gen_expval: null output");
+  int stride = 0;
+  QP_CHECK(qp_gen_set_coeffs(gen, coeffs, 0, x->batch, &stride));
+  const size_t need = (size_t)3 * x->batch;
+  QP_CHECK(qp_ctx_reserve_red(ctx, need));
+  QP_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * need, ctx->stream));
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.chk = ctx->d_red;
+  QP_CHECK(qp_launch_fused(gen, EPI_DOT, stride, x->d, x->batch, e));
+  QP_CUDA(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * need, cudaMemcpyDeviceToHost, ctx->stream));
+  QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t b = 0; b < x->batch; ++b) out[b] = qp_c128{ctx->h_red[3 * b], ctx->h_red[3 * b + 1]};
+  return QP_OK;
 }

@@ -9,6 +9,7 @@
 //   EPI_CHEB_MID    v2 = c(Hx - b x) + y;  y <- v2;  acc += ak v2          src/cheby.jl:186-209
 //   EPI_CHEB_LAST   v2 as MID; acc <- phase (acc + ak v2)  (v2 not stored) src/cheby.jl:211
 //   EPI_CHEB_ONLY   n_coeffs == 2: acc <- phase (a0 x + a1 c(Hx - b x))
+//   EPI_DOT         <x|Hx> accumulated per trajectory, nothing stored      dot(x, A, x), src/generators.jl:648-660
 //
 // so one Chebyshev term is ONE pass: the reference's mul! + 2 axpy! + lmul! + axpy!
 // (src/cheby.jl:189-205) and the per-operator read-modify-write of the result collapse
@@ -28,7 +29,12 @@
 
 #include "qprop_internal.h"
 
-enum { EPI_MUL = 0, EPI_CHEB_FIRST = 1, EPI_CHEB_MID = 2, EPI_CHEB_LAST = 3, EPI_CHEB_ONLY = 4 };
+enum { EPI_MUL = 0, EPI_CHEB_FIRST = 1, EPI_CHEB_MID = 2, EPI_CHEB_LAST = 3, EPI_CHEB_ONLY = 4, EPI_DOT = 5 };
+
+// epilogues that leave per-trajectory sums in e.chk[b*3 + {0,1,2}] (flushed with atomics)
+__host__ __device__ constexpr bool epi_has_sums(int epi) {
+  return epi == EPI_CHEB_MID || epi == EPI_CHEB_LAST || epi == EPI_DOT;
+}
 
 struct EpiArgs {
   double2 alpha, betac;  // EPI_MUL
@@ -126,6 +132,11 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, int64_t idx, double2
     e.y[idx] = r;
     return;
   }
+  if (EPI == EPI_DOT) {  // conj(x_r) (Hx)_r
+    chk_dr += xr.x * hx.x + xr.y * hx.y;
+    chk_di += xr.x * hx.y - xr.y * hx.x;
+    return;
+  }
   const double2 t = make_double2(hx.x - e.beta * xr.x, hx.y - e.beta * xr.y);
   double2 v = cmul2(e.c, t);  // c (Hx - beta x)
   if (EPI == EPI_CHEB_FIRST) {
@@ -207,7 +218,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
   }
   double dr = 0, di = 0, nn = 0;
   if (active && lane == 0) epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);
@@ -252,7 +263,7 @@ k_spmv_sell(MatView m, const double2* __restrict__ coef, int n_ops, const double
     }
     if (row < m.n) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
   }
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);
@@ -441,7 +452,7 @@ k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const do
     }
     if (live) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
   }
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);
@@ -478,8 +489,7 @@ __device__ __forceinline__ double2 ld_noalloc(const double2* p) {
 // NG groups of 8 codes taken from the 32-bit words w[]: all 8*NG gathers are issued before the
 // first one is consumed
 template <int CB, int NG>
-__device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* __restrict__ s_val,
-                                             const int32_t* __restrict__ s_delta,
+__device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s_val, const int32_t* s_delta,
                                              const double2* __restrict__ xbase, double& sr, double& si) {
   constexpr int NC = 8 * NG;
   uint32_t code[NC];
@@ -500,8 +510,7 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* _
 // one 16-byte word of codes: 8 gathers in flight at a time (16 at once was slower on B200:
 // the extra registers cost more latency hiding than the deeper queue buys)
 template <int CB>
-__device__ __forceinline__ void selld_word(const uint4& c, const double2* __restrict__ s_val,
-                                           const int32_t* __restrict__ s_delta,
+__device__ __forceinline__ void selld_word(const uint4& c, const double2* s_val, const int32_t* s_delta,
                                            const double2* __restrict__ xbase, double& sr, double& si) {
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   if (CB == 1) {
@@ -527,18 +536,24 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
   }
 }
 
-template <int EPI, int CB>
+template <int EPI, int CB, int TC>
 __global__ void __launch_bounds__(256, 2)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
-             int slices_per_cta) {
+             int slices_per_cta, const __grid_constant__ DictConst tc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* s_val = reinterpret_cast<double2*>(smem_raw);
-  int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
-  for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
-    s_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
-    s_delta[j] = m.ddelta[j];
+  // TC: the (pre-multiplied) table is a kernel parameter, read through the constant cache;
+  // otherwise it is built in shared memory from this step's coefficients
+  const double2* s_val = TC ? tc.val : reinterpret_cast<const double2*>(smem_raw);
+  const int32_t* s_delta = TC ? tc.delta : reinterpret_cast<const int32_t*>(smem_raw + sizeof(double2) * m.n_dict);
+  if (!TC) {
+    double2* w_val = reinterpret_cast<double2*>(smem_raw);
+    int32_t* w_delta = reinterpret_cast<int32_t*>(w_val + m.n_dict);
+    for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
+      w_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
+      w_delta[j] = m.ddelta[j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
@@ -605,7 +620,7 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
     if (live) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
     s = s_next;
   }
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);
@@ -649,42 +664,66 @@ k_spmm_csr(MatView m, const double2* __restrict__ coef, int coef_stride, int64_t
   }
   double dr = 0, di = 0, nn = 0;
   epilogue<EPI>(e, x, idx, idx, make_double2(sr, si), dr, di, nn);
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) chk_flush(e, b, dr, di, nn);
+  if (epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, b, dr, di, nn);
 }
 
 // ---------------------------------------------------------------------------------------
-// SELL-D, trajectory-batched: warp per (row, chunk of 32 trajectories); state layout [N][B].
-// Every lane of a warp works on the same matrix row, so the code stream, the table lookups,
-// the operator changes and the real/imaginary/complex kind of an entry are all warp-uniform:
-// the gathers are 512 B contiguous, a purely real or imaginary entry costs 2 DFMA instead of
-// 4, and the per-trajectory coefficient u_l^(b) is applied once per operator and row (entries
-// of a row are stored operator by operator).  The grid runs all row blocks of one trajectory
-// chunk before the next chunk (blockIdx.x = row block), so the chunk's slice of x
-// (N x 32 x 16 B) stays in L2 while the rows sweep over it and every gather after the first
-// is an L2 hit -- HBM traffic stays at the algorithmic 80 B per (row, trajectory).
-// CTA = one slice of 32 rows; warp w takes rows w, w+8, w+16, w+24.
+// SELL-D, trajectory-batched: warp per (row, T chunks of 32 trajectories); state layout [N][B].
+// Every lane of a warp works on the same matrix row, so the code stream, the table lookups and
+// the operator changes are warp-uniform and decoded once for T trajectories per lane; the
+// gathers are 512 B contiguous.  The per-trajectory coefficient u_l^(b) is applied once per
+// operator and row (entries of a row are stored operator by operator).  REALV: every operator
+// is purely real or purely imaginary (the usual case: ladder operators, Pauli sums), so an
+// entry is one real number (2 DFMA per trajectory instead of 4) and the factor i of an
+// imaginary operator is folded into its coefficient.
+// The grid runs all row blocks of one trajectory chunk before the next chunk (blockIdx.x = row
+// block), so the chunk's slice of x (N x 32T x 16 B) stays in L2 while the rows sweep over it:
+// every gather after the first is an L1/L2 hit and HBM traffic stays at the algorithmic 80 B
+// per (row, trajectory).  CTA = one slice of 32 rows; warp w takes rows w, w+8, w+16, w+24.
 // ---------------------------------------------------------------------------------------
-template <int EPI, int CB>
+struct DeltaOp {
+  int32_t delta;
+  int32_t op;
+};
+
+template <int G, int T, int CB>
+struct SpmmGroup {  // G consecutive codes of a row (packed) and their gathered x values for T trajectories
+  uint32_t pk[G * CB / 4];
+  double2 xv[G][T];
+  bool any;
+  __device__ __forceinline__ uint32_t code(int g) const {
+    return CB == 1 ? (pk[g >> 2] >> (8 * (g & 3))) & 0xffu : (pk[g >> 1] >> (16 * (g & 1))) & 0xffffu;
+  }
+};
+
+template <int EPI, int CB, int REALV, int T, int G>
 __global__ void __launch_bounds__(256, 2)
-k_spmm_selld(DictView m, const double2* __restrict__ coef, int coef_stride, int64_t batch,
-             const double2* __restrict__ x, EpiArgs e, int n_ops) {
+k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, const double2* __restrict__ coef,
+             int coef_stride, int64_t batch, const double2* __restrict__ x, EpiArgs e) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* s_val = reinterpret_cast<double2*>(smem_raw);
-  int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
-  uint8_t* s_op = reinterpret_cast<uint8_t*>(s_delta + m.n_dict);
+  double2* s_val2 = reinterpret_cast<double2*>(smem_raw);  // !REALV
+  double* s_val1 = reinterpret_cast<double*>(smem_raw);    // REALV
+  DeltaOp* s_dop = reinterpret_cast<DeltaOp*>(smem_raw + (size_t)m.n_dict * (REALV ? 8 : 16));
   for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
-    s_val[j] = m.dval[j];
-    s_delta[j] = m.ddelta[j];
-    s_op[j] = m.dop[j];
+    if (REALV) s_val1[j] = dvalr[j];
+    else s_val2[j] = m.dval[j];
+    s_dop[j] = DeltaOp{m.ddelta[j], (int32_t)m.dop[j]};
   }
   __syncthreads();
 
-  constexpr int CPW = 16 / CB;
+  constexpr int CPW = 16 / CB;   // codes per 16-byte word
+  constexpr int GPW = CPW / G;   // gather groups per word
+  static_assert(CPW % G == 0, "group size must divide the codes per word");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slice = blockIdx.x;
-  const int64_t b = (int64_t)blockIdx.y * 32 + lane;
-  const bool blive = b < batch;
-  const int64_t bb = blive ? b : batch - 1;
+  int64_t bcol[T];   // this lane's trajectories (clamped; dead ones are computed on a copy)
+  bool blive[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t b = ((int64_t)blockIdx.y * T + t) * 32 + lane;
+    blive[t] = b < batch;
+    bcol[t] = blive[t] ? b : batch - 1;
+  }
   uint32_t off0, off1;
   if (m.uniform_words) {
     off0 = (uint32_t)slice * m.uniform_words;
@@ -693,80 +732,130 @@ k_spmm_selld(DictView m, const double2* __restrict__ coef, int coef_stride, int6
     off0 = m.sptr[slice];
     off1 = m.sptr[slice + 1];
   }
-  // this trajectory's coefficients (n_ops <= 16 would cost 32 registers: keep them in L1/L2)
-  const double2* __restrict__ ucol = coef + (coef_stride ? bb : 0);
+  const int n_groups = (int)((off1 - off0) / QP_SELL_C) * GPW;
   const int64_t ustride = coef_stride ? batch : 1;
+  auto ucoef = [&](int op, int t) {  // u_op of trajectory t (times i for an imaginary operator)
+    const double2 u = __ldg(coef + (int64_t)op * ustride + (coef_stride ? bcol[t] : 0));
+    return (REALV && ((imag_ops >> op) & 1u)) ? make_double2(-u.y, u.x) : u;
+  };
 
-  double dr = 0, di = 0, nn = 0;
+  double dr[T], di[T], nn[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) dr[t] = di[t] = nn[t] = 0.0;
   for (int rl = warp; rl < QP_SELL_C; rl += 8) {
     const int64_t row = slice * QP_SELL_C + rl;
     if (row >= m.n) break;
-    const int64_t idx = row * batch + bb;
-    double2 xr, yv, av;
-    epi_load<EPI>(e, x, idx, idx, xr, yv, av);
-    const double2* __restrict__ xb = x + idx;  // x[(row + delta) * batch + b] = xb[delta * batch]
-    double tr = 0.0, ti = 0.0;                 // sum over all operators
-    double pr = 0.0, pi = 0.0;                 // partial sum of the current operator
+    double2 xr[T], yv[T], av[T];
+    const double2* xb[T];
+    double tr[T], ti[T], pr[T], pi[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t idx = row * batch + bcol[t];
+      epi_load<EPI>(e, x, idx, idx, xr[t], yv[t], av[t]);
+      xb[t] = x + idx;  // x[(row + delta) * batch + b] = xb[delta * batch]
+      tr[t] = ti[t] = pr[t] = pi[t] = 0.0;
+    }
     int cur_op = -1;
-    for (uint32_t off = off0 + rl; off < off1; off += QP_SELL_C) {
-      const uint4 c = __ldg(m.codes + off);    // same word for all lanes: one broadcast load
+
+    // decode group gi of this row and issue its gathers
+    auto load = [&](int gi, SpmmGroup<G, T, CB>& grp) {
+      const uint4 c = __ldg(m.codes + off0 + rl + (uint32_t)(gi / GPW) * QP_SELL_C);  // warp-uniform word
       const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+      constexpr int WPG = G * CB / 4;  // 32-bit words per group
+      const int h = (gi % GPW) * WPG;
+      uint32_t orv = 0u;
 #pragma unroll
-      for (int h = 0; h < CPW; h += 8) {
-        uint32_t code[8];
-        double2 xv[8];
+      for (int j = 0; j < WPG; ++j) {
+        uint32_t v = w[0];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int tt = h + t;
-          code[t] = CB == 1 ? (w[tt >> 2] >> (8 * (tt & 3))) & 0xffu : (w[tt >> 1] >> (16 * (tt & 1))) & 0xffffu;
-        }
-        if (CB == 1 && h == 8 && (w[2] | w[3]) == 0u) break;  // all padding (warp-uniform)
+        for (int q = 1; q < 4; ++q) v = (h + j == q) ? w[q] : v;
+        grp.pk[j] = v;
+        orv |= v;
+      }
+      grp.any = orv != 0u;
+      if (!grp.any) return;  // all padding (warp-uniform)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) xv[t] = __ldg(xb + (int64_t)s_delta[code[t]] * batch);
+      for (int g = 0; g < G; ++g) {
+        const int64_t o = (int64_t)s_dop[grp.code(g)].delta * batch;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          if (code[t] == 0u) continue;  // padding
-          const int op = s_op[code[t]];
-          if (op != cur_op) {           // warp-uniform: fold the finished operator
-            if (cur_op >= 0) {
-              const double2 u = __ldg(ucol + cur_op * ustride);
-              tr += u.x * pr - u.y * pi;
-              ti += u.x * pi + u.y * pr;
+        for (int t = 0; t < T; ++t) grp.xv[g][t] = __ldg(xb[t] + o);
+      }
+    };
+    auto consume = [&](const SpmmGroup<G, T, CB>& grp) {
+      if (!grp.any) return;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t code = grp.code(g);
+        if (code == 0u) continue;  // padding / entry kept in an explicit diagonal
+        const int op = s_dop[code].op;
+        if (op != cur_op) {        // warp-uniform: fold the finished operator
+          if (cur_op >= 0) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const double2 u = ucoef(cur_op, t);
+              tr[t] += u.x * pr[t] - u.y * pi[t];
+              ti[t] += u.x * pi[t] + u.y * pr[t];
+              pr[t] = pi[t] = 0.0;
             }
-            cur_op = op;
-            pr = pi = 0.0;
           }
-          const double2 v = s_val[code[t]];
-          if (v.y == 0.0) {             // real entry: 2 DFMA
-            pr += v.x * xv[t].x;
-            pi += v.x * xv[t].y;
-          } else if (v.x == 0.0) {      // imaginary entry: 2 DFMA
-            pr -= v.y * xv[t].y;
-            pi += v.y * xv[t].x;
-          } else {
-            pr += v.x * xv[t].x - v.y * xv[t].y;
-            pi += v.x * xv[t].y + v.y * xv[t].x;
+          cur_op = op;
+        }
+        if (REALV) {
+          const double v = s_val1[code];
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            pr[t] += v * grp.xv[g][t].x;
+            pi[t] += v * grp.xv[g][t].y;
+          }
+        } else {
+          const double2 v = s_val2[code];
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            pr[t] += v.x * grp.xv[g][t].x - v.y * grp.xv[g][t].y;
+            pi[t] += v.x * grp.xv[g][t].y + v.y * grp.xv[g][t].x;
           }
         }
       }
+    };
+    // one group (G codes x T trajectories = 8 gathers per lane) at a time: holding a second group
+    // in flight costs more in registers / decode instructions than it hides (measured: slower)
+    SpmmGroup<G, T, CB> ga;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      load(gi, ga);
+      consume(ga);
     }
     if (cur_op >= 0) {
-      const double2 u = __ldg(ucol + cur_op * ustride);
-      tr += u.x * pr - u.y * pi;
-      ti += u.x * pi + u.y * pr;
-    }
-    if (m.n_diag > 0) {  // explicit diagonals (warp-uniform matrix element, per-trajectory u)
-      const double2 xs = EPI == EPI_MUL ? __ldg(x + idx) : xr;
-      for (int i = 0; i < m.n_diag; ++i) {
-        const double2 u = __ldg(ucol + (int64_t)((m.diag_ops >> (4 * i)) & 15ull) * ustride);
-        const double2 t = cmul2(u, __ldg(m.diag + (int64_t)i * m.n + row));
-        tr += t.x * xs.x - t.y * xs.y;
-        ti += t.x * xs.y + t.y * xs.x;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const double2 u = ucoef(cur_op, t);
+        tr[t] += u.x * pr[t] - u.y * pi[t];
+        ti[t] += u.x * pi[t] + u.y * pr[t];
       }
     }
-    if (blive) epi_apply<EPI>(e, idx, make_double2(tr, ti), xr, yv, av, dr, di, nn);
+    if (m.n_diag > 0) {  // explicit diagonals (warp-uniform matrix element, per-trajectory u)
+      for (int i = 0; i < m.n_diag; ++i) {
+        const int op = (int)((m.diag_ops >> (4 * i)) & 15ull);
+        const double2 d = __ldg(m.diag + (int64_t)i * m.n + row);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const double2 u = __ldg(coef + (int64_t)op * ustride + (coef_stride ? bcol[t] : 0));
+          const double2 ud = cmul2(u, d);
+          const double2 xs = EPI == EPI_MUL ? __ldg(xb[t]) : xr[t];
+          tr[t] += ud.x * xs.x - ud.y * xs.y;
+          ti[t] += ud.x * xs.y + ud.y * xs.x;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (blive[t])
+        epi_apply<EPI>(e, row * batch + bcol[t], make_double2(tr[t], ti[t]), xr[t], yv[t], av[t], dr[t], di[t], nn[t]);
   }
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr && blive) chk_flush(e, b, dr, di, nn);
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (blive[t]) chk_flush(e, bcol[t], dr[t], di[t], nn[t]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -804,7 +893,7 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
   }
   double dr = 0, di = 0, nn = 0;
   if (row < n && lane == 0) epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
-  if ((EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) && e.chk != nullptr) {
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);

@@ -149,6 +149,14 @@ class DeviceGenerator:
         )
         return y
 
+    def expval(self, x: "DeviceState", coeffs=None):
+        """⟨x|H|x⟩ per trajectory in one fused pass (``qp_gen_expval``): the expectation value of
+        a matrix observable (reference ``src/storage.jl:100-123``)."""
+        c = self._coeffs(coeffs)
+        out = np.zeros(x.batch, dtype=np.complex128)
+        L.check(self.ctx._lib.qp_gen_expval(self.handle, L.ptr(c), x.handle, L.ptr(out)), self.ctx.handle)
+        return complex(out[0]) if x.batch == 1 else out
+
     def dot(self, x: "DeviceState", y: "DeviceState", coeffs):
         """3-argument ``dot(x, H, y)`` (reference ``src/generators.jl:648-660``)."""
         c = self._coeffs(coeffs)

@@ -18,7 +18,7 @@ import warnings
 import numpy as np
 
 from . import controls as _c
-from .cheby import ChebyWrk, cheby_
+from .cheby import ChebyWrk, cheby_, cheby_propagate_
 from .controls import IdDict, discretize, discretize_on_midpoints
 from .device import Context, DeviceState, default_context
 from .generators import Generator, Operator, canonical, evaluate, evaluate_, get_controls, _as_operator
@@ -334,12 +334,68 @@ def reinit_prop(p, state, transform_control_ranges=None, **_):
     p._set_t(float(tlist[-1] if p.backward else tlist[0]))
 
 
-def _observe(observables, state: DeviceState):
-    """Default observable: the state itself (downloaded copy); otherwise a tuple of callables
-    on the DeviceState (reference ``src/storage.jl:67-80``)."""
+def _is_matrix_observable(obs):
+    import scipy.sparse as sp
+
+    return sp.issparse(obs) or (isinstance(obs, np.ndarray) and obs.ndim == 2)
+
+
+class _ObservableCache:
+    """Device form of matrix observables (uploaded once per propagate call)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.gens = {}
+
+    def gen(self, obs):
+        from .device import DeviceGenerator
+
+        key = id(obs)
+        if key not in self.gens:
+            self.gens[key] = DeviceGenerator(self.ctx, [obs], 0)
+        return self.gens[key]
+
+
+def _observe(observables, state: DeviceState, cache=None):
+    """Default observable: the state itself (downloaded copy); otherwise a tuple whose entries
+    are callables on the DeviceState or matrices, for which the expectation value ⟨Ψ|O|Ψ⟩ is
+    recorded (reference ``src/storage.jl:67-80, 100-123``)."""
     if observables is None:
         return state.to_host()
-    return np.array([obs(state) for obs in observables])
+    out = []
+    for obs in observables:
+        if _is_matrix_observable(obs):
+            cache = cache or _ObservableCache(state.ctx)
+            out.append(cache.gen(obs).expval(state))
+        else:
+            out.append(obs(state))
+    return np.array(out)
+
+
+def _propagate_on_device(p, observables, storage):
+    """Fast path of ``propagate``: the whole remaining grid in ONE library call
+    (``qp_cheby_propagate``), matrix observables evaluated on the device; no per-step host work
+    and no state download.  Legal because without a callback nothing can change
+    ``propagator.parameters`` between the steps of one ``propagate`` call."""
+    tlist = p.tlist
+    nt = len(tlist)
+    steps = list(range(p.n, 0, -1)) if p.backward else list(range(p.n, nt))
+    gen = p._generator()
+    table = np.zeros((len(steps), p.wrk.gen.n_coeffs), dtype=np.complex128)
+    for s, n in enumerate(steps):
+        H = p._coeffs_for(n)
+        if isinstance(H, Operator):
+            table[s, :] = H.coeffs
+    dt = -p.wrk.dt if p.backward else p.wrk.dt
+    cache = _ObservableCache(p.ctx)
+    obs_gens = [cache.gen(o) for o in observables] if observables else []
+    ev, _ = cheby_propagate_(p.state, p.wrk, table, dt, observables=obs_gens)
+    for _ in steps:
+        p._advance_time()
+    if storage is not None:
+        for s in range(nt):  # storage is written back to front when propagating backward
+            storage[..., (nt - 1 - s) if p.backward else s] = ev[s]
+    return p.state
 
 
 def propagate(
@@ -367,18 +423,35 @@ def propagate(
     tlist = p.tlist
     nt = len(tlist)
     return_storage = storage is True
+    cache = _ObservableCache(p.ctx)
+    # whole grid in one library call when nothing has to run on the host between the steps:
+    # Chebyshev, in place, no callback, and storage (if any) of matrix observables only
+    on_device = (
+        isinstance(p, ChebyPropagator) and p.inplace and callback is None and not p.check_normalization
+        and p.state.batch == 1 and p.n == (nt - 1 if p.backward else 1)
+        and (storage is None or (observables is not None and len(observables) > 0
+                                 and all(_is_matrix_observable(o) for o in observables)))
+    )
     if storage is True:
-        first = _observe(observables, p.state)
-        storage = np.zeros(first.shape + (nt,), dtype=first.dtype)
+        if on_device:
+            storage = np.zeros((len(observables), nt), dtype=np.complex128)
+        else:
+            first = _observe(observables, p.state, cache)
+            storage = np.zeros(first.shape + (nt,), dtype=first.dtype)
+    if on_device:
+        _propagate_on_device(p, observables, storage)
+        if return_storage:
+            return storage
+        return p.state.to_host() if p._host_io else p.state
     if storage is not None:
-        storage[..., nt - 1 if p.backward else 0] = _observe(observables, p.state)
+        storage[..., nt - 1 if p.backward else 0] = _observe(observables, p.state, cache)
     intervals = range(nt - 1, 0, -1) if p.backward else range(1, nt)
     for i in intervals:
         prop_step(p)
         if callback is not None:
             callback(p, observables)
         if storage is not None:
-            storage[..., (i - 1) if p.backward else i] = _observe(observables, p.state)
+            storage[..., (i - 1) if p.backward else i] = _observe(observables, p.state, cache)
     if return_storage:
         return storage
     return p.state.to_host() if p._host_io else p.state

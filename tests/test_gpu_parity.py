@@ -690,3 +690,89 @@ def test_timings_labels(qp):
     n_step, t_step = c.timing("prop_step!")
     n_mv, t_mv = c.timing("matrix-vector product")
     assert n_step == 100 and n_mv > 200 and 0 < t_mv <= t_step
+
+
+# ---------------------------------------------------------------------------------------
+# on-device observables and the one-call propagation loop (src/propagate.jl:283-344,
+# src/storage.jl:100-123)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fmt,n,B", [("csr", 300, 1), ("sell", 4100, 1), ("selld", 4100, 1), ("auto", 500, 5), ("auto", 500, 40)])
+def test_expval_fused(qp, ctx, fmt, n, B):
+    rng = np.random.default_rng(n + B)
+    ops = _structured_ops(rng, n, 7, [[0, -3, 1], [5, -5, 40]])
+    coeffs = [0.3 - 0.4j]
+    gen = qp.DeviceGenerator(ctx, ops, 1, fmt)
+    X = rand_state(rng, n, None if B == 1 else B)
+    dx = qp.DeviceState.from_host(ctx, X)
+    H = (ops[0] + coeffs[0] * ops[1]).tocsr()
+    ref = np.vdot(X, H @ X) if B == 1 else np.einsum("ib,ib->b", X.conj(), H @ X)
+    assert np.allclose(gen.expval(dx, coeffs), ref, rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(dx.to_host(), X)  # the state is untouched
+
+
+def test_expval_dense(qp, ctx):
+    rng = np.random.default_rng(21)
+    n = 130
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    for B in (1, 9):
+        X = rand_state(rng, n, None if B == 1 else B)
+        dx = qp.DeviceState.from_host(ctx, X)
+        ref = np.vdot(X, A @ X) if B == 1 else np.einsum("ib,ib->b", X.conj(), A @ X)
+        assert np.allclose(qp.DeviceGenerator(ctx, [A], 0).expval(dx), ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("backward", [False, True])
+def test_propagate_one_call_with_observables(qp, ctx, backward):
+    """propagate(...; storage=true, observables=(O1, O2)) with matrix observables runs as ONE
+    library call with the expectation values recorded on the device; it must agree with the
+    oracle's step loop and with this package's own per-step loop."""
+    w = qp.workloads.config2_tfim(10, nt=21, dt=0.1)
+    N = w["psi0"].shape[0]
+    O1 = w["ops"][2]                                   # sum Z_i (diagonal)
+    O2 = (w["ops"][1] + 0.5j * sp.eye(N)).tocsr()      # sum X_i + 0.5i: complex expectation values
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"], backward=backward)
+    obs_host = (lambda psi: np.vdot(psi, O1 @ psi), lambda psi: np.vdot(psi, O2 @ psi))
+    ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "cheby", storage=True,
+                      observables=obs_host, **kw)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    launches0 = ctx.launch_count
+    fast = qp.propagate(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, storage=True, observables=(O1, O2), **kw)
+    assert fast.shape == (2, 21)
+    assert np.max(np.abs(fast - ref)) < 1e-10 * N ** 0.5
+    # the slow loop (a callback forces it) gives the same numbers
+    slow = qp.propagate(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, storage=True, observables=(O1, O2),
+                        callback=lambda p, obs: None, **kw)
+    assert np.max(np.abs(fast - slow)) < 1e-11
+    # and the final state of the one-call path equals the oracle's
+    p = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx, **kw)
+    out = qp.propagate(p)
+    ref_state = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), w["tlist"], "cheby", **kw)
+    assert rel(out, ref_state) < RTOL
+    assert p.t == (w["tlist"][0] if backward else w["tlist"][-1])
+    assert qp.prop_step(p) is None  # grid exhausted, like after the step loop
+    assert ctx.launch_count > launches0
+
+
+def test_cheby_propagate_norms_batched(qp, ctx):
+    """qp_cheby_propagate on a batch: per-trajectory coefficient table, norms recorded on device."""
+    rng = np.random.default_rng(31)
+    w = qp.workloads.config3_transmon(n_sites=3, levels=3, B=20, nt=6, dt=0.5)
+    H0, H1, H2 = w["ops"]
+    B, n_steps = 20, 5
+    psi0 = rand_state(rng, H0.shape[0], B)
+    bound = float((abs(H0) + 0.1 * abs(H1) + 0.1 * abs(H2)).sum(axis=1).max())
+    st = qp.DeviceState.from_host(ctx, psi0)
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    wrk = qp.ChebyWrk(st, gen, 2 * bound, -bound, 0.5)
+    table = rng.uniform(-0.07, 0.07, (n_steps, 2, B)).astype(complex)
+    obs = qp.DeviceGenerator(ctx, [H0], 0)
+    ev, norms = qp.cheby_propagate_(st, wrk, table, 0.5, observables=[obs], norms=True, per_trajectory=True)
+    assert ev.shape == (n_steps + 1, 1, B) and norms.shape == (n_steps + 1, B)
+    assert np.max(np.abs(norms - 1)) < 1e-12
+    st2 = qp.DeviceState.from_host(ctx, psi0)
+    for s in range(n_steps):
+        assert np.allclose(ev[s, 0], np.einsum("ib,ib->b", st2.to_host().conj(), H0 @ st2.to_host()), atol=1e-12)
+        qp.cheby_(st2, None, 0.5, wrk, coeffs=table[s], per_trajectory=True)
+    assert rel(st.to_host(), st2.to_host()) < 1e-14

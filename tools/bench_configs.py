@@ -65,6 +65,18 @@ def config1(ctx, args):
         for _ in range(steps):
             qp.prop_step(p)
     wall = time.perf_counter() - t0
+    # the whole 500-step grid as ONE library call (qp_cheby_propagate; what propagate() does without a callback)
+    p2 = qp.init_prop(w["psi0"], qp.hamiltonian(*terms), w["tlist"], "cheby", ctx=ctx, E_min=w["E_min"], E_max=w["E_max"])
+    qp.propagate(p2)
+    p2 = qp.init_prop(w["psi0"], qp.hamiltonian(*terms), w["tlist"], "cheby", ctx=ctx, E_min=w["E_min"], E_max=w["E_max"])
+    t1 = time.perf_counter()
+    with Timer(ctx) as t2:
+        qp.propagate(p2)
+    wall2 = time.perf_counter() - t1
+    n2 = len(w["tlist"]) - 1
+    emit(config=1, workload="random sparse Hermitian N=1000 + 1 control, Cheby, propagate() = one qp_cheby_propagate call",
+         steps=n2, prop_steps_per_s=n2 / (t2.ms * 1e-3), us_per_step=1e3 * t2.ms / n2, wall_us_per_step=1e6 * wall2 / n2,
+         norm_dev=abs(p2.state.norm() - 1))
     emit(config=1, workload="random sparse Hermitian N=1000 + 1 control, Cheby", n_coeffs=p.wrk.n_coeffs, steps=steps,
          prop_steps_per_s=steps / (t.ms * 1e-3), us_per_step=1e3 * t.ms / steps, wall_us_per_step=1e6 * wall / steps,
          launches_per_step=(ctx.launch_count - l0) / steps, format=p.wrk.gen.format,
@@ -142,8 +154,8 @@ def config4(ctx, args):
             qp.prop_step(p)
     N = w["psi0"].shape[0]
     emit(config=4, workload=f"Liouvillian of {n_spins}-spin TFIM + decay, dim {N}, Newton m_max=10", steps=args.newton_steps,
-         prop_steps_per_s=args.newton_steps / (t.ms * 1e-3), ms_per_step=t.ms / args.newton_steps, format=p.wrk.gen.format,
-         n_dict=p.wrk.gen.n_dict, matrix_bytes=p.wrk.gen.matrix_bytes, launches_per_step=(ctx.launch_count - l0) / args.newton_steps,
+         prop_steps_per_s=args.newton_steps / (t.ms * 1e-3), ms_per_step=t.ms / args.newton_steps, format=p.wrk.krylov.gen.format,
+         n_dict=p.wrk.krylov.gen.n_dict, matrix_bytes=p.wrk.krylov.gen.matrix_bytes, launches_per_step=(ctx.launch_count - l0) / args.newton_steps,
          restarts_per_step=getattr(p.wrk, "restarts", None), setup_s=t_build)
 
 
