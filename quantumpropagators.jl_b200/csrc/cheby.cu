@@ -313,7 +313,6 @@ extern "C" int32_t qp_cheby_propagate(qp_cheby_t w, qp_state_t st, const qp_c128
   int32_t rc = record(0);
   for (int s = 0; s < n_steps && rc == QP_OK; ++s) {
     gen->d_coef = d_tbl + (size_t)s * per_step;
-    gen->h_coef = coeffs_per_traj ? nullptr : h_tbl.data() + (size_t)s * per_step;
     {
       QpScopedTimer step_timer(ctx, "prop_step!");  // same label and count as the step loop
       rc = cheby_step_device(w, st, coeffs_per_traj ? 1 : 0, dt_signed, nullptr);
@@ -321,7 +320,6 @@ extern "C" int32_t qp_cheby_propagate(qp_cheby_t w, qp_state_t st, const qp_c128
     if (rc == QP_OK) rc = record(s + 1);
   }
   gen->d_coef = saved_coef;
-  gen->h_coef = nullptr;
   if (rc != QP_OK) return cleanup(rc);
 
   if (rec_doubles) {

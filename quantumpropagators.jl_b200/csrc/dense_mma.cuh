@@ -13,8 +13,10 @@
 //
 // CTA tile: (WM * MT * 8) rows x (WN * 8) trajectories; warp tile: MT m8-tiles x 2 n8-tiles
 // (8 trajectories); K tile: 16 complex per stage, STAGES-deep cp.async pipeline running
-// seamlessly across the operators of the lazy sum (the coefficient u_l -- per trajectory in
-// ensemble mode -- is applied to the X fragment, so one accumulator set serves all operators).
+// seamlessly across the operators of the lazy sum.  The coefficient u_l (per trajectory in
+// ensemble mode) is applied to the accumulators once per operator, NOT to the fragments: the
+// DMMA runs on the FP64 pipe, and any DFMA/DMUL between two DMMAs drains it (measured: 69 % ->
+// see profiles/), so the K loop contains only LDS, integer selects and DMMA.
 // KS warp groups split every K tile between them (same output tile, partial sums added through
 // shared memory at the end): the DMMA pipe needs ~4 warps per scheduler to stay busy, and the
 // row count of the operator (8192 / 148 SMs = 56 rows per CTA) leaves no other way to get them.
@@ -106,21 +108,31 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
     cp_async_commit();
   };
 
-  double acc[MT][NQ][2];
+  double acc[MT][NQ][2], tot[MT][NQ][2];  // current operator / sum over finished operators
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+    for (int q = 0; q < NQ; ++q) acc[i][q][0] = acc[i][q][1] = tot[i][q][0] = tot[i][q][1] = 0.0;
+  // tot += u_l * acc for the operator that just finished (C-side trajectory of n8-tile q: 4q + t)
+  auto fold = [&](int l) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const double2 u = s_coef[l * T::TRAJ + wn * NQ * 4 + q * 4 + t];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        tot[i][q][0] += u.x * acc[i][q][0] - u.y * acc[i][q][1];
+        tot[i][q][1] += u.x * acc[i][q][1] + u.y * acc[i][q][0];
+        acc[i][q][0] = acc[i][q][1] = 0.0;
+      }
+    }
+  };
 
 #pragma unroll
   for (int s = 0; s < DM_STAGES - 1; ++s) load_stage(s, s);
 
   const int cpar = g & 1;              // this lane's B column is the (re | im) part of its trajectory
   const int bt = wn * NQ * 4 + (g >> 1);  // B-side trajectory of n8-tile 0 (tile q: +4q)
-  double2 u[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) u[q] = make_double2(1.0, 0.0);
-  int cur_op = -1;
+  int cur_op = 0;
 
   for (int it = 0; it < total_it; ++it) {
     cp_async_wait<DM_STAGES - 2>();
@@ -128,10 +140,9 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
     load_stage((it + DM_STAGES - 1) % DM_STAGES, it + DM_STAGES - 1);
 
     const int l = it / KT;
-    if (l != cur_op) {
+    if (l != cur_op) {  // operator boundary (n_ops - 1 times per kernel)
+      fold(cur_op);
       cur_op = l;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) u[q] = s_coef[l * T::TRAJ + bt + 4 * q];
     }
     const double* As = stage_A(it % DM_STAGES) + (wm * MT * 8 + g) * DM_A_STRIDE + 2 * t;
     const double2* Xs = stage_X(it % DM_STAGES) + t * T::X_STRIDE + bt;
@@ -144,9 +155,13 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
       double be[NQ], bo[NQ];
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        const double2 z = cmul2(u[q], Xs[jp * 4 * T::X_STRIDE + q * 4]);
-        be[q] = cpar ? z.y : z.x;   // K = real part of H:  [Xr | Xi]
-        bo[q] = cpar ? z.x : -z.y;  // K = imag part of H:  [-Xi | Xr]
+        const double2 z = Xs[jp * 4 * T::X_STRIDE + q * 4];
+        // sign flip on the bit pattern: no FP64-pipe instruction between the DMMAs
+        int hi = __double2hiint(z.y);
+        asm volatile("xor.b32 %0, %0, 0x80000000;" : "+r"(hi));  // opaque to the optimiser (else it emits DADD)
+        const double nzy = __hiloint2double(hi, __double2loint(z.y));
+        be[q] = cpar ? z.y : z.x;  // K = real part of H:  [Xr | Xi]
+        bo[q] = cpar ? z.x : nzy;  // K = imag part of H:  [-Xi | Xr]
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i)
@@ -159,6 +174,14 @@ k_gemm_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n, const
     }
   }
   cp_async_wait<0>();
+  fold(cur_op);
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      acc[i][q][0] = tot[i][q][0];
+      acc[i][q][1] = tot[i][q][1];
+    }
   if (KS > 1) {  // add the K groups' partial sums through shared memory (the stages are drained)
     double2* red = reinterpret_cast<double2*>(smem_raw);
     for (int k = KS - 1; k >= 1; --k) {
@@ -241,8 +264,8 @@ static int32_t launch_dense_batched(qp_gen_t gen, int coef_stride, const double2
   if (batch > 32) {
     if (variant == 1) return launch_gemm_dense<EPI, 1, 16, 7, 1, 1>(gen, coef_stride, x, batch, e);  // 56 x 64, 16 warps, 7 acc/warp
     if (variant == 2) return launch_gemm_dense<EPI, 2, 8, 4, 2, 1>(gen, coef_stride, x, batch, e);   // 64 x 64, 16 warps, 8 acc/warp
-    if (variant == 3) return launch_gemm_dense<EPI, 1, 8, 7, 2, 1>(gen, coef_stride, x, batch, e);   // 56 x 64, 8 warps, 14 acc/warp
-    return launch_gemm_dense<EPI, 1, 8, 7, 2, 2>(gen, coef_stride, x, batch, e);                     // 56 x 64, 2 x 8 warps (K split)
+    if (variant == 3) return launch_gemm_dense<EPI, 1, 8, 7, 2, 2>(gen, coef_stride, x, batch, e);   // 56 x 64, 2 x 8 warps (K split)
+    return launch_gemm_dense<EPI, 1, 8, 7, 2, 1>(gen, coef_stride, x, batch, e);                     // 56 x 64, 8 warps, 14 acc/warp
   }
   if (batch > 16) return launch_gemm_dense<EPI, 2, 4, 4, 2, 2>(gen, coef_stride, x, batch, e);   // 64 rows x 32 traj, 16 warps
   if (batch > 8) return launch_gemm_dense<EPI, 4, 2, 2, 2, 2>(gen, coef_stride, x, batch, e);    // 64 rows x 16 traj, 16 warps

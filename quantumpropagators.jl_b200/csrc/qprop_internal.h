@@ -86,16 +86,8 @@ struct DictView {
   unsigned long long diag_ops;  // operator index of vector i in bits [4i, 4i+4)
 };
 
-constexpr int QP_DICT_CONST = 128;      // tables up to this size travel as a kernel parameter (constant bank)
 constexpr int QP_DICT_MAX = 4096;       // table entries incl. the padding entry
 constexpr int QP_DICT_HASH_CAP = 16384; // open-addressing capacity used while building
-
-// small dictionary passed by value (__grid_constant__): lookups go through the constant cache,
-// not the L1/shared-memory pipe that the x gathers saturate
-struct DictConst {
-  double2 val[QP_DICT_CONST];   // u_op * value
-  int32_t delta[QP_DICT_CONST];
-};
 
 struct qp_gen_s {
   qp_ctx_t ctx = nullptr;
@@ -124,11 +116,6 @@ struct qp_gen_s {
   double2* d_dval = nullptr;
   int32_t* d_ddelta = nullptr;
   uint8_t* d_dop = nullptr;
-  std::vector<double2> h_dval;   // host copy of the table (small tables are pre-multiplied by the
-  std::vector<int32_t> h_ddelta; // step's coefficients on the host and passed as a kernel parameter)
-  std::vector<uint8_t> h_dop;
-  const double2* h_coef = nullptr;  // host view of the coefficients last set (n_ops numbers, B = 1 only)
-  double2 h_coef_buf[QP_MAX_OPS];   // storage behind h_coef for qp_gen_set_coeffs
   double* d_dvalr = nullptr;  // table values as one real number each (valid when dict_realv)
   bool dict_realv = false;    // every operator purely real or purely imaginary
   unsigned imag_ops = 0;      // bit l: operator l is purely imaginary (value stored = Im)

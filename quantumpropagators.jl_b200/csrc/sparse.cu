@@ -588,9 +588,6 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
   D_CUDA(cudaMemcpy(g->d_dvalr, h_valr.data(), sizeof(double) * n_dict, cudaMemcpyHostToDevice));
   g->dict_realv = realv;
   g->imag_ops = realv ? has_im : 0u;
-  g->h_dval = h_val;
-  g->h_ddelta = h_delta;
-  g->h_dop = h_op;
 
   // slice widths in 16-byte words
   D_CUDA(cudaMalloc(&d_words, sizeof(uint32_t) * (n_slices + 1)));
@@ -925,12 +922,6 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
     }
   QP_CUDA(ctx, cudaMemcpyAsync(gen->d_coef, h, sizeof(double2) * elems, cudaMemcpyHostToDevice, ctx->stream));
   QP_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
-  // host copy for launchers that fold the coefficients into kernel parameters
-  gen->h_coef = nullptr;
-  if (!per_traj) {
-    for (int l = 0; l < gen->n_ops; ++l) gen->h_coef_buf[l] = make_double2(h[l].re, h[l].im);
-    gen->h_coef = gen->h_coef_buf;
-  }
   if (coef_stride_out) *coef_stride_out = per_traj ? 1 : 0;
   return QP_OK;
 }
@@ -970,11 +961,11 @@ static DictView make_dict_view(qp_gen_t gen) {
 
 // SELL-D kernel: CTAs = SMs x resident CTAs per SM (or fewer for small matrices), each owning a
 // contiguous slice range; dynamic shared memory = the coefficient-scaled table.
-template <int EPI, int CB, int TC>
+template <int EPI, int CB>
 static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
-  auto kern = k_spmv_selld<EPI, CB, TC>;
-  const size_t smem = TC ? 0 : (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
+  auto kern = k_spmv_selld<EPI, CB>;
+  const size_t smem = (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ctx->smem_configured.insert((const void*)kern);
@@ -994,15 +985,7 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   static const int spc_env = getenv("QPROP_SELLD_SPC") ? atoi(getenv("QPROP_SELLD_SPC")) : 0;
   if (spc_env > 0) spc = spc_env;
   ctas = (gen->n_slices + spc - 1) / spc;
-  DictConst tc;
-  if (TC) {  // pre-multiply the table by this step's coefficients on the host (<= 128 entries)
-    for (int j = 0; j < gen->n_dict; ++j) {
-      const double2 u = gen->h_coef[gen->h_dop[j]], v = gen->h_dval[j];
-      tc.val[j] = make_double2(u.x * v.x - u.y * v.y, u.x * v.y + u.y * v.x);
-      tc.delta[j] = gen->h_ddelta[j];
-    }
-  }
-  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc, tc);
+  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc);
   QP_LAUNCHED(ctx);
   return QP_OK;
 }
@@ -1063,10 +1046,7 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     const DictView m = make_dict_view(gen);
     // compiled for 2 resident CTAs of 256 threads per SM (<= 128 registers): measured best on
     // B200 against 3 / 4 CTAs and a 16-gather variant (profiles/r1_variants.txt)
-    static const bool no_tc = getenv("QPROP_SELLD_NO_CONST") != nullptr;
-    if (gen->code_bytes == 1 && gen->n_dict <= QP_DICT_CONST && gen->h_coef != nullptr && !no_tc)
-      return launch_selld<EPI, 1, 1>(gen, m, x, e);
-    return gen->code_bytes == 1 ? launch_selld<EPI, 1, 0>(gen, m, x, e) : launch_selld<EPI, 2, 0>(gen, m, x, e);
+    return gen->code_bytes == 1 ? launch_selld<EPI, 1>(gen, m, x, e) : launch_selld<EPI, 2>(gen, m, x, e);
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};

@@ -536,24 +536,21 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
   }
 }
 
-template <int EPI, int CB, int TC>
+template <int EPI, int CB>
 __global__ void __launch_bounds__(256, 2)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
-             int slices_per_cta, const __grid_constant__ DictConst tc) {
+             int slices_per_cta) {
+  // the table, pre-multiplied by this step's operator coefficients, lives in shared memory
+  // (passing it as a kernel parameter and reading it through the constant cache was 33 %
+  // slower: per-lane indexed LDC serialises on distinct addresses)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // TC: the (pre-multiplied) table is a kernel parameter, read through the constant cache;
-  // otherwise it is built in shared memory from this step's coefficients
-  const double2* s_val = TC ? tc.val : reinterpret_cast<const double2*>(smem_raw);
-  const int32_t* s_delta = TC ? tc.delta : reinterpret_cast<const int32_t*>(smem_raw + sizeof(double2) * m.n_dict);
-  if (!TC) {
-    double2* w_val = reinterpret_cast<double2*>(smem_raw);
-    int32_t* w_delta = reinterpret_cast<int32_t*>(w_val + m.n_dict);
-    for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
-      w_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
-      w_delta[j] = m.ddelta[j];
-    }
-    __syncthreads();
+  double2* s_val = reinterpret_cast<double2*>(smem_raw);
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
+  for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
+    s_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
+    s_delta[j] = m.ddelta[j];
   }
+  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
@@ -686,16 +683,6 @@ struct DeltaOp {
   int32_t op;
 };
 
-template <int G, int T, int CB>
-struct SpmmGroup {  // G consecutive codes of a row (packed) and their gathered x values for T trajectories
-  uint32_t pk[G * CB / 4];
-  double2 xv[G][T];
-  bool any;
-  __device__ __forceinline__ uint32_t code(int g) const {
-    return CB == 1 ? (pk[g >> 2] >> (8 * (g & 3))) & 0xffu : (pk[g >> 1] >> (16 * (g & 1))) & 0xffffu;
-  }
-};
-
 template <int EPI, int CB, int REALV, int T, int G>
 __global__ void __launch_bounds__(256, 2)
 k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, const double2* __restrict__ coef,
@@ -712,7 +699,6 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
   __syncthreads();
 
   constexpr int CPW = 16 / CB;   // codes per 16-byte word
-  constexpr int GPW = CPW / G;   // gather groups per word
   static_assert(CPW % G == 0, "group size must divide the codes per word");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slice = blockIdx.x;
@@ -732,7 +718,6 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
     off0 = m.sptr[slice];
     off1 = m.sptr[slice + 1];
   }
-  const int n_groups = (int)((off1 - off0) / QP_SELL_C) * GPW;
   const int64_t ustride = coef_stride ? batch : 1;
   auto ucoef = [&](int op, int t) {  // u_op of trajectory t (times i for an imaginary operator)
     const double2 u = __ldg(coef + (int64_t)op * ustride + (coef_stride ? bcol[t] : 0));
@@ -757,72 +742,61 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
     }
     int cur_op = -1;
 
-    // decode group gi of this row and issue its gathers
-    auto load = [&](int gi, SpmmGroup<G, T, CB>& grp) {
-      const uint4 c = __ldg(m.codes + off0 + rl + (uint32_t)(gi / GPW) * QP_SELL_C);  // warp-uniform word
+    for (uint32_t off = off0 + rl; off < off1; off += QP_SELL_C) {
+      const uint4 c = __ldg(m.codes + off);  // same word for all lanes: one broadcast load
       const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-      constexpr int WPG = G * CB / 4;  // 32-bit words per group
-      const int h = (gi % GPW) * WPG;
-      uint32_t orv = 0u;
 #pragma unroll
-      for (int j = 0; j < WPG; ++j) {
-        uint32_t v = w[0];
+      for (int h = 0; h < CPW; h += G) {  // G codes x T trajectories = 8 gathers in flight per lane
+        uint32_t code[G];
+        DeltaOp dop[G];
+        double2 xv[G][T];
+        bool any = false;
 #pragma unroll
-        for (int q = 1; q < 4; ++q) v = (h + j == q) ? w[q] : v;
-        grp.pk[j] = v;
-        orv |= v;
-      }
-      grp.any = orv != 0u;
-      if (!grp.any) return;  // all padding (warp-uniform)
+        for (int g = 0; g < G; ++g) {
+          const int tt = h + g;
+          code[g] = CB == 1 ? (w[tt >> 2] >> (8 * (tt & 3))) & 0xffu : (w[tt >> 1] >> (16 * (tt & 1))) & 0xffffu;
+          any |= code[g] != 0u;
+        }
+        if (!any) continue;  // all padding (warp-uniform)
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int64_t o = (int64_t)s_dop[grp.code(g)].delta * batch;
+        for (int g = 0; g < G; ++g) {
+          dop[g] = s_dop[code[g]];
+          const int64_t o = (int64_t)dop[g].delta * batch;
 #pragma unroll
-        for (int t = 0; t < T; ++t) grp.xv[g][t] = __ldg(xb[t] + o);
-      }
-    };
-    auto consume = [&](const SpmmGroup<G, T, CB>& grp) {
-      if (!grp.any) return;
+          for (int t = 0; t < T; ++t) xv[g][t] = __ldg(xb[t] + o);
+        }
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const uint32_t code = grp.code(g);
-        if (code == 0u) continue;  // padding / entry kept in an explicit diagonal
-        const int op = s_dop[code].op;
-        if (op != cur_op) {        // warp-uniform: fold the finished operator
-          if (cur_op >= 0) {
+        for (int g = 0; g < G; ++g) {
+          if (code[g] == 0u) continue;  // padding / entry kept in an explicit diagonal
+          if (dop[g].op != cur_op) {    // warp-uniform: fold the finished operator
+            if (cur_op >= 0) {
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                const double2 u = ucoef(cur_op, t);
+                tr[t] += u.x * pr[t] - u.y * pi[t];
+                ti[t] += u.x * pi[t] + u.y * pr[t];
+                pr[t] = pi[t] = 0.0;
+              }
+            }
+            cur_op = dop[g].op;
+          }
+          if (REALV) {
+            const double v = s_val1[code[g]];
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const double2 u = ucoef(cur_op, t);
-              tr[t] += u.x * pr[t] - u.y * pi[t];
-              ti[t] += u.x * pi[t] + u.y * pr[t];
-              pr[t] = pi[t] = 0.0;
+              pr[t] += v * xv[g][t].x;
+              pi[t] += v * xv[g][t].y;
             }
-          }
-          cur_op = op;
-        }
-        if (REALV) {
-          const double v = s_val1[code];
+          } else {
+            const double2 v = s_val2[code[g]];
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            pr[t] += v * grp.xv[g][t].x;
-            pi[t] += v * grp.xv[g][t].y;
-          }
-        } else {
-          const double2 v = s_val2[code];
-#pragma unroll
-          for (int t = 0; t < T; ++t) {
-            pr[t] += v.x * grp.xv[g][t].x - v.y * grp.xv[g][t].y;
-            pi[t] += v.x * grp.xv[g][t].y + v.y * grp.xv[g][t].x;
+            for (int t = 0; t < T; ++t) {
+              pr[t] += v.x * xv[g][t].x - v.y * xv[g][t].y;
+              pi[t] += v.x * xv[g][t].y + v.y * xv[g][t].x;
+            }
           }
         }
       }
-    };
-    // one group (G codes x T trajectories = 8 gathers per lane) at a time: holding a second group
-    // in flight costs more in registers / decode instructions than it hides (measured: slower)
-    SpmmGroup<G, T, CB> ga;
-    for (int gi = 0; gi < n_groups; ++gi) {
-      load(gi, ga);
-      consume(ga);
     }
     if (cur_op >= 0) {
 #pragma unroll
