@@ -32,7 +32,7 @@ using QuantumPropagators.Cheby: cheby_coeffs
 using QuantumPropagators.Arnoldi: diagonalize_hessenberg_matrix
 using QuantumPropagators.Newton: extend_leja!, extend_newton_coeffs!, leja_radius
 
-export ChebyB200, NewtonB200, DeviceState, to_device, to_host
+export ChebyB200, NewtonB200, DeviceState, to_device, to_host, propagate_on_device!, expval
 
 const libqprop = get(ENV, "QPROP_B200_LIB", joinpath(@__DIR__, "..", "quantumpropagators.jl_b200",
                                                       "csrc", "libqprop_b200.so"))
@@ -278,6 +278,47 @@ function prop_step!(p::ChebyB200Propagator)
     p.inplace || setfield!(p, :state, Ψ)
     _pwc_advance_time!(p)
     return p.state
+end
+
+"""
+    expvals, norms = propagate_on_device!(p::ChebyB200Propagator, observables; norms=false)
+
+The step loop of `propagate` (reference `src/propagate.jl:283-344`) as ONE `ccall`
+(`qp_cheby_propagate`): all remaining intervals of the grid, the amplitudes of every interval
+taken from `p.parameters` up front (legal when no callback can touch them between steps), and
+the expectation values `dot(Ψ, O, Ψ)` of the matrix observables (`src/storage.jl:100-123`)
+recorded on the device before the first and after every step -- no state is downloaded.
+`expvals[k, i]` is observable `k` at grid point `i` in propagation order.
+"""
+function propagate_on_device!(p::ChebyB200Propagator, observables::Vector{<:AbstractMatrix}=AbstractMatrix[]; norms::Bool=false)
+    tlist = getfield(p, :tlist)
+    steps = p.backward ? (p.n:-1:1) : (p.n:length(tlist)-1)
+    n_c = length(getfield(p, :genop).coeffs)
+    table = Matrix{ComplexF64}(undef, n_c, length(steps))      # column-major: [n_steps][n_coeffs] in C order
+    for (s, n) in enumerate(steps)
+        table[:, s] .= _coeffs(_pwc_set_genop!(p, n))
+    end
+    ctx = p.state.ctx
+    gens = [DeviceGenerator(ctx, O) for O in observables]
+    handles = Ptr{Cvoid}[g.handle for g in gens]
+    ev = Matrix{ComplexF64}(undef, length(gens), length(steps) + 1)
+    nr = Vector{Float64}(undef, norms ? length(steps) + 1 : 0)
+    GC.@preserve gens check(ccall((:qp_cheby_propagate, libqprop), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Int32, Float64, Int32, Ptr{Ptr{Cvoid}}, Ptr{ComplexF64}, Ptr{Float64}),
+                p.wrk, p.state.handle, table, 0, length(steps), p.backward ? -p.dt : p.dt, length(gens),
+                isempty(gens) ? C_NULL : handles, isempty(gens) ? C_NULL : ev, norms ? nr : C_NULL), ctx.handle)
+    for _ in steps
+        _pwc_advance_time!(p)
+    end
+    return ev, nr
+end
+
+"""`dot(Ψ, O, Ψ)` of a device-resident state in one fused pass (`qp_gen_expval`)."""
+function expval(G::DeviceGenerator, Ψ::DeviceState, coeffs::Vector{ComplexF64}=ComplexF64[])
+    out = Ref{ComplexF64}(0)
+    check(ccall((:qp_gen_expval, libqprop), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Ref{ComplexF64}),
+                G.handle, coeffs, Ψ.handle, out), Ψ.ctx.handle)
+    return out[]
 end
 
 function reinit_prop!(p::ChebyB200Propagator, state; transform_control_ranges=(c, lo, hi, check) -> (lo, hi), _...)

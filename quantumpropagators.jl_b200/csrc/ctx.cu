@@ -442,18 +442,25 @@ __global__ void k_dot_partial_bn(const double2* __restrict__ x, const double2* _
   }
 }
 
-// final: one thread per batch column sums the block partials in order
+// final: one warp per batch column sums the block partials (fixed order: deterministic)
 __global__ void k_dot_final(const double* __restrict__ partial, int nblocks, int64_t batch,
                             double* __restrict__ out) {
-  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (b >= batch) return;
   double tr = 0, ti = 0;
-  for (int k = 0; k < nblocks; ++k) {
+  for (int k = lane; k < nblocks; k += 32) {
     tr += partial[2 * (k * batch + b) + 0];
     ti += partial[2 * (k * batch + b) + 1];
   }
-  out[2 * b + 0] = tr;
-  out[2 * b + 1] = ti;
+  for (int o = 16; o > 0; o >>= 1) {
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    ti += __shfl_xor_sync(0xffffffffu, ti, o);
+  }
+  if (lane == 0) {
+    out[2 * b + 0] = tr;
+    out[2 * b + 1] = ti;
+  }
 }
 
 template <bool NORM>
@@ -479,7 +486,7 @@ static int32_t reduce_impl(qp_ctx_t ctx, const double2* x, const double2* y, int
     k_dot_partial_bn<NORM><<<grid, block, 0, ctx->stream>>>(x, y, n, batch, partial);
   }
   QP_LAUNCHED(ctx);
-  k_dot_final<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(partial, nblocks, batch, ctx->d_red);
+  k_dot_final<<<(unsigned)((batch * 32 + 127) / 128), 128, 0, ctx->stream>>>(partial, nblocks, batch, ctx->d_red);
   QP_LAUNCHED(ctx);
   QP_CUDA(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * 2 * batch,
                                cudaMemcpyDeviceToHost, ctx->stream));

@@ -20,11 +20,22 @@ struct Weights {
   double2 w[KV];
 };
 
-// partial[block][KV+1][2]: <q_i|w> for i < nv and |w|^2 in slot KV
+// Per-column control block on the device: the whole Arnoldi process runs without a host
+// round trip (the host reads all columns once at the end).
+struct ColCtl {
+  double ww;     // |w|^2 before the projection
+  double nrm2;   // |w|^2 after the (last) projection
+  double inv;    // 1 / |w|, used by the normalisation kernel
+  double again;  // != 0: the DGKS criterion asks for a second projection round
+};
+
+// partial[block][KV+1][2]: <q_i|w> for i < nv and |w|^2 in slot KV.  `gate` (or nullptr): the
+// launch is a no-op unless *gate != 0 (second Gram-Schmidt round, decided on the device).
 template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ w, int64_t n,
-           double* __restrict__ partial) {
+           double* __restrict__ partial, const double* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0.0) return;
   double sr[NV], si[NV], ww = 0.0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) sr[i] = si[i] = 0.0;
@@ -65,30 +76,34 @@ k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __rest
   }
 }
 
-// h[i] = sum_blocks partial[.][i] ;  |w|^2 -> out_ww
-__global__ void k_multidot_final(const double* __restrict__ partial, int nblocks, int nv,
-                                 double2* __restrict__ h, double* __restrict__ out_ww) {
-  int t = threadIdx.x;
-  if (t < nv) {
-    double tr = 0, ti = 0;
-    for (int k = 0; k < nblocks; ++k) {
-      tr += partial[(size_t)k * (2 * KV + 2) + 2 * t];
-      ti += partial[(size_t)k * (2 * KV + 2) + 2 * t + 1];
-    }
-    h[t] = make_double2(tr, ti);
-  }
-  if (t == nv && out_ww) {
-    double s = 0;
-    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * (2 * KV + 2) + 2 * KV];
-    *out_ww = s;
+// deterministic sum over the blocks' partials, one warp per slot (block = (2 KV + 1) warps):
+// h[i] (+)= <q_i|w> ; slot 2 KV -> ctl->ww (first pass of the first round only)
+__global__ void __launch_bounds__(32 * (2 * KV + 1))
+k_multidot_final(const double* __restrict__ partial, int nblocks, int nv, double2* __restrict__ h, int accumulate,
+                 ColCtl* __restrict__ ctl, int write_ww, const double* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0.0) return;
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_ww = slot == 2 * KV;
+  if (!is_ww && slot >= 2 * nv) return;
+  double t = 0.0;
+  for (int k = lane; k < nblocks; k += 32) t += partial[(size_t)k * (2 * KV + 2) + slot];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane != 0) return;
+  if (is_ww) {
+    if (write_ww) ctl->ww = t;
+  } else {
+    double* dst = reinterpret_cast<double*>(h + (slot >> 1)) + (slot & 1);
+    *dst = accumulate ? *dst + t : t;
   }
 }
 
-// w -= sum_i h[i] q_i ; partial[block] = |w_new|^2 contribution
+// w -= sum_i h[i] q_i ; partial[block] = |w_new|^2 contribution.  `h` holds this round's
+// coefficients (round 2 uses its own correction, kept apart from the accumulated column).
 template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h,
-              double2* __restrict__ w, int64_t n, double* __restrict__ partial) {
+              double2* __restrict__ w, int64_t n, double* __restrict__ partial, const double* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0.0) return;
   double2 hv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) hv[i] = h[i];
@@ -115,15 +130,38 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
   }
 }
 
-__global__ void k_sum_partial(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0;
-    for (int k = 0; k < nblocks; ++k) t += partial[k];
-    *out = t;
+// one warp: |w|^2 after the projection; round 1 decides on the device whether a second
+// (DGKS) round is needed -- when the projection removed more than half of |w|^2 -- and the
+// second round adds its correction to the accumulated column
+__global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, ColCtl* __restrict__ ctl, int round,
+                              double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec) {
+  if (round == 2 && ctl->again == 0.0) return;
+  const int lane = threadIdx.x;
+  double t = 0.0;
+  for (int k = lane; k < nblocks; k += 32) t += partial[k];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (round == 2)
+    for (int i = lane; i < nvec; i += 32) {
+      h_acc[i].x += h_corr[i].x;
+      h_acc[i].y += h_corr[i].y;
+    }
+  if (lane == 0) {
+    ctl->nrm2 = t;
+    ctl->inv = 1.0 / sqrt(t);
+    if (round == 1) ctl->again = (t < 0.5 * ctl->ww && t != 0.0) ? 1.0 : 0.0;
   }
 }
 
 __global__ void k_scale_real(double2* __restrict__ x, double s, int64_t n) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double2 v = x[r];
+    x[r] = make_double2(s * v.x, s * v.y);
+  }
+}
+
+// x *= ctl->inv (normalisation with the norm still on the device)
+__global__ void k_scale_dev(double2* __restrict__ x, const ColCtl* __restrict__ ctl, int64_t n) {
+  const double s = ctl->inv;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     double2 v = x[r];
     x[r] = make_double2(s * v.x, s * v.y);
@@ -184,9 +222,13 @@ extern "C" int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max
   K->m_max = m_max;
   cudaError_t e;
   if ((e = cudaMalloc(&K->q, sizeof(double2) * (size_t)K->n * (size_t)(m_max + 1))) != cudaSuccess ||
-      (e = cudaMalloc(&K->d_h, sizeof(double2) * (size_t)(m_max + 8))) != cudaSuccess) {
+      (e = cudaMalloc(&K->d_h, sizeof(double2) * (size_t)(m_max + 8))) != cudaSuccess ||
+      (e = cudaMalloc(&K->d_hall, sizeof(double2) * (size_t)(m_max + 1) * (size_t)(m_max + 2))) != cudaSuccess ||
+      (e = cudaMalloc(&K->d_ctl, sizeof(ColCtl) * (size_t)(m_max + 1))) != cudaSuccess) {
     cudaGetLastError();
     cudaFree(K->q);
+    cudaFree(K->d_h);
+    cudaFree(K->d_hall);
     delete K;
     return qp_fail(ctx, QP_ERR_OOM, "qp_krylov_create: cudaMalloc of %d Krylov vectors failed: %s", m_max + 1,
                    cudaGetErrorString(e));
@@ -201,56 +243,61 @@ extern "C" int32_t qp_krylov_destroy(qp_krylov_t K) {
   cudaStreamSynchronize(K->ctx->stream);
   cudaFree(K->q);
   cudaFree(K->d_h);
+  cudaFree(K->d_hall);
+  cudaFree(K->d_ctl);
   delete K;
   return QP_OK;
 }
 
-// Orthogonalise w = q[j+1] against q[0..j].  On return h_host[0..j] holds <q_i|w> (summed over
-// DGKS rounds) and *norm_out = |w| after projection.
-static int32_t orthogonalise(qp_krylov_t K, int j, std::vector<qp_c128>& h_host, double* norm_out) {
+// Orthogonalise w = q[j+1] against q[0..j], entirely on the stream (no host synchronisation):
+// column j of K->d_hall receives <q_i|w> (summed over the rounds), K->d_ctl[j] the norms.
+// Classical Gram-Schmidt; the second round always gets launched but is a no-op on the device
+// unless the DGKS criterion fired ("twice is enough").
+static int32_t orthogonalise_async(qp_krylov_t K, int j) {
   qp_ctx_t ctx = K->ctx;
   const int64_t n = K->n;
   const int nvec = j + 1;
   double2* w = K->q + (size_t)(j + 1) * n;
   const int nblocks = kgrid(ctx, n);
-  // scratch: [0 .. 2 doubles): ww, nrm ; then partials
-  const size_t need = 4 + (size_t)nblocks * (2 * KV + 2);
+  const size_t need = (size_t)nblocks * (2 * KV + 2);
   QP_CHECK(qp_ctx_reserve_red(ctx, need));
-  double* d_ww = ctx->d_red;
-  double* d_nrm = ctx->d_red + 1;
-  double* partial = ctx->d_red + 4;
-  h_host.assign(nvec, qp_c128{0.0, 0.0});
-  std::vector<double2> h_round(nvec);
-  for (int round = 0; round < 3; ++round) {
-    // column (or correction) h = Q^H w, KV vectors per pass
+  double* partial = ctx->d_red;
+  double2* h_acc = K->d_hall + (size_t)j * (K->m_max + 2);
+  double2* h_corr = K->d_h;  // this round's coefficients
+  ColCtl* ctl = K->d_ctl + j;
+  for (int round = 1; round <= 2; ++round) {
+    const double* gate = round == 2 ? &ctl->again : nullptr;
+    double2* h = round == 1 ? h_acc : h_corr;
     for (int i0 = 0; i0 < nvec; i0 += KV) {
       const int nv = std::min(KV, nvec - i0);
       const double2* q0 = K->q + (size_t)i0 * n;
-      DISPATCH_NV(nv, (k_multidot<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, w, n, partial)));
+      DISPATCH_NV(nv, (k_multidot<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
-      k_multidot_final<<<1, 32, 0, ctx->stream>>>(partial, nblocks, nv, K->d_h + i0, i0 == 0 ? d_ww : nullptr);
+      k_multidot_final<<<1, 32 * (2 * KV + 1), 0, ctx->stream>>>(partial, nblocks, nv, h + i0, 0, ctl,
+                                                                  (round == 1 && i0 == 0) ? 1 : 0, gate);
       QP_LAUNCHED(ctx);
     }
     for (int i0 = 0; i0 < nvec; i0 += KV) {
       const int nv = std::min(KV, nvec - i0);
       const double2* q0 = K->q + (size_t)i0 * n;
-      DISPATCH_NV(nv, (k_project_out<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, K->d_h + i0, w, n, partial)));
+      DISPATCH_NV(nv, (k_project_out<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, h + i0, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
     }
-    k_sum_partial<<<1, 32, 0, ctx->stream>>>(partial, nblocks, d_nrm);
+    k_norm_decide<<<1, 32, 0, ctx->stream>>>(partial, nblocks, ctl, round, h_acc, h_corr, nvec);
     QP_LAUNCHED(ctx);
-    double scal[2];
-    QP_CUDA(ctx, cudaMemcpyAsync(h_round.data(), K->d_h, sizeof(double2) * nvec, cudaMemcpyDeviceToHost, ctx->stream));
-    QP_CUDA(ctx, cudaMemcpyAsync(scal, d_ww, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < nvec; ++i) {
-      h_host[i].re += h_round[i].x;
-      h_host[i].im += h_round[i].y;
-    }
-    *norm_out = sqrt(scal[1]);
-    // DGKS criterion: re-orthogonalise when the projection removed more than half of |w|^2
-    if (!(scal[1] < 0.5 * scal[0]) || scal[1] == 0.0) break;
   }
+  return QP_OK;
+}
+
+// download columns [j0, j1) of the device-side Hessenberg data (one synchronisation)
+static int32_t fetch_columns(qp_krylov_t K, int j0, int j1, std::vector<double2>& h_all, std::vector<ColCtl>& ctl) {
+  qp_ctx_t ctx = K->ctx;
+  const size_t ldh = (size_t)K->m_max + 2;
+  h_all.resize(ldh * (size_t)(j1 - j0));
+  ctl.resize((size_t)(j1 - j0));
+  QP_CUDA(ctx, cudaMemcpyAsync(h_all.data(), K->d_hall + ldh * j0, sizeof(double2) * h_all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  QP_CUDA(ctx, cudaMemcpyAsync(ctl.data(), K->d_ctl + j0, sizeof(ColCtl) * ctl.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return QP_OK;
 }
 
@@ -278,25 +325,35 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
   memset(hess, 0, sizeof(qp_c128) * (size_t)ld * (size_t)ld);  // fill!(Hess, 0)  :78
   const int64_t n = K->n;
   QP_CUDA(ctx, cudaMemcpyAsync(K->q, v->d, sizeof(double2) * n, cudaMemcpyDeviceToDevice, ctx->stream));  // :79
-  std::vector<qp_c128> h;
-  int m_eff = m;
+  // all m columns are enqueued without a host round trip; a column whose norm falls below
+  // norm_min ends the process in the reference (:92-95) -- here the later columns are still
+  // computed (on garbage) and simply discarded when the host reads the norms
   for (int j = 0; j < m; ++j) {
     QP_CHECK(krylov_matvec(K, stride, j));
-    double hn = 0.0;
-    QP_CHECK(orthogonalise(K, j, h, &hn));
-    for (int i = 0; i <= j; ++i) {  // Hess[i,j] = dt <q_i|q_{j+1}>   :85
-      hess[(size_t)j * ld + i].re = dt * h[i].re;
-      hess[(size_t)j * ld + i].im = dt * h[i].im;
-    }
+    QP_CHECK(orthogonalise_async(K, j));
     if (j + 1 < m || extended) {  // :88-97
+      k_scale_dev<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(j + 1) * n, K->d_ctl + j, n);
+      QP_LAUNCHED(ctx);
+    }
+  }
+  std::vector<double2> h_all;
+  std::vector<ColCtl> ctl;
+  QP_CHECK(fetch_columns(K, 0, m, h_all, ctl));
+  const size_t ldh = (size_t)K->m_max + 2;
+  int m_eff = m;
+  for (int j = 0; j < m; ++j) {
+    for (int i = 0; i <= j; ++i) {  // Hess[i,j] = dt <q_i|q_{j+1}>   :85
+      hess[(size_t)j * ld + i].re = dt * h_all[ldh * j + i].x;
+      hess[(size_t)j * ld + i].im = dt * h_all[ldh * j + i].y;
+    }
+    if (j + 1 < m || extended) {
+      const double hn = sqrt(ctl[j].nrm2);
       hess[(size_t)j * ld + (j + 1)].re = dt * hn;
       hess[(size_t)j * ld + (j + 1)].im = 0.0;
       if (hn < norm_min) {  // dimensionality exhausted
         m_eff = j + 1;
         break;
       }
-      k_scale_real<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(j + 1) * n, 1.0 / hn, n);
-      QP_LAUNCHED(ctx);
     }
   }
   *m_out = m_eff;
@@ -324,12 +381,13 @@ extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, in
   k_scale_real<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
   QP_LAUNCHED(ctx);
   QP_CHECK(krylov_matvec(K, stride, m - 1));
-  std::vector<qp_c128> h;
-  double hn2 = 0.0;
-  QP_CHECK(orthogonalise(K, m - 1, h, &hn2));
+  QP_CHECK(orthogonalise_async(K, m - 1));
+  std::vector<double2> h_all;
+  std::vector<ColCtl> ctl;
+  QP_CHECK(fetch_columns(K, m - 1, m, h_all, ctl));
   for (int i = 0; i < m; ++i) {
-    hess[(size_t)(m - 1) * ld + i].re = dt * h[i].re;
-    hess[(size_t)(m - 1) * ld + i].im = dt * h[i].im;
+    hess[(size_t)(m - 1) * ld + i].re = dt * h_all[i].x;
+    hess[(size_t)(m - 1) * ld + i].im = dt * h_all[i].y;
   }
   if (extended_out) *extended_out = 1;
   return QP_OK;

@@ -158,7 +158,9 @@ struct qp_krylov_s {
   int64_t n = 0;
   int m_max = 0;
   double2* q = nullptr;    // (m_max + 1) vectors of length n, contiguous
-  double2* d_h = nullptr;  // device Hessenberg column (m_max + 2 complex)
+  double2* d_h = nullptr;  // device Hessenberg column (m_max + 2 complex): correction of a second GS round
+  double2* d_hall = nullptr;      // all columns, [m_max + 1][m_max + 2]
+  struct ColCtl* d_ctl = nullptr; // per-column norms / DGKS flag, [m_max + 1] (krylov.cu)
 };
 
 // ---------------------------------------------------------------------------------------
