@@ -213,6 +213,39 @@ int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* w, int32_t first, int32_
 int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst);
 int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src);
 
+/* newton! (src/newton.jl:246-385) as ONE call: psi <- func(H dt) psi by restarted Newton
+ * interpolation at Leja-ordered Ritz values.  The Arnoldi process and the vector updates run
+ * on the device, the small dense step (Ritz values of the Hessenberg blocks, Leja ordering,
+ * divided differences, polynomial in the Hessenberg matrix) on the host inside the library.
+ *   v:        work state of the same shape (the reference's NewtonWrk.v)
+ *   func_id:  QP_FUNC_EXPMI  exp(-i z)  (default of the reference, TDSE)
+ *             QP_FUNC_EXP    exp(z)     (`func = exp` for Liouvillians in the :LvN convention)
+ *             QP_FUNC_CALLBACK  `func` is called at the Leja points only (any analytic function)
+ *   K:        Krylov workspace with m_max > 2 (NewtonWrk, src/newton.jl:23-60)
+ * Fails with QP_ERR_NOT_CONVERGED after max_restarts (the `@assert` of src/newton.jl:375).
+ * The fine-grained entry points above remain for hosts that keep the dense step themselves. */
+#define QP_FUNC_EXPMI 0
+#define QP_FUNC_EXP 1
+#define QP_FUNC_CALLBACK 2
+typedef void (*qp_newton_func_t)(const qp_c128* z, qp_c128* f_of_z, void* user);
+int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, const qp_c128* op_coeffs, double dt,
+                       int32_t func_id, qp_newton_func_t func, void* user, double norm_min, double relerr,
+                       int32_t max_restarts, int32_t* restarts_out);
+
+/* The host-side pieces of newton! on their own (pure host code, no device needed):
+ *   diagonalize_hessenberg_matrix(Hess, m; accumulate)   src/arnoldi.jl:143-170
+ *     hess column-major ld x ld; out receives m values, or m(m+1)/2 when accumulate != 0
+ *     (blocks 1..m concatenated); each block sorted by (real, imag) like Julia's eigvals
+ *   extend_leja!(leja, n, newpoints, n_use)              src/newton.jl:97-148  (newpoints is clobbered)
+ *   extend_newton_coeffs!(a, n_a, leja, func, n_leja, radius)   src/newton.jl:176-214 */
+int32_t qp_diagonalize_hessenberg(const qp_c128* hess, int32_t ld, int32_t m, int32_t accumulate,
+                                  qp_c128* out, int32_t* n_out);
+int32_t qp_extend_leja(qp_c128* leja, int32_t capacity, int32_t* n, qp_c128* newpoints, int32_t n_new,
+                       int32_t n_use);
+int32_t qp_extend_newton_coeffs(qp_c128* a, int32_t capacity, int32_t* n_a, const qp_c128* leja,
+                                int32_t n_leja, int32_t func_id, qp_newton_func_t func, void* user,
+                                double radius);
+
 #ifdef __cplusplus
 }
 #endif

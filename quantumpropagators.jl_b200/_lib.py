@@ -110,9 +110,16 @@ SIGNATURES = {
     "qp_arnoldi": (_i32, [_vp, _vp, _vp, _i32, _f64, _i32, _f64, _vp, _i32, _P(_i32)]),
     "qp_arnoldi_extend": (_i32, [_vp, _vp, _i32, _f64, _f64, _vp, _i32, _P(_i32)]),
     "qp_krylov_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32]),
+    "qp_newton_step": (_i32, [_vp, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _f64, _f64, _i32, _P(_i32)]),
+    "qp_diagonalize_hessenberg": (_i32, [_vp, _i32, _i32, _i32, _vp, _P(_i32)]),
+    "qp_extend_leja": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32]),
+    "qp_extend_newton_coeffs": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32, _vp, _vp, _f64]),
     "qp_krylov_get": (_i32, [_vp, _i32, _vp]),
     "qp_krylov_set": (_i32, [_vp, _i32, _vp]),
 }
+
+QP_FUNC_EXPMI, QP_FUNC_EXP, QP_FUNC_CALLBACK = 0, 1, 2
+NEWTON_FUNC = C.CFUNCTYPE(None, _P(c128), _P(c128), _vp)
 
 _lib = None
 

@@ -232,10 +232,49 @@ def _default_func(z):
     return np.exp(-1j * z)
 
 
+def _newton_library(Psi, H, dt, wrk, func, norm_min, relerr, max_restarts, coeffs):
+    """One ``qp_newton_step`` call: Arnoldi + vector updates on the device, the Ritz / Leja /
+    divided-difference step in C++ inside the library (no per-restart host-language work)."""
+    K = wrk.krylov
+    c = _op_coeffs(H, K.gen, coeffs)
+    cb = None
+    if func is None or func is _default_func:
+        func_id = L.QP_FUNC_EXPMI
+    elif func is np.exp:
+        func_id = L.QP_FUNC_EXP
+    else:
+        func_id = L.QP_FUNC_CALLBACK
+
+        def _trampoline(z_ptr, out_ptr, _user):
+            f = complex(func(complex(z_ptr[0].re, z_ptr[0].im)))
+            out_ptr[0].re, out_ptr[0].im = f.real, f.imag
+
+        cb = L.NEWTON_FUNC(_trampoline)
+    restarts = C.c_int32()
+    L.check(
+        K.ctx._lib.qp_newton_step(
+            K.handle, Psi.handle, wrk.v.handle, L.ptr(c), float(dt), func_id,
+            C.cast(cb, C.c_void_p) if cb is not None else None, None,
+            float(norm_min), float(relerr), int(max_restarts), C.byref(restarts),
+        ),
+        K.ctx.handle,
+    )
+    wrk.restarts = restarts.value
+    return Psi
+
+
 def newton_(Psi: DeviceState, H, dt, wrk: NewtonWrk, func=None, norm_min=1e-14, relerr=1e-12, max_restarts=50,
-            coeffs=None) -> DeviceState:
+            coeffs=None, host_step="library") -> DeviceState:
     """``newton!(Ψ, H, dt, wrk; func, norm_min, relerr, max_restarts)`` (reference
-    ``src/newton.jl:246-385``): Ψ ← func(H dt) Ψ in place on the device."""
+    ``src/newton.jl:246-385``): Ψ ← func(H dt) Ψ in place on the device.
+
+    ``host_step="library"`` (default) runs the whole restart loop inside ``qp_newton_step``;
+    ``host_step="python"`` keeps the small dense step in this module (the fine-grained ABI the
+    Julia wrapper uses: ``qp_arnoldi`` + ``qp_krylov_combine``), filling ``wrk.a`` / ``wrk.leja``."""
+    if float(dt) == 0.0:
+        raise AssertionError("dt must be non-zero")
+    if host_step == "library":
+        return _newton_library(Psi, H, dt, wrk, func, norm_min, relerr, max_restarts, coeffs)
     func = _default_func if func is None else func
     K = wrk.krylov
     m = wrk.m_max

@@ -201,3 +201,110 @@ def test_workloads_shapes():
     lhs = (L1.toarray() @ rho.reshape(-1, order="F")).reshape(8, 8, order="F")
     assert np.allclose(lhs, H1s.toarray() @ rho - rho @ H1s.toarray())
     assert W.optomech().shape == (55, 55)
+
+
+# ---------------------------------------------------------------------------------------
+# host-side math of qp_newton_step (pure C++, no device): against the oracle's restatement of
+# src/arnoldi.jl:143-170 and src/newton.jl:97-214
+# ---------------------------------------------------------------------------------------
+
+
+def _host_lib():
+    from qprop_b200 import _lib
+
+    return _lib, _lib.load()
+
+
+def test_library_ritz_values_match_oracle():
+    import ctypes as C
+    import importlib
+
+    OA = importlib.import_module("oracle.arnoldi")
+    _lib, lib = _host_lib()
+    rng = np.random.default_rng(1)
+    for trial in range(120):
+        m = int(rng.integers(1, 41))
+        ld = m + 1
+        A = rng.standard_normal((ld, ld)) + 1j * rng.standard_normal((ld, ld))
+        if trial % 3 == 0:  # Hermitian tridiagonal (Lanczos-like, real spectrum)
+            A = (A + A.conj().T) / 2
+            H = np.tril(np.triu(A, -1), 1)
+        elif trial % 3 == 1:  # general upper Hessenberg
+            H = np.triu(A, -1)
+        else:  # nearly decoupled blocks (tiny sub-diagonal entries)
+            H = np.triu(A, -1)
+            for k in range(1, ld, 3):
+                H[k, k - 1] *= 1e-13
+        Hf = np.asfortranarray(H, dtype=np.complex128)
+        for acc in (0, 1):
+            ref = OA.diagonalize_hessenberg_matrix(H, m, accumulate=bool(acc))
+            out = np.zeros(m * (m + 1) // 2, dtype=np.complex128)
+            n = C.c_int32()
+            rc = lib.qp_diagonalize_hessenberg(Hf.ctypes.data_as(C.c_void_p), ld, m, acc, out.ctypes.data_as(C.c_void_p), C.byref(n))
+            assert rc == 0
+            got = out[: n.value]
+            assert n.value == len(ref)
+            scale = max(1.0, float(np.max(np.abs(ref))))
+            # as multisets (ties in the (real, imag) order may resolve differently at rounding level)
+            used = np.zeros(len(ref), dtype=bool)
+            for z in got:
+                d = np.abs(ref - z)
+                d[used] = np.inf
+                k = int(np.argmin(d))
+                assert d[k] < 1e-9 * scale * (m if trial % 3 else 1), (trial, m, d[k])
+                used[k] = True
+
+
+def test_library_leja_and_newton_coeffs_match_oracle():
+    import ctypes as C
+    import importlib
+
+    ON = importlib.import_module("oracle.newton")
+    _lib, lib = _host_lib()
+    rng = np.random.default_rng(2)
+    for trial in range(30):
+        m = int(rng.integers(3, 12))
+        cap = 10 * m + 1
+        leja_ref = np.zeros(cap, dtype=np.complex128)
+        a_ref = np.zeros(cap, dtype=np.complex128)
+        leja_lib, a_lib = leja_ref.copy(), a_ref.copy()
+        n_ref = na_ref = 0
+        n_lib, na_lib = C.c_int32(0), C.c_int32(0)
+        radius = None
+        for restart in range(3):  # three restarts extend the same sequences
+            pts = (rng.standard_normal(m * (m + 1) // 2) + 0.3j * rng.standard_normal(m * (m + 1) // 2)) * 2.0
+            if radius is None:
+                radius = ON.leja_radius(pts)
+            p1, p2 = pts.copy(), pts.copy()
+            n_ref, leja_ref = ON.extend_leja(leja_ref, n_ref, p1, m)
+            assert lib.qp_extend_leja(leja_lib.ctypes.data_as(C.c_void_p), cap, C.byref(n_lib),
+                                      p2.ctypes.data_as(C.c_void_p), len(p2), m) == 0
+            assert n_lib.value == n_ref
+            np.testing.assert_array_equal(leja_lib[:n_ref], leja_ref[:n_ref])  # same selection, bit for bit
+            na_ref, a_ref = ON.extend_newton_coeffs(a_ref, na_ref, leja_ref, lambda z: np.exp(-1j * z), n_ref, radius)
+            assert lib.qp_extend_newton_coeffs(a_lib.ctypes.data_as(C.c_void_p), cap, C.byref(na_lib),
+                                               leja_lib.ctypes.data_as(C.c_void_p), n_ref, _lib.QP_FUNC_EXPMI, None, None,
+                                               float(radius)) == 0
+            assert na_lib.value == na_ref
+            # divided differences of high order are ill-conditioned coefficient by coefficient
+            # (the two sides round differently), the interpolant they define is not: compare
+            # the Newton polynomials at points inside the cloud, and the leading coefficients
+            assert np.max(np.abs(a_lib[:m] - a_ref[:m])) <= 1e-10 * np.max(np.abs(a_ref[:m]))
+            for z in pts[:5] * 0.7:
+                vals = []
+                for a in (a_lib, a_ref):
+                    acc, prod = 0.0j, 1.0 + 0.0j
+                    for k in range(na_ref):
+                        acc += a[k] * prod
+                        prod *= (z - leja_ref[k]) / radius
+                    vals.append(acc)
+                assert abs(vals[0] - vals[1]) <= 1e-9 * max(1.0, abs(vals[1]))
+        # callback form of func
+        cb = _lib.NEWTON_FUNC(lambda z, out, user: (setattr(out[0], "re", float(np.exp(z[0].re + 1j * z[0].im).real)),
+                                                     setattr(out[0], "im", float(np.exp(z[0].re + 1j * z[0].im).imag)), None)[2])
+        a_cb, a_exp = np.zeros(cap, dtype=np.complex128), np.zeros(cap, dtype=np.complex128)
+        for arr, fid, fn in ((a_cb, _lib.QP_FUNC_CALLBACK, C.cast(cb, C.c_void_p)), (a_exp, _lib.QP_FUNC_EXP, None)):
+            na = C.c_int32(0)
+            assert lib.qp_extend_newton_coeffs(arr.ctypes.data_as(C.c_void_p), cap, C.byref(na),
+                                               leja_lib.ctypes.data_as(C.c_void_p), m, fid, fn, None, float(radius)) == 0
+        assert np.max(np.abs(a_cb[:m] - a_exp[:m])) <= 1e-12 * np.max(np.abs(a_exp[:m]))

@@ -776,3 +776,32 @@ def test_cheby_propagate_norms_batched(qp, ctx):
         assert np.allclose(ev[s, 0], np.einsum("ib,ib->b", st2.to_host().conj(), H0 @ st2.to_host()), atol=1e-12)
         qp.cheby_(st2, None, 0.5, wrk, coeffs=table[s], per_trajectory=True)
     assert rel(st.to_host(), st2.to_host()) < 1e-14
+
+
+@pytest.mark.parametrize("hermitian", [True, False])
+def test_newton_library_vs_python_host_step(qp, ctx, hermitian):
+    """qp_newton_step (dense step in C++ inside the library) against the fine-grained path
+    (qp_arnoldi + qp_krylov_combine with the dense step in this package's Python mirror) and
+    against dense exp; also a func given as a callback."""
+    rng = np.random.default_rng(90 + hermitian)
+    n = 300
+    A = rand_sparse(rng, n, 0.05, hermitian=hermitian)
+    if not hermitian:
+        A = A - 0.2j * sp.identity(n)  # dissipative
+    psi = rand_state(rng, n)
+    dt = 0.3
+    expected = sla.expm(-1j * dt * A.toarray()) @ psi
+    outs = {}
+    for mode in ("library", "python"):
+        st = qp.DeviceState.from_host(ctx, psi)
+        wrk = qp.NewtonWrk(st, A, m_max=10)
+        qp.newton_(st, A, dt, wrk, coeffs=[], host_step=mode)
+        outs[mode] = (st.to_host(), wrk.restarts)
+        assert rel(outs[mode][0], expected) < RTOL
+    assert outs["library"][1] == outs["python"][1]  # same number of restarts
+    assert rel(outs["library"][0], outs["python"][0]) < 1e-12
+    # arbitrary func through the callback: exp(-i z) written by hand must give the same answer
+    st = qp.DeviceState.from_host(ctx, psi)
+    wrk = qp.NewtonWrk(st, A, m_max=10)
+    qp.newton_(st, A, dt, wrk, coeffs=[], func=lambda z: np.cos(z) - 1j * np.sin(z))
+    assert rel(st.to_host(), expected) < RTOL
