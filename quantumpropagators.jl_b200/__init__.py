@@ -26,6 +26,21 @@ from .generators import (  # noqa: F401
     evaluate,
     evaluate_,
     get_controls,
+    substitute,
+    liouvillian,
+)
+from . import interfaces  # noqa: F401
+from .interfaces import (  # noqa: F401
+    check_amplitude,
+    check_control,
+    check_generator,
+    check_operator,
+    check_propagator,
+    check_state,
+    check_tlist,
+    supports_inplace,
+    supports_matrix_interface,
+    supports_vector_interface,
 )
 from .cheby import cheby_coeffs, cheby_coeffs_, ChebyWrk, cheby_, cheby, cheby_propagate_  # noqa: F401
 from .newton import (  # noqa: F401

@@ -16,6 +16,7 @@ __all__ = [
     "t_mid",
     "evaluate",
     "get_controls",
+    "substitute",
 ]
 
 
@@ -170,3 +171,12 @@ def evaluate(obj, *args, vals_dict=None):
             "or on the midpoints of `tlist`"
         )
     return obj
+
+
+def substitute(obj, replacements):
+    """``substitute(object, replacements)`` for controls and amplitudes (reference
+    ``src/controls.jl:476-500``): an object that is a key of ``replacements`` (by identity) is
+    replaced, anything else is returned unchanged."""
+    if isinstance(replacements, dict):
+        replacements = IdDict(replacements)
+    return replacements.get(obj, obj)

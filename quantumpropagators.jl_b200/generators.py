@@ -25,6 +25,10 @@ __all__ = [
     "evaluate",
     "evaluate_",
     "get_controls",
+    "substitute",
+    "liouvillian",
+    "ham_to_superop",
+    "lindblad_to_superop",
 ]
 
 
@@ -272,3 +276,121 @@ def evaluate_(op, generator, *args, vals_dict=None):
             raise AssertionError("amplitude does not evaluate to a number")
         op.coeffs[i] = c
     return op
+
+
+def substitute(generator, replacements):
+    """``substitute(generator, replacements)`` (reference ``src/controls.jl:476-520``,
+    ``src/generators.jl:769-782``): replaces operators and amplitudes / controls by identity;
+    tuple generators are substituted term by term."""
+    if isinstance(replacements, dict):
+        replacements = _controls.IdDict(replacements)
+    if generator in replacements:
+        return replacements[generator]
+    if isinstance(generator, (tuple, list)):
+        out = []
+        for term in generator:
+            if isinstance(term, (tuple, list)):
+                op, ampl = term
+                out.append((substitute(op, replacements), _controls.substitute(ampl, replacements)))
+            else:
+                out.append(substitute(term, replacements))
+        return tuple(out)
+    if isinstance(generator, Generator):
+        ops = [substitute(op, replacements) for op in generator.ops]
+        amplitudes = [_controls.substitute(a, replacements) for a in generator.amplitudes]
+        if all(a is b for a, b in zip(ops, generator.ops)) and all(a is b for a, b in zip(amplitudes, generator.amplitudes)):
+            return generator
+        return Generator(ops, amplitudes)
+    if isinstance(generator, Operator):
+        ops = [substitute(op, replacements) for op in generator.ops]
+        if all(a is b for a, b in zip(ops, generator.ops)):
+            return generator
+        return Operator(ops, list(generator.coeffs))
+    return generator
+
+
+# ---------------------------------------------------------------------------------------
+# Liouvillian super-operators (reference src/generators.jl:470-632; column-stacking vec)
+# ---------------------------------------------------------------------------------------
+
+
+def _check_convention(convention):
+    if convention not in ("TDSE", "LvN"):
+        raise ValueError("convention must be TDSE or LvN")
+
+
+def ham_to_superop(H, convention):
+    """𝟙⊗H − Hᵀ⊗𝟙 for ``convention="TDSE"``, times i for ``"LvN"`` (reference
+    ``src/generators.jl:470-488``; arXiv:1312.0111 App. B.2)."""
+    _check_convention(convention)
+    H = sp.csr_matrix(H, dtype=np.complex128)
+    ident = sp.identity(H.shape[0], dtype=np.complex128, format="csr")
+    Lop = (sp.kron(ident, H, format="csr") - sp.kron(H.T.tocsr(), ident, format="csr")).tocsr()
+    if convention == "LvN":
+        Lop = (1j * Lop).tocsr()
+    Lop.eliminate_zeros()
+    Lop.sort_indices()
+    return Lop
+
+
+def lindblad_to_superop(A, convention):
+    """(A†)ᵀ⊗A − (𝟙⊗A†A)/2 − ((A†A)ᵀ⊗𝟙)/2 for ``"LvN"``, times i for ``"TDSE"`` (reference
+    ``src/generators.jl:491-508``)."""
+    _check_convention(convention)
+    A = sp.csr_matrix(A, dtype=np.complex128)
+    Ad = A.conj().T.tocsr()
+    AdA = (Ad @ A).tocsr()
+    ident = sp.identity(A.shape[0], dtype=np.complex128, format="csr")
+    D = (
+        sp.kron(Ad.T.tocsr(), A, format="csr")
+        - sp.kron(ident, AdA, format="csr") / 2
+        - sp.kron(AdA.T.tocsr(), ident, format="csr") / 2
+    ).tocsr()
+    if convention == "TDSE":
+        D = (1j * D).tocsr()
+    D.eliminate_zeros()
+    D.sort_indices()
+    return D
+
+
+def _dissipator(c_ops, convention):
+    n = c_ops[0].shape[0]
+    if c_ops[0].shape[1] != n:
+        raise AssertionError("Lindblad operators must be square")
+    D = sp.csr_matrix((n * n, n * n), dtype=np.complex128)
+    for A in c_ops:
+        D = D + lindblad_to_superop(A, convention)
+    D = D.tocsr()
+    D.sort_indices()
+    return D
+
+
+def liouvillian(H, c_ops=(), *, convention, check=True):
+    """``liouvillian(Ĥ, c_ops; convention)`` (reference ``src/generators.jl:520-632``): the
+    sparse Liouvillian super-operator of a Hamiltonian (matrix, ``Generator`` / ``Operator`` or
+    tuple of terms; ``None`` for a pure dissipator) and Lindblad operators ``c_ops``, acting on
+    column-stacked density matrices.  A time-dependent Ĥ gives a ``Generator`` with the same
+    amplitudes: drift commutator + dissipator first, then one commutator per control term.
+    ``convention`` is mandatory, as in the reference."""
+    _check_convention(convention)
+    c_ops = list(c_ops)
+    if isinstance(H, (tuple, list)):
+        H = hamiltonian(*H, check=check)
+    terms = []
+    if H is None:
+        if not c_ops:
+            raise ValueError("Empty Liouvillian, must give at least one of `H` or `c_ops`")
+        return hamiltonian(_dissipator(c_ops, convention), check=check)
+    if isinstance(H, (Generator, Operator)):
+        if c_ops:
+            terms.append(_dissipator(c_ops, convention))
+        second = H.amplitudes if isinstance(H, Generator) else H.coeffs
+        drift = len(H.ops) - len(second)
+        for i, op in enumerate(H.ops):
+            term = ham_to_superop(op, convention)
+            terms.append(term if i < drift else (term, second[i - drift]))
+        return hamiltonian(*terms, check=check)
+    terms.append(ham_to_superop(H, convention))
+    if c_ops:
+        terms.append(_dissipator(c_ops, convention))
+    return hamiltonian(*terms, check=check)

@@ -206,34 +206,15 @@ def config3_transmon(n_sites=8, levels=4, B=1024, nt=101, dt=0.5):
 
 
 def ham_to_superop(H, convention="TDSE"):
-    """𝟙⊗H − Hᵀ⊗𝟙 (×i for LvN) -- formulas of reference ``src/generators.jl:473-490``."""
-    H = sp.csr_matrix(H, dtype=np.complex128)
-    ident = sp.identity(H.shape[0], dtype=np.complex128, format="csr")
-    L = sp.kron(ident, H, format="csr") - sp.kron(H.T.tocsr(), ident, format="csr")
-    if convention == "TDSE":
-        return L.tocsr()
-    if convention == "LvN":
-        return (1j * L).tocsr()
-    raise ValueError("convention must be TDSE or LvN")
+    from .generators import ham_to_superop as f
+
+    return f(H, convention)
 
 
 def lindblad_to_superop(A, convention="TDSE"):
-    """(A†)ᵀ⊗A − (𝟙⊗A†A)/2 − ((A†A)ᵀ⊗𝟙)/2 (×i for TDSE) -- reference
-    ``src/generators.jl:493-513``."""
-    A = sp.csr_matrix(A, dtype=np.complex128)
-    Ad = A.conj().T.tocsr()
-    AdA = (Ad @ A).tocsr()
-    ident = sp.identity(A.shape[0], dtype=np.complex128, format="csr")
-    D = (
-        sp.kron(Ad.T.tocsr(), A, format="csr")
-        - sp.kron(ident, AdA, format="csr") / 2
-        - sp.kron(AdA.T.tocsr(), ident, format="csr") / 2
-    )
-    if convention == "TDSE":
-        return (1j * D).tocsr()
-    if convention == "LvN":
-        return D.tocsr()
-    raise ValueError("convention must be TDSE or LvN")
+    from .generators import lindblad_to_superop as f
+
+    return f(A, convention)
 
 
 def config4_liouvillian(n_spins=12, gamma=0.05, J=1.0, nt=21, dt=0.05, seed=4000):

@@ -1,0 +1,115 @@
+"""GPU tests: the device-resident types pass the reference's interface checks
+(``check_state`` / ``check_operator`` / ``check_generator`` / ``check_propagator``, mirror of
+``test/test_prop_interfaces.jl`` and ``test/test_invalid_interfaces.jl``), and the Liouvillian
+generator built by ``liouvillian`` propagates to the reference test's analytic answer."""
+
+import logging
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_state(rng, n, B=None):
+    shape = (n,) if B is None else (n, B)
+    psi = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    return psi / np.linalg.norm(psi, axis=0)
+
+
+@pytest.mark.parametrize("n,B", [(2, None), (1000, None), (300, 7)])
+def test_device_state_passes_check_state(qp, ctx, n, B):
+    rng = np.random.default_rng(n)
+    st = qp.DeviceState.from_host(ctx, rand_state(rng, n, B))
+    assert qp.supports_inplace(st) and not qp.supports_vector_interface(st)
+    assert qp.check_state(st, normalized=True)
+    st.lmul(3.0)
+    assert qp.check_state(st) and not qp.check_state(st, normalized=True, quiet=True)
+
+
+@pytest.mark.parametrize("kind", ["csr", "dense", "lazy_sum", "scaled"])
+def test_device_operators_pass_check_operator(qp, ctx, kind):
+    rng = np.random.default_rng(3)
+    n = 200
+    A = sp.random(n, n, density=0.05, random_state=np.random.RandomState(1), format="csr") * (1 + 0.5j)
+    A = (A + A.conj().T).tocsr()
+    Bm = sp.diags(rng.standard_normal(n) + 0j, 0, format="csr")
+    op = {
+        "csr": A,
+        "dense": np.asarray(A.toarray()),
+        "lazy_sum": qp.Operator([A, Bm], [0.3 - 0.1j]),
+        "scaled": 2.5 * qp.Operator([A, Bm], [0.3]),
+    }[kind]
+    st = qp.DeviceState.from_host(ctx, rand_state(rng, n))
+    assert qp.check_operator(op, state=st, tlist=np.linspace(0, 1, 5))
+    # batched states: the operator verbs act on every trajectory
+    stB = qp.DeviceState.from_host(ctx, rand_state(rng, n, 20))
+    assert qp.check_operator(op, state=stB)
+
+
+def test_check_operator_reports_dimension_mismatch(qp, ctx, caplog):
+    st = qp.DeviceState.from_host(ctx, rand_state(np.random.default_rng(0), 10))
+    with caplog.at_level(logging.ERROR, logger="qprop_b200.interfaces"):
+        assert not qp.check_operator(sp.identity(11, dtype=complex, format="csr"), state=st)
+    assert "`op * state` must be defined" in caplog.text and "dimension" in caplog.text
+
+
+def test_generator_passes_check_generator(qp, ctx):
+    w = qp.workloads.config2_tfim(8, nt=11, dt=0.1)
+    G = qp.hamiltonian(w["ops"][0], (w["ops"][1], w["controls"][0]), (w["ops"][2], w["controls"][1]))
+    st = qp.DeviceState.from_host(ctx, w["psi0"])
+    assert qp.check_generator(G, state=st, tlist=w["tlist"], for_time_continuous=True)
+    # tuple generators are canonicalised through hamiltonian()
+    assert qp.check_generator((w["ops"][0], (w["ops"][1], w["controls"][0])), state=st, tlist=w["tlist"])
+    # an amplitude that is not a number on the grid is reported
+    bad = qp.hamiltonian(w["ops"][0], (w["ops"][1], lambda t: "x"))
+    assert not qp.check_generator(bad, state=st, tlist=w["tlist"], quiet=True)
+
+
+@pytest.mark.parametrize("method,backward,inplace", [("cheby", False, True), ("cheby", True, True), ("newton", False, True), ("cheby", False, False)])
+def test_propagators_pass_check_propagator(qp, ctx, method, backward, inplace):
+    w = qp.workloads.config1_random(N=40, density=0.3, seed=21, nt=21, T=1.0)
+    G = qp.hamiltonian(w["ops"][0], (w["ops"][1], w["controls"][0]))
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"]) if method == "cheby" else {}
+    state = qp.DeviceState.from_host(ctx, w["psi0"]) if inplace else w["psi0"]
+    p = qp.init_prop(state, G, w["tlist"], method, ctx=ctx, backward=backward, inplace=inplace, **kw)
+    assert qp.check_propagator(p)
+
+
+def test_liouvillian_tls_dissipation_newton_on_device(qp, ctx):
+    """test/test_liouvillian.jl "TLS dissipation" through the device Newton propagator (the
+    reference uses expprop): analytic density matrix after T = 1."""
+    g1, g2, T = 0.5, 0.2, 1.0
+    A1 = np.sqrt(g1) * np.array([[0, 1], [0, 0]], dtype=complex)
+    A2 = np.sqrt(2 * g2) * np.array([[0, 0], [0, 1]], dtype=complex)
+    psi0 = np.array([1, 1], dtype=complex) / np.sqrt(2)
+    rho0 = np.outer(psi0, psi0.conj()).reshape(-1, order="F")
+    L = qp.liouvillian(None, [A1, A2], convention="TDSE")
+    tlist = np.linspace(0.0, T, 11)
+    out = qp.propagate(rho0, L, tlist, "newton", ctx=ctx)
+    rho = np.asarray(out).reshape(2, 2, order="F")
+    e1, e2 = np.exp(-g1 * T), np.exp(-(g1 / 2 + g2) * T)
+    expected = 0.5 * np.array([[2 - e1, e2], [e2, e1]], dtype=complex)
+    assert abs(1 - np.trace(rho)) < 1e-12
+    assert np.linalg.norm(rho - expected) < 1e-12
+
+
+def test_liouvillian_generator_vs_oracle(qp, ctx):
+    """Driven, dissipative two-spin system: liouvillian(hamiltonian(...), c_ops) on the device
+    (Newton) against the oracle on the same super-operators."""
+    w = qp.workloads.config2_tfim(2, nt=9, dt=0.1)
+    H = qp.hamiltonian(w["ops"][0], (w["ops"][1], w["controls"][0]))
+    sm = np.array([[0, 1], [0, 0]], dtype=complex)
+    c_ops = [np.sqrt(0.05) * np.kron(sm, np.eye(2)), np.sqrt(0.05) * np.kron(np.eye(2), sm)]
+    Lg = qp.liouvillian(H, c_ops, convention="TDSE")
+    assert isinstance(Lg, qp.Generator) and qp.get_controls(Lg) == (w["controls"][0],)
+    rng = np.random.default_rng(2)
+    psi = rand_state(rng, 4)
+    rho0 = np.outer(psi, psi.conj()).reshape(-1, order="F")
+    out = qp.propagate(rho0, Lg, w["tlist"], "newton", ctx=ctx)
+    ref = O.propagate(rho0, O.hamiltonian(Lg.ops[0], (Lg.ops[1], w["controls"][0])), w["tlist"], "newton")
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 1e-10
+    assert abs(np.trace(np.asarray(out).reshape(4, 4, order="F")) - 1) < 1e-10
