@@ -990,32 +990,42 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   return QP_OK;
 }
 
-template <int EPI, int CB, int REALV, int T, int G>
+template <int EPI, int CB, int REALV, int T, int G, int LATE>
 static int32_t launch_spmm_selld_t(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
   const DictView m = make_dict_view(gen);
   const int64_t chunks = (batch + 32 * T - 1) / (32 * T);
   if (chunks > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "batch too large for one launch");
   const size_t smem = ((size_t)gen->n_dict * ((REALV ? 8 : 16) + sizeof(DeltaOp)) + 127) / 128 * 128;
-  auto kern = k_spmm_selld<EPI, CB, REALV, T, G>;
+  auto kern = k_spmm_selld<EPI, CB, REALV, T, G, LATE>;
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ctx->smem_configured.insert((const void*)kern);
   }
-  dim3 grid((unsigned)gen->n_slices, (unsigned)chunks);
-  kern<<<grid, 256, smem, ctx->stream>>>(m, gen->d_dvalr, gen->imag_ops, gen->d_coef, coef_stride, batch, x, e);
+  static const int spc_env = getenv("QPROP_SPMM_SPC") ? atoi(getenv("QPROP_SPMM_SPC")) : 1;
+  const int spc = spc_env > 0 ? spc_env : 1;
+  dim3 grid((unsigned)((gen->n_slices + spc - 1) / spc), (unsigned)chunks);
+  kern<<<grid, 256, smem, ctx->stream>>>(m, gen->d_dvalr, gen->imag_ops, gen->d_coef, coef_stride, batch, x, e, spc);
   QP_LAUNCHED(ctx);
   return QP_OK;
 }
 
 template <int EPI>
 static int32_t launch_spmm_selld(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
-  // two trajectory chunks per lane amortise the row decode (QPROP_SPMM_T=1 forces one)
+  // The row decode (code words, table lookups, operator changes) is paid once per warp and row:
+  // T trajectory chunks per lane amortise it.  Measured on config 3 (N = 2^16, B = 1024, 45 entries
+  // per row): 5.72 / 3.59 / 2.86 ms per term for T = 1 / 2 / 4, i.e. ~4.3 ms / T of decode on top of
+  // ~1.5 ms of per-trajectory work (the 16-byte gathers through L1: 46 GB per term).  T = 4 (128
+  // trajectories per warp) when the batch is large enough and the chunk's slice of x
+  // (N x 128 x 16 B; 134 MB on config 3, measured fine) does not exceed L2 by much;
+  // QPROP_SPMM_T forces 1 / 2 / 4.
   static const int t_env = getenv("QPROP_SPMM_T") ? atoi(getenv("QPROP_SPMM_T")) : 0;
-  const bool two = t_env ? t_env == 2 : batch > 32;
+  int tsel = batch > 64 && (int64_t)gen->n * 128 * 16 <= (int64_t)144 << 20 ? 4 : batch > 32 ? 2 : 1;
+  if (t_env == 1 || t_env == 2 || t_env == 4) tsel = t_env;
 #define QP_SPMM(CB, RV) \
-  (two ? launch_spmm_selld_t<EPI, CB, RV, 2, 4>(gen, coef_stride, x, batch, e) \
-       : launch_spmm_selld_t<EPI, CB, RV, 1, 8>(gen, coef_stride, x, batch, e))
+  (tsel == 4 ? launch_spmm_selld_t<EPI, CB, RV, 4, 2, 1>(gen, coef_stride, x, batch, e) \
+   : tsel == 2 ? launch_spmm_selld_t<EPI, CB, RV, 2, 4, 0>(gen, coef_stride, x, batch, e) \
+               : launch_spmm_selld_t<EPI, CB, RV, 1, 8, 0>(gen, coef_stride, x, batch, e))
   if (gen->code_bytes == 1) return gen->dict_realv ? QP_SPMM(1, 1) : QP_SPMM(1, 0);
   return gen->dict_realv ? QP_SPMM(2, 1) : QP_SPMM(2, 0);
 #undef QP_SPMM

@@ -197,6 +197,11 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
   const int lane = (int)(gtid % LANES);
   double sr = 0.0, si = 0.0;
   const bool active = row < m.n;
+  // epilogue operands requested before the row is walked: at small N the kernel is a chain of
+  // dependent L2 round trips (row pointer -> entries -> gathered x -> epilogue), this removes one
+  double2 xr, yv, av;
+  xr = yv = av = make_double2(0.0, 0.0);
+  if (active && lane == 0) epi_load<EPI>(e, x, row, row, xr, yv, av);
   if (active) {
     const uint32_t p0 = m.ptr[row], p1 = m.ptr[row + 1];
 #pragma unroll 4
@@ -217,7 +222,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
     si += __shfl_xor_sync(0xffffffffu, si, o);
   }
   double dr = 0, di = 0, nn = 0;
-  if (active && lane == 0) epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
+  if (active && lane == 0) epi_apply<EPI>(e, row, make_double2(sr, si), xr, yv, av, dr, di, nn);
   if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
       dr += __shfl_xor_sync(0xffffffffu, dr, o);
@@ -683,10 +688,10 @@ struct DeltaOp {
   int32_t op;
 };
 
-template <int EPI, int CB, int REALV, int T, int G>
+template <int EPI, int CB, int REALV, int T, int G, int LATE>
 __global__ void __launch_bounds__(256, 2)
 k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, const double2* __restrict__ coef,
-             int coef_stride, int64_t batch, const double2* __restrict__ x, EpiArgs e) {
+             int coef_stride, int64_t batch, const double2* __restrict__ x, EpiArgs e, int slices_per_cta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_val2 = reinterpret_cast<double2*>(smem_raw);  // !REALV
   double* s_val1 = reinterpret_cast<double*>(smem_raw);    // REALV
@@ -701,22 +706,14 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
   constexpr int CPW = 16 / CB;   // codes per 16-byte word
   static_assert(CPW % G == 0, "group size must divide the codes per word");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t slice = blockIdx.x;
-  int64_t bcol[T];   // this lane's trajectories (clamped; dead ones are computed on a copy)
+  const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
+  int32_t bcol[T];   // this lane's trajectories (clamped; dead ones are computed on a copy)
   bool blive[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int64_t b = ((int64_t)blockIdx.y * T + t) * 32 + lane;
     blive[t] = b < batch;
-    bcol[t] = blive[t] ? b : batch - 1;
-  }
-  uint32_t off0, off1;
-  if (m.uniform_words) {
-    off0 = (uint32_t)slice * m.uniform_words;
-    off1 = off0 + m.uniform_words;
-  } else {
-    off0 = m.sptr[slice];
-    off1 = m.sptr[slice + 1];
+    bcol[t] = (int32_t)(blive[t] ? b : batch - 1);
   }
   const int64_t ustride = coef_stride ? batch : 1;
   auto ucoef = [&](int op, int t) {  // u_op of trajectory t (times i for an imaginary operator)
@@ -727,23 +724,41 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
   double dr[T], di[T], nn[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) dr[t] = di[t] = nn[t] = 0.0;
+  // a CTA sweeps `slices_per_cta` consecutive slices: the gathers of nearby rows (offsets up to
+  // the tile height) hit lines this CTA fetched a moment ago
+  const int64_t slice_end = min((int64_t)(blockIdx.x + 1) * slices_per_cta, n_slices);
+  for (int64_t slice = (int64_t)blockIdx.x * slices_per_cta; slice < slice_end; ++slice) {
+  uint32_t off0, off1;
+  if (m.uniform_words) {
+    off0 = (uint32_t)slice * m.uniform_words;
+    off1 = off0 + m.uniform_words;
+  } else {
+    off0 = m.sptr[slice];
+    off1 = m.sptr[slice + 1];
+  }
   for (int rl = warp; rl < QP_SELL_C; rl += 8) {
     const int64_t row = slice * QP_SELL_C + rl;
     if (row >= m.n) break;
     double2 xr[T], yv[T], av[T];
-    const double2* xb[T];
+    const double2* xb0 = x + row * batch;  // x[(row + delta) * batch + b] = xb0[delta * batch + b]
     double tr[T], ti[T], pr[T], pi[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int64_t idx = row * batch + bcol[t];
-      epi_load<EPI>(e, x, idx, idx, xr[t], yv[t], av[t]);
-      xb[t] = x + idx;  // x[(row + delta) * batch + b] = xb[delta * batch]
+      // LATE (many trajectories per lane): the epilogue operands are loaded after the row instead
+      // of being held in registers across it
+      if (!LATE) epi_load<EPI>(e, x, idx, idx, xr[t], yv[t], av[t]);
       tr[t] = ti[t] = pr[t] = pi[t] = 0.0;
     }
     int cur_op = -1;
 
+    // the row's code words form a dependent chain of global loads (word -> table -> gathers):
+    // the next word is requested before the current one is decoded
+    uint4 c_next = make_uint4(0u, 0u, 0u, 0u);
+    if (off0 + rl < off1) c_next = __ldg(m.codes + off0 + rl);  // same word for all lanes: one broadcast load
     for (uint32_t off = off0 + rl; off < off1; off += QP_SELL_C) {
-      const uint4 c = __ldg(m.codes + off);  // same word for all lanes: one broadcast load
+      const uint4 c = c_next;
+      if (off + QP_SELL_C < off1) c_next = __ldg(m.codes + off + QP_SELL_C);
       const uint32_t w[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int h = 0; h < CPW; h += G) {  // G codes x T trajectories = 8 gathers in flight per lane
@@ -763,7 +778,7 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
           dop[g] = s_dop[code[g]];
           const int64_t o = (int64_t)dop[g].delta * batch;
 #pragma unroll
-          for (int t = 0; t < T; ++t) xv[g][t] = __ldg(xb[t] + o);
+          for (int t = 0; t < T; ++t) xv[g][t] = __ldg(xb0 + o + bcol[t]);
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -806,6 +821,13 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
         ti[t] += u.x * pi[t] + u.y * pr[t];
       }
     }
+    if (LATE) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int64_t idx = row * batch + bcol[t];
+        epi_load<EPI>(e, x, idx, idx, xr[t], yv[t], av[t]);
+      }
+    }
     if (m.n_diag > 0) {  // explicit diagonals (warp-uniform matrix element, per-trajectory u)
       for (int i = 0; i < m.n_diag; ++i) {
         const int op = (int)((m.diag_ops >> (4 * i)) & 15ull);
@@ -814,7 +836,7 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
         for (int t = 0; t < T; ++t) {
           const double2 u = __ldg(coef + (int64_t)op * ustride + (coef_stride ? bcol[t] : 0));
           const double2 ud = cmul2(u, d);
-          const double2 xs = EPI == EPI_MUL ? __ldg(xb[t]) : xr[t];
+          const double2 xs = EPI == EPI_MUL ? __ldg(xb0 + bcol[t]) : xr[t];
           tr[t] += ud.x * xs.x - ud.y * xs.y;
           ti[t] += ud.x * xs.y + ud.y * xs.x;
         }
@@ -822,10 +844,18 @@ k_spmm_selld(DictView m, const double* __restrict__ dvalr, unsigned imag_ops, co
     }
 #pragma unroll
     for (int t = 0; t < T; ++t)
-      if (blive[t])
-        epi_apply<EPI>(e, row * batch + bcol[t], make_double2(tr[t], ti[t]), xr[t], yv[t], av[t], dr[t], di[t], nn[t]);
+      if (blive[t]) {
+        if (EPI == EPI_DOT) {  // sums carried across the CTA's rows
+          epi_apply<EPI>(e, row * batch + bcol[t], make_double2(tr[t], ti[t]), xr[t], yv[t], av[t], dr[t], di[t], nn[t]);
+        } else {  // normalization check (debug option): flushed per row, nothing held across rows
+          double cr = 0, ci = 0, cn = 0;
+          epi_apply<EPI>(e, row * batch + bcol[t], make_double2(tr[t], ti[t]), xr[t], yv[t], av[t], cr, ci, cn);
+          if (epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, bcol[t], cr, ci, cn);
+        }
+      }
   }
-  if (epi_has_sums(EPI) && e.chk != nullptr) {
+  }
+  if (EPI == EPI_DOT && e.chk != nullptr) {
 #pragma unroll
     for (int t = 0; t < T; ++t)
       if (blive[t]) chk_flush(e, bcol[t], dr[t], di[t], nn[t]);

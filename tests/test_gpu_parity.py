@@ -179,10 +179,11 @@ def test_selld_refuses_incompressible(qp, ctx):
     assert qp.DeviceGenerator(ctx, [A], 0).format == "csr"
 
 
-@pytest.mark.parametrize("n,n_vals,B", [(100, 5, 16), (1000, 300, 33), (333, 40, 70)])
+@pytest.mark.parametrize("n,n_vals,B", [(100, 5, 16), (1000, 300, 33), (333, 40, 70), (500, 30, 129), (200, 300, 300)])
 def test_operator_mul_batched_selld(qp, ctx, n, n_vals, B):
     """Trajectory-batched dictionary kernel (B >= 16, AUTO format): real, imaginary and complex
-    entries, 8- and 16-bit codes, partial trajectory chunks."""
+    entries, 8- and 16-bit codes, partial trajectory chunks; 1, 2 and 4 chunks of 32 trajectories
+    per lane (B <= 32, <= 64, > 64)."""
     rng = np.random.default_rng(n + B)
     offsets = [[0], [-7, 1, 2, 64], [-n // 2, -1, 3, n // 3]]
     ops = _structured_ops(rng, n, n_vals, offsets)
@@ -312,10 +313,11 @@ def test_cheby_tfim_vs_oracle_and_expm(qp, ctx, n_spins):
     assert rel(out, psi) < 1e-9
 
 
-@pytest.mark.parametrize("B", [5, 40])
+@pytest.mark.parametrize("B", [5, 40, 150])
 def test_cheby_batched_per_trajectory(qp, ctx, B):
     """Ensemble: B trajectories with their own control scale share one coefficient table
-    (B = 5: merged-CSR SpMM kernel, B = 40: dictionary SpMM kernel)."""
+    (B = 5: merged-CSR SpMM kernel, B = 40 / 150: dictionary SpMM kernel with 2 / 4 trajectory
+    chunks per lane)."""
     rng = np.random.default_rng(3)
     w = qp.workloads.config3_transmon(n_sites=3, levels=3, B=B, nt=9, dt=0.5)
     H0, H1, H2 = w["ops"]
@@ -361,6 +363,18 @@ def test_cheby_check_normalization_and_errors(qp, ctx):
     with pytest.raises(qp.QPropError) as exc:
         qp.cheby_(st, None, 0.1, bad, check_normalization=True, coeffs=[])
     assert exc.value.status == -5 and "Incorrect normalization" in str(exc.value)
+    # the same check on a batch (sums flushed per row by the batched kernels), all trajectory counts per lane
+    for B in (40, 100):
+        w3 = qp.workloads.config3_transmon(n_sites=3, levels=3, B=B, nt=3, dt=0.5)
+        gen3 = qp.DeviceGenerator(ctx, w3["ops"], 2)
+        bound = float((abs(w3["ops"][0]) + 0.1 * abs(w3["ops"][1]) + 0.1 * abs(w3["ops"][2])).sum(axis=1).max())
+        stB = qp.DeviceState.from_host(ctx, rand_state(rng, w3["ops"][0].shape[0], B))
+        wB = qp.ChebyWrk(stB, gen3, 2 * bound, -bound, 0.5)
+        qp.cheby_(stB, None, 0.5, wB, check_normalization=True, coeffs=[0.05, -0.02])
+        assert np.max(np.abs(stB.norm() - 1)) < 1e-12
+        wBad = qp.ChebyWrk(stB, gen3, 2 * bound / 40, -bound / 40, 0.5)
+        with pytest.raises(qp.QPropError, match="Incorrect normalization"):
+            qp.cheby_(stB, None, 0.5, wBad, check_normalization=True, coeffs=[0.05, -0.02])
     # wrong dt (src/cheby.jl:157)
     with pytest.raises(qp.QPropError) as exc:
         qp.cheby_(st, None, 0.2, good, coeffs=[])
