@@ -54,6 +54,8 @@ extern "C" {
 #define QP_FORMAT_SELLD 4 /* dictionary-compressed sliced-ELL: one 8/16-bit code per entry
                              indexing a table of distinct (operator, value, column-row)
                              triples; chosen when the table has < 4096 entries            */
+#define QP_FORMAT_LR 5    /* matrix-free left/right products on column-stacked matrices
+                             (qp_op_create_leftright); chosen automatically for such operators */
 
 typedef struct qp_ctx_s* qp_ctx_t;
 typedef struct qp_op_s* qp_op_t;
@@ -99,6 +101,17 @@ int32_t qp_op_upload_sparse(qp_ctx_t ctx, int64_t nrows, int64_t ncols, int64_t 
                             int32_t layout, int32_t index_base, qp_op_t* op);
 /* column-major (Julia Matrix) n x n */
 int32_t qp_op_upload_dense(qp_ctx_t ctx, int64_t n, const qp_c128* colmajor, qp_op_t* op);
+/* Matrix-free super-operator on column-stacked n x n matrices (vec index i + n*j):
+ *     rho  ->  sum_t  c_t * P_t rho Q_t ,     P_t / Q_t sparse n x n operators or NULL (= identity).
+ * Replaces the explicit sparse super-operators the reference builds with Kronecker products in
+ * ham_to_superop / lindblad_to_superop (src/generators.jl:470-508; vec(P rho Q) = (Q^T (x) P) vec rho):
+ *     1 (x) H  = (H, NULL),   H^T (x) 1 = (NULL, H),   (A^+)^T (x) A = (A, A^+),
+ * so a Liouvillian of an n-dimensional system costs O(nnz(H)) memory instead of O(n * nnz(H)).
+ * The result is an operator of dimension n^2; a generator is either made of such operators only
+ * (format QP_FORMAT_LR, single states) or of matrices only.  `left` / `right` must be sparse
+ * operators of this context and outlive the new operator. */
+int32_t qp_op_create_leftright(qp_ctx_t ctx, int64_t n, int32_t n_terms, const qp_op_t* left,
+                               const qp_op_t* right, const qp_c128* coeffs, qp_op_t* op);
 int32_t qp_op_destroy(qp_op_t op);
 int32_t qp_op_info(qp_op_t op, int64_t* nrows, int64_t* ncols, int64_t* nnz, int32_t* is_dense);
 

@@ -28,6 +28,7 @@ from .generators import (  # noqa: F401
     get_controls,
     substitute,
     liouvillian,
+    LeftRightOperator,
 )
 from . import interfaces  # noqa: F401
 from .interfaces import (  # noqa: F401

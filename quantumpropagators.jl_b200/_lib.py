@@ -32,7 +32,8 @@ QP_FORMAT_CSR = 1
 QP_FORMAT_SELL = 2
 QP_FORMAT_DENSE = 3
 QP_FORMAT_SELLD = 4
-FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense", 4: "selld"}
+QP_FORMAT_LR = 5
+FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense", 4: "selld", 5: "leftright"}
 
 
 class QPropLibraryError(RuntimeError):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "qp_timer_reset": (_i32, [_vp]),
     "qp_op_upload_sparse": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _P(_vp)]),
     "qp_op_upload_dense": (_i32, [_vp, _i64, _vp, _P(_vp)]),
+    "qp_op_create_leftright": (_i32, [_vp, _i64, _i32, _P(_vp), _P(_vp), _vp, _P(_vp)]),
     "qp_op_destroy": (_i32, [_vp]),
     "qp_op_info": (_i32, [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i32)]),
     "qp_gen_create": (_i32, [_vp, _i32, _P(_vp), _i32, _i32, _P(_vp)]),

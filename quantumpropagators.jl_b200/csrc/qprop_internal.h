@@ -46,9 +46,35 @@ struct qp_ctx_s {
   std::set<const void*> smem_configured;  // kernels already opted in to large dynamic smem
 };
 
+// one term c * P rho Q of a matrix-free left/right operator (qp_op_create_leftright)
+struct LRTermHost {
+  qp_op_t left = nullptr;       // borrowed sparse operator or nullptr (identity)
+  uint32_t* d_rptr = nullptr;   // Q^T as CSR (row j lists (b, Q[b, j])), owned; nullptr = identity
+  uint32_t* d_rcol = nullptr;
+  double2* d_rval = nullptr;
+  int64_t r_nnz = 0;
+  double2 c = {1.0, 0.0};
+};
+
+// device form of a term inside a generator
+struct LRTerm {
+  const uint32_t* lptr;
+  const uint32_t* lcol;
+  const double2* lval;
+  const uint32_t* rptr;
+  const uint32_t* rcol;
+  const double2* rval;
+  double2 c;
+  int op;  // operator index within the generator (selects the coefficient)
+  int pad;
+};
+
 struct qp_op_s {
   qp_ctx_t ctx = nullptr;
   bool dense = false;
+  bool leftright = false;        // matrix-free: nrows = ncols = lr_n^2, no matrix arrays
+  int64_t lr_n = 0;
+  std::vector<LRTermHost> lr_terms;
   int64_t nrows = 0, ncols = 0, nnz = 0;
   // sparse: canonical CSR, Int32 indices
   uint32_t* d_ptr = nullptr;
@@ -127,6 +153,10 @@ struct qp_gen_s {
   uint32_t uniform_words = 0;
   int64_t dict_words = 0;  // 16-byte words stored
   int64_t stored_bytes = 0;  // bytes of the matrix stream actually read per application
+  // QP_FORMAT_LR: terms of all operators
+  LRTerm* d_lr_terms = nullptr;
+  int n_lr_terms = 0;
+  int64_t lr_n = 0;
   // dense: pointers to the row-major operators
   const double2** d_dense_ops = nullptr;
   // device copy of the effective per-operator coefficients (drift ops = 1), [n_ops][B]

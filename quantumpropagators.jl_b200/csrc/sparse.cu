@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "spmv.cuh"
+#include "spmv_lr.cuh"
 #include "dense_mma.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -160,7 +161,92 @@ extern "C" int32_t qp_op_destroy(qp_op_t op) {
   cudaFree(op->d_col);
   cudaFree(op->d_val);
   cudaFree(op->d_dense);
+  for (LRTermHost& t : op->lr_terms) {
+    cudaFree(t.d_rptr);
+    cudaFree(t.d_rcol);
+    cudaFree(t.d_rval);
+  }
   delete op;
+  return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// matrix-free left/right super-operators (spmv_lr.cuh)
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t qp_op_create_leftright(qp_ctx_t ctx, int64_t n, int32_t n_terms, const qp_op_t* left,
+                                          const qp_op_t* right, const qp_c128* coeffs, qp_op_t* out) {
+  QP_CHECK(qp_ctx_bind(ctx));
+  QP_REQUIRE(ctx, out != nullptr, "qp_op_create_leftright: null output pointer");
+  *out = nullptr;
+  QP_REQUIRE(ctx, n >= 1 && n_terms >= 1 && left && right && coeffs, "qp_op_create_leftright: bad argument");
+  if (n_terms > QP_LR_MAX_TERMS)
+    return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_op_create_leftright: %d terms exceed the limit of %d", n_terms, QP_LR_MAX_TERMS);
+  if (n * n >= (int64_t(1) << QP_COL_BITS))
+    return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_op_create_leftright: dimension n^2 = %lld exceeds 2^%d", (long long)(n * n), QP_COL_BITS);
+  for (int t = 0; t < n_terms; ++t)
+    for (qp_op_t f : {left[t], right[t]}) {
+      if (!f) continue;
+      QP_REQUIRE(ctx, f->ctx == ctx, "qp_op_create_leftright: factor of term %d belongs to another context", t);
+      QP_REQUIRE(ctx, !f->dense && !f->leftright, "qp_op_create_leftright: factors must be sparse operators (term %d)", t);
+      QP_REQUIRE(ctx, f->nrows == n && f->ncols == n, "qp_op_create_leftright: factor of term %d is %lld x %lld, expected %lld x %lld",
+                 t, (long long)f->nrows, (long long)f->ncols, (long long)n, (long long)n);
+    }
+  qp_op_t op = new qp_op_s();
+  op->ctx = ctx;
+  op->leftright = true;
+  op->lr_n = n;
+  op->nrows = op->ncols = n * n;
+  auto fail = [&](int32_t rc) {
+    qp_op_destroy(op);
+    return rc;
+  };
+  for (int t = 0; t < n_terms; ++t) {
+    LRTermHost T;
+    T.left = left[t];
+    T.c = make_double2(coeffs[t].re, coeffs[t].im);
+    op->nnz += left[t] ? left[t]->nnz : 0;
+    if (qp_op_t Q = right[t]) {
+      // Q^T in CSR: row j lists the entries (b, Q[b, j]) of column j of Q (counting sort on the host:
+      // the factors are n x n, tiny next to the n^2-dimensional state)
+      const int64_t nnz = Q->nnz;
+      std::vector<uint32_t> h_ptr((size_t)n + 1), h_col((size_t)std::max<int64_t>(nnz, 1));
+      std::vector<double2> h_val((size_t)std::max<int64_t>(nnz, 1));
+      cudaError_t e = cudaMemcpy(h_ptr.data(), Q->d_ptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(h_col.data(), Q->d_col, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(h_val.data(), Q->d_val, sizeof(double2) * nnz, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_CUDA, "qp_op_create_leftright: download failed: %s", cudaGetErrorString(e)));
+      std::vector<uint32_t> t_ptr((size_t)n + 1, 0), t_col((size_t)std::max<int64_t>(nnz, 1));
+      std::vector<double2> t_val((size_t)std::max<int64_t>(nnz, 1));
+      for (int64_t k = 0; k < nnz; ++k) t_ptr[h_col[k] + 1]++;
+      for (int64_t c = 0; c < n; ++c) t_ptr[c + 1] += t_ptr[c];
+      std::vector<uint32_t> fill(t_ptr.begin(), t_ptr.end() - 1);
+      for (int64_t r = 0; r < n; ++r)
+        for (uint32_t k = h_ptr[r]; k < h_ptr[r + 1]; ++k) {
+          const uint32_t dst = fill[h_col[k]]++;
+          t_col[dst] = (uint32_t)r;
+          t_val[dst] = h_val[k];
+        }
+      if ((e = cudaMalloc(&T.d_rptr, sizeof(uint32_t) * (n + 1))) != cudaSuccess ||
+          (e = cudaMalloc(&T.d_rcol, sizeof(uint32_t) * std::max<int64_t>(nnz, 1))) != cudaSuccess ||
+          (e = cudaMalloc(&T.d_rval, sizeof(double2) * std::max<int64_t>(nnz, 1))) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(T.d_rptr);
+        cudaFree(T.d_rcol);
+        cudaFree(T.d_rval);
+        return fail(qp_fail(ctx, QP_ERR_OOM, "qp_op_create_leftright: cudaMalloc failed: %s", cudaGetErrorString(e)));
+      }
+      op->lr_terms.push_back(T);  // owned from here on (freed by qp_op_destroy)
+      if ((e = cudaMemcpy(T.d_rptr, t_ptr.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice)) != cudaSuccess ||
+          (nnz > 0 && (e = cudaMemcpy(T.d_rcol, t_col.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice)) != cudaSuccess) ||
+          (nnz > 0 && (e = cudaMemcpy(T.d_rval, t_val.data(), sizeof(double2) * nnz, cudaMemcpyHostToDevice)) != cudaSuccess))
+        return fail(qp_fail(ctx, QP_ERR_CUDA, "qp_op_create_leftright: upload failed: %s", cudaGetErrorString(e)));
+      op->lr_terms.back().r_nnz = nnz;
+      op->nnz += nnz;
+    } else {
+      op->lr_terms.push_back(T);
+    }
+  }
+  *out = op;
   return QP_OK;
 }
 
@@ -463,6 +549,7 @@ static void gen_free(qp_gen_t g) {
   cudaFree(g->d_diag);
   cudaFree(g->d_dvalr);
   cudaFree((void*)g->d_dense_ops);
+  cudaFree(g->d_lr_terms);
   cudaFree(g->d_coef);
   delete g;
 }
@@ -678,8 +765,8 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   // "The number of coefficients cannot exceed the number of operators" src/generators.jl:116-121
   QP_REQUIRE(ctx, n_coeffs >= 0 && n_coeffs <= n_ops,
              "qp_gen_create: the number of coefficients (%d) cannot exceed the number of operators (%d)", n_coeffs, n_ops);
-  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_SELLD, "qp_gen_create: bad format %d", format);
-  bool any_dense = false, all_dense = true;
+  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_LR, "qp_gen_create: bad format %d", format);
+  bool any_dense = false, all_dense = true, any_lr = false, all_lr = true;
   for (int l = 0; l < n_ops; ++l) {
     QP_REQUIRE(ctx, ops[l] != nullptr, "qp_gen_create: operator %d is null", l);
     QP_REQUIRE(ctx, ops[l]->ctx == ctx, "qp_gen_create: operator %d belongs to another context", l);
@@ -687,7 +774,13 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     QP_REQUIRE(ctx, ops[l]->nrows == ops[0]->nrows, "qp_gen_create: operator %d has a different size", l);
     any_dense |= ops[l]->dense;
     all_dense &= ops[l]->dense;
+    any_lr |= ops[l]->leftright;
+    all_lr &= ops[l]->leftright;
   }
+  if (any_lr && !all_lr)
+    return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: mixing matrix-free (left/right) operators and matrices is not supported");
+  if ((format == QP_FORMAT_LR) != all_lr && !(all_lr && format == QP_FORMAT_AUTO))
+    return qp_fail(ctx, QP_ERR_INVALID_ARG, "qp_gen_create: QP_FORMAT_LR is the format of left/right operators (and only theirs)");
   if (any_dense && !all_dense)
     return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: mixing dense and sparse operators is not supported");
 
@@ -714,6 +807,44 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     }                                                                                            \
   } while (0)
 
+  if (all_lr) {  // matrix-free: one table of terms over all operators
+    g->format = QP_FORMAT_LR;
+    g->lr_n = ops[0]->lr_n;
+    std::vector<LRTerm> h;
+    for (int l = 0; l < n_ops; ++l) {
+      if (ops[l]->lr_n != g->lr_n) return bail(qp_fail(ctx, QP_ERR_INVALID_ARG, "qp_gen_create: operator %d acts on a different matrix size", l));
+      for (const LRTermHost& T : ops[l]->lr_terms) {
+        LRTerm d;
+        memset(&d, 0, sizeof(d));
+        if (T.left) {
+          d.lptr = T.left->d_ptr;
+          d.lcol = T.left->d_col;
+          d.lval = T.left->d_val;
+          g->matrix_bytes += 20 * T.left->nnz + 4 * (g->lr_n + 1);
+          g->nnz_total += T.left->nnz;
+        }
+        if (T.d_rptr) {
+          d.rptr = T.d_rptr;
+          d.rcol = T.d_rcol;
+          d.rval = T.d_rval;
+          g->matrix_bytes += 20 * T.r_nnz + 4 * (g->lr_n + 1);
+          g->nnz_total += T.r_nnz;
+        }
+        d.c = T.c;
+        d.op = l;
+        h.push_back(d);
+      }
+    }
+    if ((int)h.size() > QP_LR_MAX_TERMS)
+      return bail(qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: %d left/right terms exceed the limit of %d", (int)h.size(), QP_LR_MAX_TERMS));
+    g->n_lr_terms = (int)h.size();
+    G_CUDA(cudaMalloc(&g->d_lr_terms, sizeof(LRTerm) * h.size()));
+    G_CUDA(cudaMemcpy(g->d_lr_terms, h.data(), sizeof(LRTerm) * h.size(), cudaMemcpyHostToDevice));
+    g->stored_entries = g->nnz_total;
+    g->stored_bytes = g->matrix_bytes;
+    *out = g;
+    return QP_OK;
+  }
   if (all_dense) {
     if (format != QP_FORMAT_AUTO && format != QP_FORMAT_DENSE)
       return bail(qp_fail(ctx, QP_ERR_INVALID_ARG, "qp_gen_create: dense operators need QP_FORMAT_DENSE"));
@@ -1036,6 +1167,15 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   qp_ctx_t ctx = gen->ctx;
   const int64_t n = gen->n;
   cudaStream_t st = ctx->stream;
+  if (gen->format == QP_FORMAT_LR) {
+    if (batch != 1) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "matrix-free left/right generators take single states (batch = %lld)", (long long)batch);
+    const int64_t n_slices = ((gen->lr_n + 31) / 32) * gen->lr_n;
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((n_slices + 7) / 8, (int64_t)ctx->sm_count * 8));
+    k_spmv_lr<EPI><<<(unsigned)blocks, 256, sizeof(LRTerm) * gen->n_lr_terms, st>>>(gen->d_lr_terms, gen->n_lr_terms, gen->n_ops, gen->lr_n,
+                                                                                      gen->d_coef, x, e);
+    QP_LAUNCHED(ctx);
+    return QP_OK;
+  }
   if (gen->format == QP_FORMAT_DENSE) {
     if (batch != 1) return launch_dense_batched<EPI>(gen, coef_stride, x, batch, e);  // FP64 tensor cores
     k_gemv_dense<EPI><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e);

@@ -77,7 +77,24 @@ class DeviceOperator:
         self.ctx = ctx
         lib = ctx._lib
         h = C.c_void_p()
-        if sp.issparse(A):
+        if getattr(A, "is_leftright", False):
+            # matrix-free super-operator Σ c P ρ Q (generators.LeftRightOperator): the n x n factors
+            # are uploaded as ordinary sparse operators, the n² x n² matrix is never built
+            self.factors = []
+            left = (C.c_void_p * len(A.terms))()
+            right = (C.c_void_p * len(A.terms))()
+            for t, (P, Q, _) in enumerate(A.terms):
+                for arr, F in ((left, P), (right, Q)):
+                    if F is None:
+                        arr[t] = None
+                    else:
+                        d = DeviceOperator(ctx, sp.csr_matrix(F, dtype=np.complex128))
+                        self.factors.append(d)
+                        arr[t] = d.handle
+            coeffs = L.as_c128_array([c for _, _, c in A.terms])
+            L.check(lib.qp_op_create_leftright(ctx.handle, int(A.n), len(A.terms), left, right, L.ptr(coeffs), C.byref(h)), ctx.handle)
+            self.dense = False
+        elif sp.issparse(A):
             if A.format not in ("csr", "csc"):
                 A = A.tocsr()
             layout = L.QP_LAYOUT_CSR if A.format == "csr" else L.QP_LAYOUT_CSC

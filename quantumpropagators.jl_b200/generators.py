@@ -29,6 +29,7 @@ __all__ = [
     "liouvillian",
     "ham_to_superop",
     "lindblad_to_superop",
+    "LeftRightOperator",
 ]
 
 
@@ -93,7 +94,7 @@ class Operator:
         out = np.zeros(self.shape, dtype=np.complex128)
         for i, op in enumerate(self.ops):
             c = self.coeffs[i - drift] if i >= drift else 1.0
-            out += c * (op.toarray() if sp.issparse(op) else np.asarray(op))
+            out += c * (op.toarray() if (sp.issparse(op) or hasattr(op, "toarray")) else np.asarray(op))
         return out
 
     def to_device(self, ctx: Context, fmt="auto") -> DeviceGenerator:
@@ -353,7 +354,101 @@ def lindblad_to_superop(A, convention):
     return D
 
 
-def _dissipator(c_ops, convention):
+class LeftRightOperator:
+    """Matrix-free super-operator ρ ↦ Σ_t c_t P_t ρ Q_t on column-stacked n × n matrices
+    (``vec(P ρ Q) = (Qᵀ ⊗ P) vec ρ``): what ``ham_to_superop`` / ``lindblad_to_superop``
+    (reference ``src/generators.jl:470-508``) build explicitly with Kronecker products, kept as
+    its n × n factors.  ``terms`` is a list of ``(P, Q, c)`` with ``P`` / ``Q`` sparse matrices or
+    ``None`` (identity).  Uploaded with ``qp_op_create_leftright``; the device applies it without
+    ever forming the n² × n² matrix (O(nnz) instead of O(n·nnz) memory)."""
+
+    is_leftright = True
+
+    def __init__(self, n, terms):
+        self.n = int(n)
+        self.terms = []
+        left, right = None, None  # all left-only / right-only terms merge into one factor each
+        for P, Q, c in terms:
+            P = None if P is None else sp.csr_matrix(P, dtype=np.complex128)
+            Q = None if Q is None else sp.csr_matrix(Q, dtype=np.complex128)
+            for F in (P, Q):
+                if F is not None and F.shape != (self.n, self.n):
+                    raise ValueError(f"factor of shape {F.shape} in a left/right operator on {self.n} x {self.n} matrices")
+            if P is not None and Q is None:
+                left = c * P if left is None else left + c * P
+            elif P is None and Q is not None:
+                right = c * Q if right is None else right + c * Q
+            else:
+                self.terms.append((P, Q, complex(c)))
+        for F, side in ((right, "right"), (left, "left")):
+            if F is not None:
+                F = F.tocsr()
+                F.eliminate_zeros()
+                F.sort_indices()
+                self.terms.insert(0, (F, None, 1.0 + 0j) if side == "left" else (None, F, 1.0 + 0j))
+
+    @property
+    def shape(self):
+        return (self.n * self.n, self.n * self.n)
+
+    def tosparse(self):
+        """The explicit n² × n² matrix Σ c Qᵀ ⊗ P (for tests and small systems)."""
+        ident = sp.identity(self.n, dtype=np.complex128, format="csr")
+        out = sp.csr_matrix(self.shape, dtype=np.complex128)
+        for P, Q, c in self.terms:
+            out = out + c * sp.kron((ident if Q is None else Q).T.tocsr(), ident if P is None else P, format="csr")
+        out = out.tocsr()
+        out.sort_indices()
+        return out
+
+    def toarray(self):
+        return self.tosparse().toarray()
+
+    def __add__(self, other):
+        if not isinstance(other, LeftRightOperator) or other.n != self.n:
+            return NotImplemented
+        return LeftRightOperator(self.n, self.terms + other.terms)
+
+    def __mul__(self, alpha):
+        if not _is_number(alpha):
+            return NotImplemented
+        return LeftRightOperator(self.n, [(P, Q, alpha * c) for P, Q, c in self.terms])
+
+    __rmul__ = __mul__
+
+    def __matmul__(self, vec):
+        """Host application to a column-stacked matrix (NumPy): Σ c P ρ Q."""
+        rho = np.asarray(vec).reshape(self.n, self.n, order="F")
+        out = np.zeros_like(rho, dtype=np.complex128)
+        for P, Q, c in self.terms:
+            t = rho if P is None else P @ rho
+            out += c * (t if Q is None else (Q.T @ t.T).T)
+        return out.reshape(-1, order="F")
+
+    def __repr__(self):
+        return f"LeftRightOperator on {self.n} x {self.n} matrices with {len(self.terms)} terms"
+
+
+def _ham_lr(H, convention):
+    f = 1.0 if convention == "TDSE" else 1j
+    H = sp.csr_matrix(H, dtype=np.complex128)
+    return LeftRightOperator(H.shape[0], [(H, None, f), (None, H, -f)])
+
+
+def _lindblad_lr(A, convention):
+    f = 1j if convention == "TDSE" else 1.0
+    A = sp.csr_matrix(A, dtype=np.complex128)
+    Ad = A.conj().T.tocsr()
+    AdA = (Ad @ A).tocsr()
+    return LeftRightOperator(A.shape[0], [(A, Ad, f), (AdA, None, -0.5 * f), (None, AdA, -0.5 * f)])
+
+
+def _dissipator(c_ops, convention, matrix_free=False):
+    if matrix_free:
+        D = _lindblad_lr(c_ops[0], convention)
+        for A in c_ops[1:]:
+            D = D + _lindblad_lr(A, convention)
+        return D
     n = c_ops[0].shape[0]
     if c_ops[0].shape[1] != n:
         raise AssertionError("Lindblad operators must be square")
@@ -365,32 +460,38 @@ def _dissipator(c_ops, convention):
     return D
 
 
-def liouvillian(H, c_ops=(), *, convention, check=True):
+def liouvillian(H, c_ops=(), *, convention, check=True, matrix_free=False):
     """``liouvillian(Ĥ, c_ops; convention)`` (reference ``src/generators.jl:520-632``): the
     sparse Liouvillian super-operator of a Hamiltonian (matrix, ``Generator`` / ``Operator`` or
     tuple of terms; ``None`` for a pure dissipator) and Lindblad operators ``c_ops``, acting on
     column-stacked density matrices.  A time-dependent Ĥ gives a ``Generator`` with the same
     amplitudes: drift commutator + dissipator first, then one commutator per control term.
-    ``convention`` is mandatory, as in the reference."""
+    ``convention`` is mandatory, as in the reference.
+
+    ``matrix_free=True`` (no reference counterpart) returns the same generator
+    with every super-operator kept as a :class:`LeftRightOperator` (its n × n factors) instead of
+    an n² × n² sparse matrix: identical action on column-stacked density matrices, O(nnz(Ĥ))
+    memory."""
     _check_convention(convention)
     c_ops = list(c_ops)
+    superop = (lambda M: _ham_lr(M, convention)) if matrix_free else (lambda M: ham_to_superop(M, convention))
     if isinstance(H, (tuple, list)):
         H = hamiltonian(*H, check=check)
     terms = []
     if H is None:
         if not c_ops:
             raise ValueError("Empty Liouvillian, must give at least one of `H` or `c_ops`")
-        return hamiltonian(_dissipator(c_ops, convention), check=check)
+        return hamiltonian(_dissipator(c_ops, convention, matrix_free), check=check)
     if isinstance(H, (Generator, Operator)):
         if c_ops:
-            terms.append(_dissipator(c_ops, convention))
+            terms.append(_dissipator(c_ops, convention, matrix_free))
         second = H.amplitudes if isinstance(H, Generator) else H.coeffs
         drift = len(H.ops) - len(second)
         for i, op in enumerate(H.ops):
-            term = ham_to_superop(op, convention)
+            term = superop(op)
             terms.append(term if i < drift else (term, second[i - drift]))
         return hamiltonian(*terms, check=check)
-    terms.append(ham_to_superop(H, convention))
+    terms.append(superop(H))
     if c_ops:
-        terms.append(_dissipator(c_ops, convention))
+        terms.append(_dissipator(c_ops, convention, matrix_free))
     return hamiltonian(*terms, check=check)

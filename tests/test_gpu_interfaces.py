@@ -113,3 +113,107 @@ def test_liouvillian_generator_vs_oracle(qp, ctx):
     ref = O.propagate(rho0, O.hamiltonian(Lg.ops[0], (Lg.ops[1], w["controls"][0])), w["tlist"], "newton")
     assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 1e-10
     assert abs(np.trace(np.asarray(out).reshape(4, 4, order="F")) - 1) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------
+# matrix-free left/right super-operators (qp_op_create_leftright, QP_FORMAT_LR)
+# ---------------------------------------------------------------------------------------
+
+
+def _rand_sparse(rng, n, density):
+    A = sp.random(n, n, density=density, random_state=np.random.RandomState(rng.integers(1 << 30)), format="csr")
+    B = sp.random(n, n, density=density, random_state=np.random.RandomState(rng.integers(1 << 30)), format="csr")
+    return (A + 1j * B).tocsr()
+
+
+@pytest.mark.parametrize("n", [5, 37, 64])
+def test_leftright_operator_mul_matches_explicit_kron(qp, ctx, n):
+    """Σ c P ρ Q with left-only, right-only, sandwich and pure-scalar terms, two operators with a
+    coefficient, n not a multiple of the warp size: mul! / dot / expval against Σ c Qᵀ ⊗ P."""
+    rng = np.random.default_rng(n)
+    P1, P2, Q1, Q2 = (_rand_sparse(rng, n, 0.2) for _ in range(4))
+    op0 = qp.LeftRightOperator(n, [(P1, None, 0.7), (None, Q1, -0.4j), (P2, Q2, 1.1 - 0.3j), (None, None, 0.25)])
+    op1 = qp.LeftRightOperator(n, [(P2, None, 1.0), (None, P2, -1.0), (Q1, P1, 0.5j)])
+    coeffs = [0.6 - 0.2j]
+    gen = qp.DeviceGenerator(ctx, [op0, op1], 1)
+    assert gen.format == "leftright" and gen.n == n * n
+    full = (op0.tosparse() + coeffs[0] * op1.tosparse()).tocsr()
+    x = rand_state(rng, n * n)
+    y0 = rand_state(rng, n * n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+        dy = qp.DeviceState.from_host(ctx, y0)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        ref = beta * y0 + alpha * (full @ x)
+        assert np.linalg.norm(dy.to_host() - ref) / np.linalg.norm(ref) < 1e-13
+    assert abs(gen.expval(dx, coeffs) - np.vdot(x, full @ x)) < 1e-12 * n
+    dy0 = qp.DeviceState.from_host(ctx, y0)
+    assert abs(gen.dot(dy0, dx, coeffs) - np.vdot(y0, full @ x)) < 1e-12 * n
+    # the lazy-sum Operator of the host mirror passes the operator interface check
+    assert qp.check_operator(qp.Operator([op0, op1], coeffs), state=dx)
+
+
+def test_leftright_errors(qp, ctx):
+    n = 8
+    rng = np.random.default_rng(0)
+    lr = qp.LeftRightOperator(n, [(_rand_sparse(rng, n, 0.3), None, 1.0)])
+    with pytest.raises(qp.QPropError, match="mixing"):
+        qp.DeviceGenerator(ctx, [lr, sp.identity(n * n, dtype=complex, format="csr")], 0)
+    gen = qp.DeviceGenerator(ctx, [lr], 0)
+    xB = qp.DeviceState.from_host(ctx, rand_state(rng, n * n, 3))
+    with pytest.raises(qp.QPropError, match="single states"):
+        gen.mul(xB.similar(), xB, [])
+    with pytest.raises(ValueError, match="shape"):
+        qp.LeftRightOperator(n, [(sp.identity(n + 1, format="csr"), None, 1.0)])
+
+
+@pytest.mark.parametrize("n_spins", [3, 5])
+def test_liouvillian_matrix_free_newton_vs_explicit_and_oracle(qp, ctx, n_spins):
+    """Config 4 shape (driven TFIM + local decay, TDSE convention) propagated with Newton through
+    the matrix-free generator, through the explicit sparse super-operators, and by the oracle."""
+    H0, H1, _ = qp.workloads.tfim_chain(n_spins)
+    nh = 1 << n_spins
+    sm = sp.csr_matrix(np.array([[0, 1], [0, 0]], dtype=complex))
+    c_ops = []
+    for k in range(n_spins):
+        left = sp.identity(1 << (n_spins - 1 - k), dtype=complex, format="csr")
+        right = sp.identity(1 << k, dtype=complex, format="csr")
+        c_ops.append(np.sqrt(0.05) * sp.kron(sp.kron(left, sm), right, format="csr"))
+    tlist = np.linspace(0.0, 0.4, 9)
+
+    def u1(t):
+        return float(np.sin(np.pi * t / 0.4) ** 2)
+
+    Lf = qp.liouvillian((H0, (H1, u1)), c_ops, convention="TDSE", matrix_free=True)
+    Lm = qp.liouvillian((H0, (H1, u1)), c_ops, convention="TDSE")
+    rng = np.random.default_rng(n_spins)
+    psi = rand_state(rng, nh)
+    rho0 = np.outer(psi, psi.conj()).reshape(-1, order="F")
+    out_f = qp.propagate(rho0, Lf, tlist, "newton", ctx=ctx)
+    out_m = qp.propagate(rho0, Lm, tlist, "newton", ctx=ctx)
+    ref = O.propagate(rho0, O.hamiltonian(Lm.ops[0], (Lm.ops[1], u1)), tlist, "newton")
+    assert np.linalg.norm(out_f - ref) / np.linalg.norm(ref) < 1e-10
+    assert np.linalg.norm(out_f - out_m) / np.linalg.norm(out_m) < 1e-11
+    rho = np.asarray(out_f).reshape(nh, nh, order="F")
+    assert abs(np.trace(rho) - 1) < 1e-10 and np.linalg.norm(rho - rho.conj().T) < 1e-10
+
+
+def test_liouvillian_matrix_free_cheby_unitary(qp, ctx):
+    """Without dissipation the super-operator [H, ·] is Hermitian: the Chebyshev propagator (all
+    fused epilogues of the matrix-free kernel) must reproduce ρ(t) = U ρ U†."""
+    import scipy.linalg as sla
+
+    H0, H1, _ = qp.workloads.tfim_chain(4)
+    nh = 16
+    Hs = (H0 + 0.3 * H1).toarray()
+    ev = np.linalg.eigvalsh(Hs)
+    Lf = qp.liouvillian(H0 + 0.3 * H1, convention="TDSE", matrix_free=True)
+    rng = np.random.default_rng(4)
+    psi = rand_state(rng, nh)
+    rho0 = np.outer(psi, psi.conj())
+    tlist = np.linspace(0.0, 1.0, 6)
+    width = ev[-1] - ev[0]
+    out = qp.propagate(rho0.reshape(-1, order="F"), Lf, tlist, "cheby", ctx=ctx, E_min=-width, E_max=width)
+    U = sla.expm(-1j * Hs * 1.0)
+    ref = U @ rho0 @ U.conj().T
+    assert np.linalg.norm(np.asarray(out).reshape(nh, nh, order="F") - ref) < 1e-11

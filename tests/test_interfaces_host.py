@@ -170,3 +170,32 @@ def test_liouvillian_matches_lindblad_equation():
         qp.liouvillian(None, [], convention="LvN")
     with pytest.raises(TypeError):
         qp.liouvillian(H0)  # the convention is mandatory
+
+
+def test_liouvillian_matrix_free_equals_explicit_superoperators():
+    """``liouvillian(..., matrix_free=True)`` keeps every super-operator as its n x n factors
+    (``LeftRightOperator``: Σ c P ρ Q); expanding them with Kronecker products gives exactly the
+    matrices of the reference's formulas (src/generators.jl:470-508), in both conventions."""
+    rng = np.random.default_rng(1)
+    n = 7
+    H0, H1 = _herm(rng, n, 1.0), _herm(rng, n, 0.3)
+    c_ops = [0.3 * np.diag(np.ones(n - 1), 1).astype(complex), 0.2 * np.diag(np.arange(n)).astype(complex)]
+
+    def u(t):
+        return 0.5
+
+    rho = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    for conv in ("TDSE", "LvN"):
+        Lm = qp.liouvillian((H0, (H1, u)), c_ops, convention=conv)
+        Lf = qp.liouvillian((H0, (H1, u)), c_ops, convention=conv, matrix_free=True)
+        assert isinstance(Lf, qp.Generator) and qp.get_controls(Lf) == (u,)
+        for a, b in zip(Lm.ops, Lf.ops):
+            assert isinstance(b, qp.LeftRightOperator) and b.shape == a.shape
+            assert abs(a - b.tosparse()).max() < 1e-15
+            assert np.abs(a @ rho - b @ rho).max() < 1e-13
+        # left-only and right-only factors are merged: drift = H_eff ρ, ρ H_eff†-like, 2 sandwiches
+        assert len(Lf.ops[0].terms) == 4 and len(Lf.ops[1].terms) == 2
+    D = qp.liouvillian(None, c_ops, convention="LvN", matrix_free=True)
+    assert isinstance(D, qp.LeftRightOperator)
+    assert abs(D.tosparse() - qp.liouvillian(None, c_ops, convention="LvN")).max() < 1e-15
+    assert abs((2.0 * D).tosparse() - 2.0 * D.tosparse()).max() < 1e-15
