@@ -1169,10 +1169,19 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   cudaStream_t st = ctx->stream;
   if (gen->format == QP_FORMAT_LR) {
     if (batch != 1) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "matrix-free left/right generators take single states (batch = %lld)", (long long)batch);
-    const int64_t n_slices = ((gen->lr_n + 31) / 32) * gen->lr_n;
-    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((n_slices + 7) / 8, (int64_t)ctx->sm_count * 8));
-    k_spmv_lr<EPI><<<(unsigned)blocks, 256, sizeof(LRTerm) * gen->n_lr_terms, st>>>(gen->d_lr_terms, gen->n_lr_terms, gen->n_ops, gen->lr_n,
-                                                                                      gen->d_coef, x, e);
+    // CTA = 256 rows of rho x a range of columns swept JB at a time; enough column ranges to fill
+    // the machine a few times over
+    constexpr int JB = 4;
+    const int64_t nh = gen->lr_n;
+    const int64_t row_blocks = (nh + 255) / 256;
+    int64_t col_ranges = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 6 + row_blocks - 1) / row_blocks);
+    int64_t cols = (nh + col_ranges - 1) / col_ranges;
+    cols = std::max<int64_t>(JB, (cols + JB - 1) / JB * JB);
+    col_ranges = (nh + cols - 1) / cols;
+    if (col_ranges > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "left/right generator too large for one launch");
+    dim3 grid((unsigned)row_blocks, (unsigned)col_ranges);
+    k_spmv_lr<EPI, JB><<<grid, 256, sizeof(LRTerm) * gen->n_lr_terms, st>>>(gen->d_lr_terms, gen->n_lr_terms, gen->n_ops, nh,
+                                                                               gen->d_coef, x, e, (int)cols);
     QP_LAUNCHED(ctx);
     return QP_OK;
   }

@@ -217,30 +217,29 @@ def lindblad_to_superop(A, convention="TDSE"):
     return f(A, convention)
 
 
-def config4_liouvillian(n_spins=12, gamma=0.05, J=1.0, nt=21, dt=0.05, seed=4000):
+def config4_liouvillian(n_spins=12, gamma=0.05, J=1.0, nt=21, dt=0.05, seed=4000, matrix_free=False):
     """n-spin TFIM + local decay A_k = sqrt(γ) σ⁻_k, TDSE convention (func = exp(-i z));
-    L0 = commutator(H0) + dissipator, L1 = commutator(Σ X_i)."""
+    L0 = commutator(H0) + dissipator, L1 = commutator(Σ X_i).
+    ``matrix_free``: the two super-operators as ``LeftRightOperator`` (n × n factors) instead of
+    4^n × 4^n sparse matrices."""
+    from .generators import liouvillian
+
     H0, H1, _ = tfim_chain(n_spins, J)
     NH = 1 << n_spins
-    L0 = ham_to_superop(H0)
     sm = sp.csr_matrix(np.array([[0, 1], [0, 0]], dtype=np.complex128))  # |0><1|
+    c_ops = []
     for k in range(n_spins):
         left = sp.identity(1 << (n_spins - 1 - k), dtype=np.complex128, format="csr")
         right = sp.identity(1 << k, dtype=np.complex128, format="csr")
-        Ak = np.sqrt(gamma) * sp.kron(sp.kron(left, sm, format="csr"), right, format="csr")
-        L0 = L0 + lindblad_to_superop(Ak)
-    L0 = L0.tocsr()
-    L0.eliminate_zeros()
-    L0.sort_indices()
-    L1 = ham_to_superop(H1)
-    L1.eliminate_zeros()
-    L1.sort_indices()
+        c_ops.append(np.sqrt(gamma) * sp.kron(sp.kron(left, sm, format="csr"), right, format="csr"))
     T = dt * (nt - 1)
     tlist = np.linspace(0.0, T, nt)
 
     def u1(t):
         return float(np.sin(np.pi * t / T) ** 2)
 
+    Lgen = liouvillian((H0, (H1, u1)), c_ops, convention="TDSE", matrix_free=matrix_free)
+    L0, L1 = Lgen.ops
     rng = np.random.default_rng(seed)
     psi = rng.standard_normal(NH) + 1j * rng.standard_normal(NH)
     psi /= np.linalg.norm(psi)
@@ -250,7 +249,7 @@ def config4_liouvillian(n_spins=12, gamma=0.05, J=1.0, nt=21, dt=0.05, seed=4000
         controls=[u1],
         psi0=rho0,
         tlist=tlist,
-        name=f"config4_liouvillian_n{n_spins}",
+        name=f"config4_liouvillian_n{n_spins}" + ("_matrix_free" if matrix_free else ""),
     )
 
 

@@ -141,7 +141,9 @@ def config5(ctx, args):
 
 def config4(ctx, args):
     n_spins = args.liou_spins
-    w = qp.workloads.config4_liouvillian(n_spins=n_spins, nt=args.newton_steps + 3, dt=0.05)
+    t_host = time.perf_counter()
+    w = qp.workloads.config4_liouvillian(n_spins=n_spins, nt=args.newton_steps + 3, dt=0.05, matrix_free=args.matrix_free)
+    t_host = time.perf_counter() - t_host
     t_build = time.perf_counter()
     terms = [w["ops"][0]] + list(zip(w["ops"][1:], w["controls"]))
     p = qp.init_prop(w["psi0"], qp.hamiltonian(*terms), w["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12)
@@ -153,7 +155,9 @@ def config4(ctx, args):
         for _ in range(args.newton_steps):
             qp.prop_step(p)
     N = w["psi0"].shape[0]
-    emit(config=4, workload=f"Liouvillian of {n_spins}-spin TFIM + decay, dim {N}, Newton m_max=10", steps=args.newton_steps,
+    free, total = torch.cuda.mem_get_info()
+    emit(config=4, workload=f"Liouvillian of {n_spins}-spin TFIM + decay, dim {N}, Newton m_max=10" + (", matrix-free" if args.matrix_free else ""),
+         steps=args.newton_steps, host_build_s=t_host, device_memory_used_gb=(total - free) / 2**30,
          prop_steps_per_s=args.newton_steps / (t.ms * 1e-3), ms_per_step=t.ms / args.newton_steps, format=p.wrk.krylov.gen.format,
          n_dict=p.wrk.krylov.gen.n_dict, matrix_bytes=p.wrk.krylov.gen.matrix_bytes, launches_per_step=(ctx.launch_count - l0) / args.newton_steps,
          restarts_per_step=getattr(p.wrk, "restarts", None), setup_s=t_build)
@@ -169,6 +173,7 @@ def main():
     ap.add_argument("--dense-B", default="1,16,64")
     ap.add_argument("--liou-spins", type=int, default=10)
     ap.add_argument("--newton-steps", type=int, default=5)
+    ap.add_argument("--matrix-free", action="store_true", help="config 4 with liouvillian(..., matrix_free=True)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ctx = qp.Context(0)
