@@ -166,6 +166,44 @@ function upload_op(ctx::Context, A::Matrix{ComplexF64})
     return h[]
 end
 
+"""Matrix-free super-operator ρ ↦ Σ_t c_t P_t ρ Q_t on column-stacked n × n matrices: what
+`ham_to_superop` / `lindblad_to_superop` (reference `src/generators.jl:470-508`) build with
+Kronecker products, kept as its n × n factors (`nothing` = identity).  A generator whose
+`ops` are all `LeftRight` runs on the matrix-free kernel (`QP_FORMAT_LR`); `size` is n² × n², so
+it can stand wherever the explicit sparse super-operator stood in a `Generator`."""
+struct LeftRight
+    n::Int
+    terms::Vector{Tuple{Union{Nothing,SparseMatrixCSC{ComplexF64,Int64}},Union{Nothing,SparseMatrixCSC{ComplexF64,Int64}},ComplexF64}}
+end
+Base.size(A::LeftRight) = (A.n^2, A.n^2)
+Base.size(A::LeftRight, d) = A.n^2
+
+"""`liouvillian(Ĥ, c_ops; convention)` without the Kronecker products: same arguments for a
+static Hamiltonian matrix; returns a `LeftRight` (use one per term of a time-dependent Ĥ)."""
+function liouvillian_matrix_free(H::AbstractMatrix, c_ops=(); convention)
+    f, g = convention == :TDSE ? (1.0 + 0im, 1.0im) : convention == :LvN ? (1.0im, 1.0 + 0im) :
+           throw(ArgumentError("convention must be :TDSE or :LvN"))
+    S(A) = SparseMatrixCSC{ComplexF64,Int64}(sparse(A))
+    terms = Any[(S(H), nothing, f), (nothing, S(H), -f)]
+    for A in c_ops
+        AdA = S(A' * A)
+        push!(terms, (S(A), S(A'), g), (AdA, nothing, -g / 2), (nothing, AdA, -g / 2))
+    end
+    return LeftRight(size(H, 1), [(P, Q, ComplexF64(c)) for (P, Q, c) in terms])
+end
+
+function upload_op(ctx::Context, A::LeftRight)
+    # the factors are ordinary sparse operators; they must outlive the left/right operator
+    left = Ptr{Cvoid}[P === nothing ? C_NULL : upload_op(ctx, P) for (P, _, _) in A.terms]
+    right = Ptr{Cvoid}[Q === nothing ? C_NULL : upload_op(ctx, Q) for (_, Q, _) in A.terms]
+    coeffs = ComplexF64[c for (_, _, c) in A.terms]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_op_create_leftright, libqprop), Int32,
+                (Ptr{Cvoid}, Int64, Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                ctx.handle, A.n, length(A.terms), left, right, coeffs, h), ctx.handle)
+    return h[]
+end
+
 upload_op(ctx::Context, A::AbstractSparseMatrix) = upload_op(ctx, SparseMatrixCSC{ComplexF64,Int64}(A))
 upload_op(ctx::Context, A::AbstractMatrix) = upload_op(ctx, Matrix{ComplexF64}(A))
 
