@@ -63,6 +63,8 @@ from .propagator import (  # noqa: F401
     set_t,
     reinit_prop,
     propagate,
+    propagate_sequence,
+    Propagation,
     ChebyPropagator,
     NewtonPropagator,
     PWCPropagator,

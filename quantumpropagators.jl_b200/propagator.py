@@ -455,3 +455,47 @@ def propagate(
     if return_storage:
         return storage
     return p.state.to_host() if p._host_io else p.state
+
+
+class Propagation:
+    """Wrapper around the arguments of one :func:`propagate` call inside
+    :func:`propagate_sequence` (reference ``src/propagate_sequence.jl:1-33``):
+    ``Propagation(generator, tlist, **kwargs)`` or ``Propagation(propagator, **kwargs)``; may
+    carry its own ``pre_propagation`` / ``post_propagation`` functions."""
+
+    def __init__(self, *args, **kwargs):
+        self.args = list(args)
+        self.kwargs = dict(kwargs)
+
+
+def propagate_sequence(state, propagations, pre_propagation=None, post_propagation=None, **kwargs):
+    """``propagate_sequence(state, propagations; storage, pre_propagation, post_propagation,
+    kwargs...)`` (reference ``src/propagate_sequence.jl:36-137``): a sequence of
+    :func:`propagate` calls, each starting from the state the previous one ended with, optionally
+    transformed instantaneously before / after each step.  Returns the list of states after each
+    step (copies), or the list of storage arrays when ``storage=True``; every other keyword is
+    forwarded to ``propagate`` (per-step keywords in the ``Propagation`` are overridden by common
+    ones, as in the reference)."""
+    psi = state
+    results = []
+    for prop in propagations:
+        if not isinstance(prop, Propagation):
+            raise TypeError("propagations must be a list of Propagation instances")
+        kw = dict(prop.kwargs)
+        pre = kw.pop("pre_propagation", pre_propagation)
+        post = kw.pop("post_propagation", post_propagation)
+        kw.update(kwargs)
+        if pre is not None:
+            psi = pre(psi, *prop.args, **kw)
+        run_kw = {k: kw.pop(k) for k in ("storage", "observables", "callback", "show_progress") if k in kw}
+        if len(prop.args) == 1 and isinstance(prop.args[0], PWCPropagator):
+            p = prop.args[0]  # pre-initialised propagator: restarted from the current state
+            reinit_prop(p, psi, **kw)
+        else:
+            p = init_prop(psi, *prop.args, **kw)
+        out = propagate(p, **run_kw)
+        psi = p.state.to_host() if p._host_io else p.state
+        if post is not None:
+            psi = post(psi, *prop.args, **kw, **run_kw)
+        results.append(out if run_kw.get("storage", None) is True else psi.copy())
+    return results

@@ -217,3 +217,52 @@ def test_liouvillian_matrix_free_cheby_unitary(qp, ctx):
     U = sla.expm(-1j * Hs * 1.0)
     ref = U @ rho0 @ U.conj().T
     assert np.linalg.norm(np.asarray(out).reshape(nh, nh, order="F") - ref) < 1e-11
+
+
+def test_propagate_sequence(qp, ctx):
+    """test/test_propagate_sequence.jl in miniature: three propagations with different generators,
+    instantaneous pre/post transformations, a pre-initialised propagator and storage=True."""
+    import scipy.linalg as sla
+
+    rng = np.random.default_rng(12)
+    n = 30
+
+    def herm(scale):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        return scale * (A + A.conj().T) / 2
+
+    Ha, Hb, Hc = herm(0.3), herm(0.2), herm(0.4)
+    psi0 = rand_state(rng, n)
+    t1, t2, t3 = np.linspace(0, 1, 11), np.linspace(1, 1.5, 6), np.linspace(1.5, 3.0, 4)
+    phase = np.exp(1j * np.linspace(0, 1, n))
+    calls = []
+
+    def to_frame(psi, *args, **kwargs):
+        calls.append("pre")
+        return phase * np.asarray(psi)
+
+    def from_frame(psi, *args, **kwargs):
+        calls.append("post")
+        return np.conj(phase) * np.asarray(psi)
+
+    kw = dict(method="newton", ctx=ctx)
+    pc = qp.init_prop(psi0, Hc, t3, "newton", ctx=ctx)  # pre-initialised propagator for the last step
+    seq = [
+        qp.Propagation(Ha, t1),
+        qp.Propagation(Hb, t2, pre_propagation=to_frame, post_propagation=from_frame),
+        qp.Propagation(pc),
+    ]
+    states = qp.propagate_sequence(psi0, seq, **kw)
+    assert len(states) == 3 and calls == ["pre", "post"]
+    s1 = sla.expm(-1j * Ha * 1.0) @ psi0
+    s2 = np.conj(phase) * (sla.expm(-1j * Hb * 0.5) @ (phase * s1))
+    s3 = sla.expm(-1j * Hc * 1.5) @ s2
+    for got, want in zip(states, (s1, s2, s3)):
+        assert np.linalg.norm(np.asarray(got) - want) < 1e-10
+    # storage=True: one storage array per step, populations as observable
+    pops = [lambda psi: np.abs(np.asarray(psi.to_host() if hasattr(psi, "to_host") else psi)) ** 2]
+    stor = qp.propagate_sequence(psi0, [qp.Propagation(Ha, t1), qp.Propagation(Hb, t2)], storage=True, observables=pops, **kw)
+    assert stor[0].shape[-1] == len(t1) and stor[1].shape[-1] == len(t2)
+    assert np.allclose(np.squeeze(stor[0])[..., -1], np.abs(s1) ** 2, atol=1e-10)
+    with pytest.raises(TypeError):
+        qp.propagate_sequence(psi0, [(Ha, t1)])
