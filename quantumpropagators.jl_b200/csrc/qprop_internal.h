@@ -143,6 +143,7 @@ struct qp_gen_s {
   int32_t* d_ddelta = nullptr;
   uint8_t* d_dop = nullptr;
   double* d_dvalr = nullptr;  // table values as one real number each (valid when dict_realv)
+  bool pair_ordered = false;  // rows ordered "columns shared by two operators first" (spmm_pairs.cuh)
   bool dict_realv = false;    // every operator purely real or purely imaginary
   unsigned imag_ops = 0;      // bit l: operator l is purely imaginary (value stored = Im)
   double2* d_diag = nullptr;  // explicit diagonals [n_diag][n] (see DictView)

@@ -9,6 +9,7 @@
 
 #include "spmv.cuh"
 #include "spmv_lr.cuh"
+#include "spmm_pairs.cuh"
 #include "dense_mma.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -292,6 +293,62 @@ __global__ void k_merge_rows(OpPtrs ops, int n_ops, int64_t n, const uint32_t* _
     }
     dst += p1 - p0;
   }
+}
+
+// Orders every merged row "columns hit by >= 2 operators first (column by column, operator by
+// operator), then the rest by column": the trajectory-batched pair kernel (spmm_pairs.cuh) then
+// finds the entries that share a gather next to each other and aligned to even positions.
+// Thread per row, rows of up to 64 entries (longer rows are left in operator order: every kernel
+// accepts any order).  *n_pairs counts the columns found shared.
+__global__ void k_pair_order_rows(const uint32_t* __restrict__ mptr, uint32_t* __restrict__ mcolop,
+                                  double2* __restrict__ mval, int64_t n, unsigned long long* __restrict__ n_pairs) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t p0 = mptr[r];
+  const int len = (int)(mptr[r + 1] - p0);
+  if (len < 2 || len > 64) return;
+  uint32_t co[64];
+  double2 v[64];
+  unsigned long long key[64];
+  for (int a = 0; a < len; ++a) {
+    co[a] = mcolop[p0 + a];
+    v[a] = mval[p0 + a];
+  }
+  int shared_cols = 0;
+  for (int a = 0; a < len; ++a) {
+    const uint32_t col = co[a] & QP_COL_MASK;
+    int same = 0, first = 1;
+    for (int b = 0; b < len; ++b)
+      if ((co[b] & QP_COL_MASK) == col) {
+        ++same;
+        if (b < a) first = 0;
+      }
+    // exactly two operators on the column: a pair (three or more stay with the singles so that
+    // pairs remain aligned to even positions)
+    const unsigned long long single = same == 2 ? 0ull : 1ull;
+    key[a] = (single << 40) | ((unsigned long long)col << 4) | (unsigned long long)(co[a] >> QP_COL_BITS);
+    if (same == 2 && first) ++shared_cols;
+  }
+  for (int a = 1; a < len; ++a) {  // insertion sort by key
+    const unsigned long long k = key[a];
+    const uint32_t c = co[a];
+    const double2 val = v[a];
+    int b = a - 1;
+    while (b >= 0 && key[b] > k) {
+      key[b + 1] = key[b];
+      co[b + 1] = co[b];
+      v[b + 1] = v[b];
+      --b;
+    }
+    key[b + 1] = k;
+    co[b + 1] = c;
+    v[b + 1] = val;
+  }
+  for (int a = 0; a < len; ++a) {
+    mcolop[p0 + a] = co[a];
+    mval[p0 + a] = v[a];
+  }
+  if (shared_cols) atomicAdd(n_pairs, (unsigned long long)shared_cols);
 }
 
 // SELL-32: slice width = longest merged row in the slice
@@ -896,6 +953,20 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   k_merge_rows<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(P, n_ops, n, g->d_mptr, g->d_mcolop, g->d_mval);
   ctx->launches++;
   G_CUDA(cudaGetLastError());
+  // operators that share columns (quadrature control pairs): order the rows for the pair kernel
+  if (n_ops >= 2 && n_ops <= 3 && n <= (int64_t(1) << 21) && !getenv("QPROP_NO_PAIRS")) {
+    unsigned long long* d_np = nullptr;
+    G_CUDA(cudaMalloc(&d_np, sizeof(unsigned long long)));
+    G_CUDA(cudaMemsetAsync(d_np, 0, sizeof(unsigned long long), ctx->stream));
+    k_pair_order_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(g->d_mptr, g->d_mcolop, g->d_mval, n, d_np);
+    ctx->launches++;
+    unsigned long long h_np = 0;
+    cudaError_t e1 = cudaMemcpyAsync(&h_np, d_np, sizeof(h_np), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_np);
+    G_CUDA(e1);
+    g->pair_ordered = 8 * (int64_t)h_np >= nnz_total;  // worth it when >= 1/4 of the entries are paired
+  }
 
   // ---- SELL-32 slice widths (cheap; also tells us the padding overhead)
   const int64_t n_slices = (n + QP_SELL_C - 1) / QP_SELL_C;
@@ -1153,6 +1224,33 @@ static int32_t launch_spmm_selld(qp_gen_t gen, int coef_stride, const double2* x
   static const int t_env = getenv("QPROP_SPMM_T") ? atoi(getenv("QPROP_SPMM_T")) : 0;
   int tsel = batch > 64 && (int64_t)gen->n * 128 * 16 <= (int64_t)144 << 20 ? 4 : batch > 32 ? 2 : 1;
   if (t_env == 1 || t_env == 2 || t_env == 4) tsel = t_env;
+  if (tsel == 4 && gen->pair_ordered && gen->dict_realv && gen->n_ops <= 3) {
+    const int64_t chunks = (batch + 127) / 128;
+    if (chunks > 65535) return qp_fail(gen->ctx, QP_ERR_UNSUPPORTED, "batch too large for one launch");
+    const DictView m = make_dict_view(gen);
+    const size_t smem = ((size_t)gen->n_dict * (8 + sizeof(DeltaOp)) + 127) / 128 * 128;
+    dim3 grid((unsigned)gen->n_slices, (unsigned)chunks);
+    qp_ctx_t ctx = gen->ctx;
+#define QP_PAIRS(CB, NOPS)                                                                                          \
+  do {                                                                                                              \
+    auto kern = k_spmm_selld_pairs<EPI, CB, NOPS>;                                                                  \
+    if (!ctx->smem_configured.count((const void*)kern)) {                                                           \
+      QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));            \
+      ctx->smem_configured.insert((const void*)kern);                                                               \
+    }                                                                                                               \
+    kern<<<grid, 256, smem, ctx->stream>>>(m, gen->d_dvalr, gen->imag_ops, gen->d_coef, coef_stride, batch, x, e);  \
+  } while (0)
+    if (gen->code_bytes == 1) {
+      if (gen->n_ops == 2) QP_PAIRS(1, 2);
+      else QP_PAIRS(1, 3);
+    } else {
+      if (gen->n_ops == 2) QP_PAIRS(2, 2);
+      else QP_PAIRS(2, 3);
+    }
+#undef QP_PAIRS
+    QP_LAUNCHED(ctx);
+    return QP_OK;
+  }
 #define QP_SPMM(CB, RV) \
   (tsel == 4 ? launch_spmm_selld_t<EPI, CB, RV, 4, 2, 1>(gen, coef_stride, x, batch, e) \
    : tsel == 2 ? launch_spmm_selld_t<EPI, CB, RV, 2, 4, 0>(gen, coef_stride, x, batch, e) \

@@ -313,6 +313,36 @@ def test_cheby_tfim_vs_oracle_and_expm(qp, ctx, n_spins):
     assert rel(out, psi) < 1e-9
 
 
+@pytest.mark.parametrize("n,n_vals,n_ops,B", [(300, 6, 3, 129), (1000, 200, 3, 200), (257, 10, 2, 300), (300, 6, 3, 40)])
+def test_operator_mul_batched_shared_columns(qp, ctx, n, n_vals, n_ops, B):
+    """Operators that hit the same columns (quadrature control pairs): the rows are ordered pair
+    by pair and, for B > 64, the pair kernel gathers each shared column once.  Odd numbers of
+    pairs, a column shared by all three operators, ragged rows, 8- and 16-bit codes."""
+    rng = np.random.default_rng(n + B)
+    shared = [-17, -2, 1, 5, 40]
+    base = _structured_ops(rng, n, n_vals, [[0, 3, -n // 3, 1], shared, shared + [7]])
+    ops = [sp.csr_matrix(base[0].real.astype(complex)),                  # drift: real, shares column +1 with both controls
+           sp.csr_matrix(base[1].real.astype(complex)),                  # real control operator
+           sp.csr_matrix(1j * base[2].imag)][:n_ops]                      # imaginary control operator on the same columns
+    coeffs = ([0.7 - 0.2j, -1.3] if n_ops == 3 else [0.4 + 0.3j])
+    gen = qp.DeviceGenerator(ctx, ops, len(coeffs))
+    assert gen.n_dict > 0
+    dense = ops[0].toarray() + sum(c * A.toarray() for c, A in zip(coeffs, ops[1:]))
+    X, Y = rand_state(rng, n, B), rand_state(rng, n, B)
+    dx = qp.DeviceState.from_host(ctx, X)
+    for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+        dy = qp.DeviceState.from_host(ctx, Y)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), beta * Y + alpha * (dense @ X)) < 1e-13
+    ev = gen.expval(dx, coeffs)
+    assert np.max(np.abs(ev - np.einsum("ib,ib->b", X.conj(), dense @ X))) < 1e-12 * n
+    # single state through the B = 1 kernel on the same (reordered) rows
+    x1 = rand_state(rng, n)
+    d1, dy1 = qp.DeviceState.from_host(ctx, x1), qp.DeviceState.from_host(ctx, x1)
+    gen.mul(dy1, d1, coeffs, 1.0, 0.0)
+    assert rel(dy1.to_host(), dense @ x1) < 1e-13
+
+
 @pytest.mark.parametrize("B", [5, 40, 150])
 def test_cheby_batched_per_trajectory(qp, ctx, B):
     """Ensemble: B trajectories with their own control scale share one coefficient table
