@@ -849,3 +849,46 @@ def test_newton_library_vs_python_host_step(qp, ctx, hermitian):
     wrk = qp.NewtonWrk(st, A, m_max=10)
     qp.newton_(st, A, dt, wrk, coeffs=[], func=lambda z: np.cos(z) - 1j * np.sin(z))
     assert rel(st.to_host(), expected) < RTOL
+
+
+# ---------------------------------------------------------------------------------------
+# edge cases: empty operators and rows, 1 x 1 systems, slice boundaries, every storage format
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fmt", ["csr", "sell", "selld", "auto"])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 95])
+def test_edge_shapes_all_formats(qp, ctx, fmt, n):
+    """N around the slice height (32), a 1 x 1 system, an all-zero controlled operator, rows that
+    are empty in every operator, for every sparse storage format and for B = 1 / 3 / 40."""
+    rng = np.random.default_rng(100 + n)
+    diag = sp.diags(np.arange(1, n + 1, dtype=complex) * 0.1, 0, format="csr")
+    band = sp.diags([np.full(max(n - 1, 0), 0.5 + 0.25j)], [1], shape=(n, n), format="lil")
+    if n > 4:
+        band[n // 2, :] = 0  # an empty row in the coupling operator
+    band = sp.csr_matrix(band)
+    H1 = (band + band.conj().T).tocsr()
+    zero = sp.csr_matrix((n, n), dtype=complex)
+    ops = [diag, H1, zero]
+    coeffs = [0.3 - 0.2j, 5.0]
+    gen = qp.DeviceGenerator(ctx, ops, 2, fmt)
+    dense = (diag + coeffs[0] * H1).toarray()
+    for B in (None, 3, 40):
+        X = rand_state(rng, n, B)
+        Y = rand_state(rng, n, B)
+        dx, dy = qp.DeviceState.from_host(ctx, X), qp.DeviceState.from_host(ctx, Y)
+        gen.mul(dy, dx, coeffs, 0.5 - 1j, 2.0)
+        ref = 2.0 * Y + (0.5 - 1j) * (dense @ X)
+        assert np.linalg.norm(dy.to_host() - ref) <= 1e-13 * max(1.0, np.linalg.norm(ref))
+        ev = np.atleast_1d(gen.expval(dx, coeffs))
+        want = np.atleast_1d(np.einsum("i...,i...->...", np.conj(X), dense @ X))
+        assert np.max(np.abs(ev - want)) < 1e-12
+    # a generator made of zero operators only: mul! gives beta * y, Chebyshev gives a pure phase
+    gz = qp.DeviceGenerator(ctx, [zero], 0, fmt if fmt != "selld" else "auto")
+    x = rand_state(rng, n)
+    dx, dy = qp.DeviceState.from_host(ctx, x), qp.DeviceState.from_host(ctx, x)
+    gz.mul(dy, dx, [], 1.0, 0.0)
+    assert np.linalg.norm(dy.to_host()) == 0.0
+    wrk = qp.ChebyWrk(dx, gz, 2.0, -1.0, 0.1)
+    qp.cheby_(dx, None, 0.1, wrk, coeffs=[])
+    assert np.linalg.norm(dx.to_host() - x) < 1e-13
