@@ -1339,14 +1339,30 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   MatView m{gen->d_mptr, gen->d_mcolop, gen->d_mval, n};
   const int lanes = gen->lanes;
   const unsigned blocks = (unsigned)((n * lanes + 255) / 256);
+  // programmatic dependent launch (see k_spmv_csr): the next term's launch and matrix prologue
+  // overlap the tail of this one; QPROP_PDL=0 disables it
+  static const int pdl = getenv("QPROP_PDL") ? atoi(getenv("QPROP_PDL")) : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const double2* coef = gen->d_coef;
+  const int n_ops = gen->n_ops;
+  cudaError_t le = cudaSuccess;
   switch (lanes) {
-    case 1: k_spmv_csr<1, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
-    case 2: k_spmv_csr<2, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
-    case 4: k_spmv_csr<4, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
-    case 8: k_spmv_csr<8, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
-    case 16: k_spmv_csr<16, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
-    default: k_spmv_csr<32, EPI><<<blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e); break;
+    case 1: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<1, EPI>, m, coef, n_ops, x, e); break;
+    case 2: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<2, EPI>, m, coef, n_ops, x, e); break;
+    case 4: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<4, EPI>, m, coef, n_ops, x, e); break;
+    case 8: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<8, EPI>, m, coef, n_ops, x, e); break;
+    case 16: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<16, EPI>, m, coef, n_ops, x, e); break;
+    default: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<32, EPI>, m, coef, n_ops, x, e); break;
   }
+  QP_CUDA(ctx, le);
   QP_LAUNCHED(ctx);
   return QP_OK;
 }

@@ -197,15 +197,49 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
   const int lane = (int)(gtid % LANES);
   double sr = 0.0, si = 0.0;
   const bool active = row < m.n;
-  // epilogue operands requested before the row is walked: at small N the kernel is a chain of
-  // dependent L2 round trips (row pointer -> entries -> gathered x -> epilogue), this removes one
+  // Programmatic dependent launch: at small N a Chebyshev term is a chain of dependent L2 round
+  // trips (row pointer -> entries -> gathered x -> epilogue) behind a kernel launch.  Everything
+  // that does not depend on the previous term -- the coefficients, the row pointers, the first
+  // four entries per lane -- is fetched BEFORE griddepcontrol.wait, i.e. while the previous term
+  // is still running (the launch itself overlaps too); only the x gathers and the epilogue
+  // operands wait for it.  Without the launch attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t p0 = 0, p1 = 0;
+  uint32_t pco[4];
+  double2 pv[4];
+  if (active) {
+    p0 = m.ptr[row];
+    p1 = m.ptr[row + 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t k = p0 + lane + i * LANES;
+      pco[i] = 0u;
+      pv[i] = make_double2(0.0, 0.0);
+      if (k < p1) {
+        pco[i] = ld_stream(m.colop + k);
+        pv[i] = ld_stream(m.val + k);
+      }
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // epilogue operands requested before the gathers are consumed (one round trip less)
   double2 xr, yv, av;
   xr = yv = av = make_double2(0.0, 0.0);
   if (active && lane == 0) epi_load<EPI>(e, x, row, row, xr, yv, av);
   if (active) {
-    const uint32_t p0 = m.ptr[row], p1 = m.ptr[row + 1];
+    double2 pxv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pxv[i] = __ldg(x + (pco[i] & QP_COL_MASK));  // padding: column 0, value 0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 u = s_coef[pco[i] >> QP_COL_BITS];
+      const double tr = pv[i].x * pxv[i].x - pv[i].y * pxv[i].y;
+      const double ti = pv[i].x * pxv[i].y + pv[i].y * pxv[i].x;
+      sr += u.x * tr - u.y * ti;
+      si += u.x * ti + u.y * tr;
+    }
 #pragma unroll 4
-    for (uint32_t k = p0 + lane; k < p1; k += LANES) {
+    for (uint32_t k = p0 + lane + 4 * LANES; k < p1; k += LANES) {
       const uint32_t co = ld_stream(m.colop + k);
       const double2 v = ld_stream(m.val + k);
       const double2 xv = __ldg(x + (co & QP_COL_MASK));
