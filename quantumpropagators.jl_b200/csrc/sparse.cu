@@ -1187,7 +1187,20 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   static const int spc_env = getenv("QPROP_SELLD_SPC") ? atoi(getenv("QPROP_SELLD_SPC")) : 0;
   if (spc_env > 0) spc = spc_env;
   ctas = (gen->n_slices + spc - 1) / spc;
-  kern<<<(unsigned)ctas, threads, smem, ctx->stream>>>(m, gen->d_coef, x, e, (int)spc);
+  static const int pdl = getenv("QPROP_PDL") ? atoi(getenv("QPROP_PDL")) : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const double2* coef = gen->d_coef;
+  const int spc_i = (int)spc;
+  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, m, coef, x, e, spc_i));
   QP_LAUNCHED(ctx);
   return QP_OK;
 }

@@ -585,11 +585,16 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_val = reinterpret_cast<double2*>(smem_raw);
   int32_t* s_delta = reinterpret_cast<int32_t*>(s_val + m.n_dict);
+  // programmatic dependent launch: the launch of the next term and this table set-up (which
+  // depends on the matrix and the coefficients only) overlap the tail of the previous term;
+  // nothing written by the previous term (x, y, acc) is touched before griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
     s_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
     s_delta[j] = m.ddelta[j];
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t n_slices = (m.n + QP_SELL_C - 1) / QP_SELL_C;
