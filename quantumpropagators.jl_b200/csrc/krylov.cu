@@ -35,6 +35,7 @@ template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ w, int64_t n,
            double* __restrict__ partial, const double* __restrict__ gate) {
+  pdl_sync();
   if (gate != nullptr && *gate == 0.0) return;
   double sr[NV], si[NV], ww = 0.0;
 #pragma unroll
@@ -81,6 +82,7 @@ k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __rest
 __global__ void __launch_bounds__(32 * (2 * KV + 1))
 k_multidot_final(const double* __restrict__ partial, int nblocks, int nv, double2* __restrict__ h, int accumulate,
                  ColCtl* __restrict__ ctl, int write_ww, const double* __restrict__ gate) {
+  pdl_sync();
   if (gate != nullptr && *gate == 0.0) return;
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_ww = slot == 2 * KV;
@@ -103,6 +105,7 @@ template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h,
               double2* __restrict__ w, int64_t n, double* __restrict__ partial, const double* __restrict__ gate) {
+  pdl_sync();
   if (gate != nullptr && *gate == 0.0) return;
   double2 hv[NV];
 #pragma unroll
@@ -135,6 +138,7 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
 // second round adds its correction to the accumulated column
 __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, ColCtl* __restrict__ ctl, int round,
                               double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec) {
+  pdl_sync();
   if (round == 2 && ctl->again == 0.0) return;
   const int lane = threadIdx.x;
   double t = 0.0;
@@ -153,6 +157,7 @@ __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, C
 }
 
 __global__ void k_scale_real(double2* __restrict__ x, double s, int64_t n) {
+  pdl_sync();
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     double2 v = x[r];
     x[r] = make_double2(s * v.x, s * v.y);
@@ -161,6 +166,7 @@ __global__ void k_scale_real(double2* __restrict__ x, double s, int64_t n) {
 
 // x *= ctl->inv (normalisation with the norm still on the device)
 __global__ void k_scale_dev(double2* __restrict__ x, const ColCtl* __restrict__ ctl, int64_t n) {
+  pdl_sync();
   const double s = ctl->inv;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     double2 v = x[r];
@@ -173,6 +179,7 @@ template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_combine(const double2* __restrict__ q0, int64_t stride, Weights wt, double2* __restrict__ y, int64_t n,
           int accumulate) {
+  pdl_sync();
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     double2 acc = accumulate ? y[r] : make_double2(0.0, 0.0);
 #pragma unroll
@@ -271,19 +278,19 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j) {
     for (int i0 = 0; i0 < nvec; i0 += KV) {
       const int nv = std::min(KV, nvec - i0);
       const double2* q0 = K->q + (size_t)i0 * n;
-      DISPATCH_NV(nv, (k_multidot<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, w, n, partial, gate)));
+      DISPATCH_NV(nv, (qp_launch_pdl(k_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
-      k_multidot_final<<<1, 32 * (2 * KV + 1), 0, ctx->stream>>>(partial, nblocks, nv, h + i0, 0, ctl,
-                                                                  (round == 1 && i0 == 0) ? 1 : 0, gate);
+      qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nv, h + i0, 0, ctl,
+                    (round == 1 && i0 == 0) ? 1 : 0, gate);
       QP_LAUNCHED(ctx);
     }
     for (int i0 = 0; i0 < nvec; i0 += KV) {
       const int nv = std::min(KV, nvec - i0);
       const double2* q0 = K->q + (size_t)i0 * n;
-      DISPATCH_NV(nv, (k_project_out<NV><<<nblocks, KBLOCK, 0, ctx->stream>>>(q0, n, h + i0, w, n, partial, gate)));
+      DISPATCH_NV(nv, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, h + i0, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
     }
-    k_norm_decide<<<1, 32, 0, ctx->stream>>>(partial, nblocks, ctl, round, h_acc, h_corr, nvec);
+    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec);
     QP_LAUNCHED(ctx);
   }
   return QP_OK;
@@ -332,7 +339,7 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
     QP_CHECK(krylov_matvec(K, stride, j));
     QP_CHECK(orthogonalise_async(K, j));
     if (j + 1 < m || extended) {  // :88-97
-      k_scale_dev<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(j + 1) * n, K->d_ctl + j, n);
+      qp_launch_pdl(k_scale_dev, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(j + 1) * n, K->d_ctl + j, n);
       QP_LAUNCHED(ctx);
     }
   }
@@ -378,7 +385,7 @@ extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, in
   QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
   hess[(size_t)(m - 2) * ld + (m - 1)].re = dt * hn;  // Hess[m, m-1]
   hess[(size_t)(m - 2) * ld + (m - 1)].im = 0.0;
-  k_scale_real<<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
+  qp_launch_pdl(k_scale_real, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
   QP_LAUNCHED(ctx);
   QP_CHECK(krylov_matvec(K, stride, m - 1));
   QP_CHECK(orthogonalise_async(K, m - 1));
@@ -409,7 +416,7 @@ extern "C" int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* wts, int32_t 
     for (int i = 0; i < nv; ++i) wt.w[i] = make_double2(wts[i0 + i].re, wts[i0 + i].im);
     const double2* q0 = K->q + (size_t)(first + i0) * n;
     const int acc = (accumulate || i0 > 0) ? 1 : 0;
-    DISPATCH_NV(nv, (k_combine<NV><<<kgrid(ctx, n), KBLOCK, 0, ctx->stream>>>(q0, n, wt, st->d, n, acc)));
+    DISPATCH_NV(nv, (qp_launch_pdl(k_combine<NV>, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, q0, n, wt, st->d, n, acc)));
     QP_LAUNCHED(ctx);
   }
   return QP_OK;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -241,6 +243,35 @@ struct QpScopedTimer {
   QpScopedTimer(qp_ctx_t c, const char* l);
   ~QpScopedTimer();
 };
+
+// ---------------------------------------------------------------------------------------
+// programmatic dependent launch: the launch of a kernel overlaps the execution of the previous
+// kernel of the stream; kernels launched this way call pdl_sync() before touching memory
+// (QPROP_PDL=0: plain stream order)
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t qp_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  static const int pdl = getenv("QPROP_PDL") ? atoi(getenv("QPROP_PDL")) : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // internal kernels shared between translation units
