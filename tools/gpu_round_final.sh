@@ -11,3 +11,5 @@ cut -c1-2500 gpurun_out/f_bench.json; tail -4 gpurun_out/f_bench.err
 cut -c1-300 gpurun_out/f_bench_ref.json; tail -4 gpurun_out/f_bench_ref.err
 timeout 900 python tools/bench_configs.py --configs 1,3,5 > gpurun_out/f_configs.jsonl 2> gpurun_out/f_configs.err
 cut -c1-300 gpurun_out/f_configs.jsonl; tail -3 gpurun_out/f_configs.err
+timeout 900 python tools/bench_configs.py --configs 4 --liou-spins 12 --newton-steps 3 > gpurun_out/f_config4_full.jsonl 2>> gpurun_out/f_configs.err
+cut -c1-400 gpurun_out/f_config4_full.jsonl
