@@ -1,12 +1,12 @@
 #!/bin/bash
-# GPU session T4: PDL in the Krylov kernels -- parity + config 4 (n = 10, 11) with and without.
+# GPU session T5: contiguous ranges vs interleaved chunks in the SELL-D kernel (config 2).
 mkdir -p gpurun_out
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/t_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/t_pytest.log
-tail -6 gpurun_out/t_pytest.log
-for p in 0 1; do for n in 10 11; do
-QPROP_PDL=$p timeout 600 python tools/bench_configs.py --configs 4 --liou-spins $n --newton-steps 5 2>>gpurun_out/t.err | python -c "
+( timeout 600 python -m pytest tests -m gpu -x -q -k "selld or tfim or fullsize" ) > gpurun_out/t_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/t_pytest.log
+tail -3 gpurun_out/t_pytest.log
+for c in 0 8 16 32 64; do
+QPROP_SELLD_INTER=$c python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>>gpurun_out/t.err | python -c "
 import sys, json
-for l in sys.stdin:
-    d = json.loads(l); print('pdl=$p n=$n  ms/step %.3f' % d['ms_per_step'])"
-done; done
+d = json.loads(sys.stdin.readline()); r = d['roofline']
+print('inter=$c  %8.1f steps/s  %7.2f us/launch  frac_stored %.3f  normdev %.2e' % (d['value'], r['avg_launch_us'], r['frac_stored'], d['config']['norm_deviation_after_run']))"
+done
 tail -3 gpurun_out/t.err
