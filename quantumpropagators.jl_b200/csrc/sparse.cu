@@ -1172,7 +1172,10 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ctx->smem_configured.insert((const void*)kern);
   }
-  const int threads = 256;
+  // one CTA of 512 threads per SM: all 16 resident warps sweep ONE contiguous slice range (measured
+  // 32.0 us per term on config 2 against 32.8 us for 2 x 256 and 33.5 us for 4 x 128)
+  static const int threads_env = getenv("QPROP_SELLD_THREADS") ? atoi(getenv("QPROP_SELLD_THREADS")) : 512;
+  const int threads = (threads_env == 128 || threads_env == 256) ? threads_env : 512;
   static const int per_sm = getenv("QPROP_SELLD_CTAS") ? atoi(getenv("QPROP_SELLD_CTAS")) : 0;
   int occ = per_sm;
   if (occ <= 0) {
@@ -1314,8 +1317,8 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   }
   if (gen->format == QP_FORMAT_SELLD) {
     const DictView m = make_dict_view(gen);
-    // compiled for 2 resident CTAs of 256 threads per SM (<= 128 registers): measured best on
-    // B200 against 3 / 4 CTAs and a 16-gather variant (profiles/r1_variants.txt)
+    // compiled for 16 resident warps per SM (<= 128 registers): measured best on B200 against
+    // 24 / 32 warps and a 16-gather variant (profiles/r1_variants.txt)
     return gen->code_bytes == 1 ? launch_selld<EPI, 1>(gen, m, x, e) : launch_selld<EPI, 2>(gen, m, x, e);
   }
   if (gen->format == QP_FORMAT_SELL) {

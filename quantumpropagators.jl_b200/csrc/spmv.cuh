@@ -576,7 +576,7 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
 }
 
 template <int EPI, int CB>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(512, 1)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
              int slices_per_cta) {
   // the table, pre-multiplied by this step's operator coefficients, lives in shared memory
