@@ -28,7 +28,17 @@ def _load():
 
 
 def max_threads() -> int:
-    return int(_load().cheby_ref_max_threads())
+    """Host threads the OpenMP variant may use: the cores this process is allowed to run on.
+    (Not ``omp_get_max_threads()``: torchrun exports ``OMP_NUM_THREADS=1`` to every rank, which
+    would silently turn the multi-threaded CPU baseline into a single-threaded one at N > 1.)"""
+    import os
+
+    _load()
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(int(n), 256))
 
 
 class ChebyRef:
