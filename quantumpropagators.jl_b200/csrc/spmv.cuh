@@ -529,7 +529,8 @@ __device__ __forceinline__ double2 ld_noalloc(const double2* p) {
 // first one is consumed
 template <int CB, int NG>
 __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s_val, const int32_t* s_delta,
-                                             const double2* __restrict__ xbase, double& sr, double& si) {
+                                             const double2* __restrict__ xbase, double& sr, double& si,
+                                             double& sr2, double& si2) {
   constexpr int NC = 8 * NG;
   uint32_t code[NC];
   double2 xv[NC];
@@ -540,9 +541,14 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s
   for (int t = 0; t < NC; ++t) xv[t] = __ldg(xbase + s_delta[code[t]]);
 #pragma unroll
   for (int t = 0; t < NC; ++t) {
+    // four fused multiply-adds per entry in two accumulator pairs: the plain expression compiles to
+    // DMUL + DFMA + DADD per component (6 FP64 instructions), and this loop is sensitive to every
+    // instruction (31.8 -> 31.2 us per term on config 2; profiles/r1_selld_split_experiment.md)
     const double2 v = s_val[code[t]];
-    sr += v.x * xv[t].x - v.y * xv[t].y;
-    si += v.x * xv[t].y + v.y * xv[t].x;
+    sr = fma(v.x, xv[t].x, sr);
+    si = fma(v.x, xv[t].y, si);
+    sr2 = fma(-v.y, xv[t].y, sr2);
+    si2 = fma(v.y, xv[t].x, si2);
   }
 }
 
@@ -550,13 +556,14 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s
 // the extra registers cost more latency hiding than the deeper queue buys)
 template <int CB>
 __device__ __forceinline__ void selld_word(const uint4& c, const double2* s_val, const int32_t* s_delta,
-                                           const double2* __restrict__ xbase, double& sr, double& si) {
+                                           const double2* __restrict__ xbase, double& sr, double& si,
+                                           double& sr2, double& si2) {
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   if (CB == 1) {
-    selld_groups<1, 1>(w, s_val, s_delta, xbase, sr, si);
-    if ((w[2] | w[3]) != 0u) selld_groups<1, 1>(w + 2, s_val, s_delta, xbase, sr, si);  // not all padding
+    selld_groups<1, 1>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    if ((w[2] | w[3]) != 0u) selld_groups<1, 1>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);  // not all padding
   } else {
-    selld_groups<2, 1>(w, s_val, s_delta, xbase, sr, si);
+    selld_groups<2, 1>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
   }
 }
 
@@ -634,19 +641,21 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
     const bool any = n_off0 < n_off1;
     const int64_t s_next = s + nwarps;
     if (s_next < s_end) prefetch(s_next);
-    double sr = 0.0, si = 0.0;
+    double sr = 0.0, si = 0.0, sr2 = 0.0, si2 = 0.0;
     if (any) {
       for (;;) {
         const uint32_t off_n = off + QP_SELL_C;
         const bool more = off_n < off1;
         uint4 c_n = c;
         if (more) c_n = ld_stream(m.codes + off_n);  // look one word ahead
-        selld_word<CB>(c, s_val, s_delta, xbase, sr, si);
+        selld_word<CB>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
         if (!more) break;
         c = c_n;
         off = off_n;
       }
     }
+    sr += sr2;
+    si += si2;
     if (m.n_diag > 0 && live) {  // explicit diagonals: hx += sum_i u_i d_i[row] x[row]
       const double2 xs = EPI == EPI_MUL ? __ldg(x + row) : xr;
       double2 d = make_double2(0.0, 0.0);
