@@ -79,8 +79,8 @@ k_spmv_lr(const LRTerm* __restrict__ terms, int n_terms, int n_ops, int64_t nh, 
             }
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-              pr[jj] += v0.x * xv0[jj].x - v0.y * xv0[jj].y + v1.x * xv1[jj].x - v1.y * xv1[jj].y;
-              pi[jj] += v0.x * xv0[jj].y + v0.y * xv0[jj].x + v1.x * xv1[jj].y + v1.y * xv1[jj].x;
+              pr[jj] = fma(v0.x, xv0[jj].x, fma(-v0.y, xv0[jj].y, fma(v1.x, xv1[jj].x, fma(-v1.y, xv1[jj].y, pr[jj]))));
+              pi[jj] = fma(v0.x, xv0[jj].y, fma(v0.y, xv0[jj].x, fma(v1.x, xv1[jj].y, fma(v1.y, xv1[jj].x, pi[jj]))));
             }
           }
         }
@@ -129,22 +129,22 @@ k_spmv_lr(const LRTerm* __restrict__ terms, int n_terms, int n_ops, int64_t nh, 
               for (int jj = 0; jj < JB; ++jj) xv[jj] = __ldg(xb[jj] + a);
 #pragma unroll
               for (int jj = 0; jj < JB; ++jj) {
-                ar[jj] += v.x * xv[jj].x - v.y * xv[jj].y;
-                ai[jj] += v.x * xv[jj].y + v.y * xv[jj].x;
+                ar[jj] = fma(v.x, xv[jj].x, fma(-v.y, xv[jj].y, ar[jj]));
+                ai[jj] = fma(v.x, xv[jj].y, fma(v.y, xv[jj].x, ai[jj]));
               }
             }
           }
 #pragma unroll
           for (int jj = 0; jj < JB; ++jj) {
-            pr[jj] += vb[jj].x * ar[jj] - vb[jj].y * ai[jj];
-            pi[jj] += vb[jj].x * ai[jj] + vb[jj].y * ar[jj];
+            pr[jj] = fma(vb[jj].x, ar[jj], fma(-vb[jj].y, ai[jj], pr[jj]));
+            pi[jj] = fma(vb[jj].x, ai[jj], fma(vb[jj].y, ar[jj], pi[jj]));
           }
         }
       }
 #pragma unroll
       for (int jj = 0; jj < JB; ++jj) {
-        sr[jj] += cu.x * pr[jj] - cu.y * pi[jj];
-        si[jj] += cu.x * pi[jj] + cu.y * pr[jj];
+        sr[jj] = fma(cu.x, pr[jj], fma(-cu.y, pi[jj], sr[jj]));
+        si[jj] = fma(cu.x, pi[jj], fma(cu.y, pr[jj], si[jj]));
       }
     }
     if (live) {
