@@ -154,6 +154,7 @@ struct qp_gen_s {
   int n_dict = 0;          // 0: no dictionary
   int code_bytes = 0;      // 1 or 2
   uint32_t uniform_words = 0;
+  int tail_codes = 0;      // uniform_words > 0: codes of the longest row in its LAST word (0: full / unknown)
   int64_t dict_words = 0;  // 16-byte words stored
   int64_t stored_bytes = 0;  // bytes of the matrix stream actually read per application
   // QP_FORMAT_LR: terms of all operators

@@ -527,6 +527,14 @@ __global__ void k_diag_extract(const uint32_t* __restrict__ mptr, const uint32_t
     }
 }
 
+__global__ void k_max_row_len(const uint32_t* __restrict__ mptr, int64_t n, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, mptr[r + 1] - mptr[r]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 // 16-byte words per slice: ceil(longest row / codes per word) * 32
 __global__ void k_selld_widths(const uint32_t* __restrict__ mptr, int64_t n, int64_t n_slices, int cpw,
                                uint32_t* __restrict__ slice_words) {
@@ -806,6 +814,27 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
   g->n_dict = n_dict;
   g->code_bytes = cb;
   g->uniform_words = uniform && n_slices > 0 ? h_words[0] : 0u;
+  g->tail_codes = 0;
+  if (g->uniform_words > 0) {  // codes of the longest row in its last word, rounded up to even
+    unsigned int* d_max = nullptr;
+    unsigned int h_max = 0;
+    if (cudaMalloc(&d_max, sizeof(unsigned int)) == cudaSuccess) {
+      cudaMemsetAsync(d_max, 0, sizeof(unsigned int), ctx->stream);
+      k_max_row_len<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(g->d_mptr, n, d_max);
+      ctx->launches++;
+      if (cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+          cudaStreamSynchronize(ctx->stream) == cudaSuccess && h_max > 0) {
+        const unsigned words_per_row = g->uniform_words / QP_SELL_C;
+        if ((h_max + cpw - 1) / cpw == words_per_row) {
+          const int tail = (int)(h_max - (words_per_row - 1) * cpw);
+          g->tail_codes = tail >= cpw ? 0 : (tail + 1) / 2 * 2;
+          if (g->tail_codes >= cpw || g->tail_codes == 8) g->tail_codes = 0;
+        }
+      }
+      cudaGetLastError();
+      cudaFree(d_max);
+    }
+  }
   g->dict_words = (int64_t)total_words;
   *ok = true;
   return QP_OK;
@@ -1163,10 +1192,10 @@ static DictView make_dict_view(qp_gen_t gen) {
 
 // SELL-D kernel: CTAs = SMs x resident CTAs per SM (or fewer for small matrices), each owning a
 // contiguous slice range; dynamic shared memory = the coefficient-scaled table.
-template <int EPI, int CB>
+template <int EPI, int CB, int TAIL>
 static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
-  auto kern = k_spmv_selld<EPI, CB>;
+  auto kern = k_spmv_selld<EPI, CB, TAIL>;
   const size_t smem = (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1319,7 +1348,27 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     const DictView m = make_dict_view(gen);
     // compiled for 16 resident warps per SM (<= 128 registers): measured best on B200 against
     // 24 / 32 warps and a 16-gather variant (profiles/r1_variants.txt)
-    return gen->code_bytes == 1 ? launch_selld<EPI, 1>(gen, m, x, e) : launch_selld<EPI, 2>(gen, m, x, e);
+    // every slice has the same number of words and the longest row ends with `tail_codes` codes in
+    // its last word: that word is decoded without its padding (even tails 2 / 4 / 6 of a half word)
+    static const int no_tail = getenv("QPROP_SELLD_TAIL") ? atoi(getenv("QPROP_SELLD_TAIL")) == 0 : 0;
+    const int tail = no_tail ? 0 : gen->tail_codes;
+    if (gen->code_bytes == 1) {
+      switch (tail) {
+        case 2: return launch_selld<EPI, 1, 2>(gen, m, x, e);
+        case 4: return launch_selld<EPI, 1, 4>(gen, m, x, e);
+        case 6: return launch_selld<EPI, 1, 6>(gen, m, x, e);
+        case 10: return launch_selld<EPI, 1, 10>(gen, m, x, e);
+        case 12: return launch_selld<EPI, 1, 12>(gen, m, x, e);
+        case 14: return launch_selld<EPI, 1, 14>(gen, m, x, e);
+        default: return launch_selld<EPI, 1, 0>(gen, m, x, e);
+      }
+    }
+    switch (tail) {
+      case 2: return launch_selld<EPI, 2, 2>(gen, m, x, e);
+      case 4: return launch_selld<EPI, 2, 4>(gen, m, x, e);
+      case 6: return launch_selld<EPI, 2, 6>(gen, m, x, e);
+      default: return launch_selld<EPI, 2, 0>(gen, m, x, e);
+    }
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};

@@ -527,11 +527,10 @@ __device__ __forceinline__ double2 ld_noalloc(const double2* p) {
 
 // NG groups of 8 codes taken from the 32-bit words w[]: all 8*NG gathers are issued before the
 // first one is consumed
-template <int CB, int NG>
+template <int CB, int NC>
 __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s_val, const int32_t* s_delta,
                                              const double2* __restrict__ xbase, double& sr, double& si,
                                              double& sr2, double& si2) {
-  constexpr int NC = 8 * NG;
   uint32_t code[NC];
   double2 xv[NC];
 #pragma unroll
@@ -560,10 +559,30 @@ __device__ __forceinline__ void selld_word(const uint4& c, const double2* s_val,
                                            double& sr2, double& si2) {
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   if (CB == 1) {
-    selld_groups<1, 1>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
-    if ((w[2] | w[3]) != 0u) selld_groups<1, 1>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);  // not all padding
+    selld_groups<1, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    if ((w[2] | w[3]) != 0u) selld_groups<1, 8>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);  // not all padding
   } else {
-    selld_groups<2, 1>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    selld_groups<2, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+  }
+}
+
+// the LAST word of a row when the longest row of the matrix leaves TAIL (< codes per word) codes
+// in it: the padding behind them is never decoded (no run-time test: TAIL is a property of the
+// matrix, the last word is where the word loop ends anyway)
+template <int CB, int TAIL>
+__device__ __forceinline__ void selld_word_tail(const uint4& c, const double2* s_val, const int32_t* s_delta,
+                                                const double2* __restrict__ xbase, double& sr, double& si,
+                                                double& sr2, double& si2) {
+  const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+  if (CB == 1) {
+    if (TAIL <= 8) {
+      selld_groups<1, (TAIL <= 8 ? TAIL : 8)>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    } else {
+      selld_groups<1, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+      if ((w[2] | w[3]) != 0u) selld_groups<1, (TAIL > 8 ? TAIL - 8 : 8)>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);
+    }
+  } else {
+    selld_groups<2, (TAIL < 8 ? TAIL : 8)>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
   }
 }
 
@@ -582,7 +601,7 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
   }
 }
 
-template <int EPI, int CB>
+template <int EPI, int CB, int TAIL>
 __global__ void __launch_bounds__(512, 1)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
              int slices_per_cta) {
@@ -648,6 +667,10 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
         const bool more = off_n < off1;
         uint4 c_n = c;
         if (more) c_n = ld_stream(m.codes + off_n);  // look one word ahead
+        if (TAIL > 0 && !more) {
+          selld_word_tail<CB, (TAIL > 0 ? TAIL : 8)>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
+          break;
+        }
         selld_word<CB>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
         if (!more) break;
         c = c_n;
