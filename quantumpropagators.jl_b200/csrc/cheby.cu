@@ -310,9 +310,13 @@ extern "C" int32_t qp_cheby_propagate(qp_cheby_t w, qp_state_t st, const qp_c128
   };
 
   double2* saved_coef = gen->d_coef;
+  const std::vector<double2> saved_h_coef = gen->h_coef;
+  const bool saved_h_valid = gen->h_coef_valid;
   int32_t rc = record(0);
   for (int s = 0; s < n_steps && rc == QP_OK; ++s) {
     gen->d_coef = d_tbl + (size_t)s * per_step;
+    gen->h_coef_valid = width == 1;  // host copy: selects the real-table kernel variant per step
+    if (width == 1) gen->h_coef.assign(h_tbl.begin() + (size_t)s * per_step, h_tbl.begin() + (size_t)(s + 1) * per_step);
     {
       QpScopedTimer step_timer(ctx, "prop_step!");  // same label and count as the step loop
       rc = cheby_step_device(w, st, coeffs_per_traj ? 1 : 0, dt_signed, nullptr);
@@ -320,6 +324,8 @@ extern "C" int32_t qp_cheby_propagate(qp_cheby_t w, qp_state_t st, const qp_c128
     if (rc == QP_OK) rc = record(s + 1);
   }
   gen->d_coef = saved_coef;
+  gen->h_coef = saved_h_coef;
+  gen->h_coef_valid = saved_h_valid;
   if (rc != QP_OK) return cleanup(rc);
 
   if (rec_doubles) {

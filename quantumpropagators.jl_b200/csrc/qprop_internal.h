@@ -146,6 +146,11 @@ struct qp_gen_s {
   uint8_t* d_dop = nullptr;
   double* d_dvalr = nullptr;  // table values as one real number each (valid when dict_realv)
   bool pair_ordered = false;  // rows ordered "columns shared by two operators first" (spmm_pairs.cuh)
+  unsigned dict_has_re = 0, dict_has_im = 0;  // bit l: operator l has table values with a real / imaginary part
+  // host copy of the effective per-operator coefficients (valid when they were set from the host
+  // and are not per-trajectory): decides the real-table variant of the SELL-D kernel per launch
+  std::vector<double2> h_coef;
+  bool h_coef_valid = false;
   bool dict_realv = false;    // every operator purely real or purely imaginary
   unsigned imag_ops = 0;      // bit l: operator l is purely imaginary (value stored = Im)
   double2* d_diag = nullptr;  // explicit diagonals [n_diag][n] (see DictView)

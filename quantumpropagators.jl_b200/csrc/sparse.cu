@@ -740,6 +740,8 @@ static int32_t build_dict(qp_ctx_t ctx, qp_gen_t g, bool* ok, bool skip_diag) {
   D_CUDA(cudaMemcpy(g->d_dvalr, h_valr.data(), sizeof(double) * n_dict, cudaMemcpyHostToDevice));
   g->dict_realv = realv;
   g->imag_ops = realv ? has_im : 0u;
+  g->dict_has_re = has_re;
+  g->dict_has_im = has_im;
 
   // slice widths in 16-byte words
   D_CUDA(cudaMalloc(&d_words, sizeof(uint32_t) * (n_slices + 1)));
@@ -1151,6 +1153,11 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
       else
         h[l * width + b] = op_coeffs[(size_t)(l - gen->drift) * width + b];
     }
+  gen->h_coef_valid = !per_traj;
+  if (!per_traj) {
+    gen->h_coef.resize(gen->n_ops);
+    for (int l = 0; l < gen->n_ops; ++l) gen->h_coef[l] = make_double2(h[l].re, h[l].im);
+  }
   QP_CUDA(ctx, cudaMemcpyAsync(gen->d_coef, h, sizeof(double2) * elems, cudaMemcpyHostToDevice, ctx->stream));
   QP_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
   if (coef_stride_out) *coef_stride_out = per_traj ? 1 : 0;
@@ -1192,10 +1199,10 @@ static DictView make_dict_view(qp_gen_t gen) {
 
 // SELL-D kernel: CTAs = SMs x resident CTAs per SM (or fewer for small matrices), each owning a
 // contiguous slice range; dynamic shared memory = the coefficient-scaled table.
-template <int EPI, int CB, int TAIL>
+template <int EPI, int CB, int TAIL, int REALT>
 static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
-  auto kern = k_spmv_selld<EPI, CB, TAIL>;
+  auto kern = k_spmv_selld<EPI, CB, TAIL, REALT>;
   const size_t smem = (size_t)m.n_dict * (sizeof(double2) + sizeof(int32_t));
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1349,26 +1356,34 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     // compiled for 16 resident warps per SM (<= 128 registers): measured best on B200 against
     // 24 / 32 warps and a 16-gather variant (profiles/r1_variants.txt)
     // every slice has the same number of words and the longest row ends with `tail_codes` codes in
-    // its last word: that word is decoded without its padding (even tails 2 / 4 / 6 of a half word)
+    // its last word: that word is decoded without its padding (even tails 2 / 4 / 6 of a group)
     static const int no_tail = getenv("QPROP_SELLD_TAIL") ? atoi(getenv("QPROP_SELLD_TAIL")) == 0 : 0;
-    const int tail = no_tail ? 0 : gen->tail_codes;
+    int tail = no_tail ? 0 : gen->tail_codes;
+    if (tail > 6) tail = 0;
+    // real table: every (coefficient x value) product of this step is real -- known on the host
+    // when the coefficients were set from the host: operator by operator, real values with a
+    // real coefficient or purely imaginary values with a purely imaginary coefficient
+    static const int no_real = getenv("QPROP_SELLD_REAL") ? atoi(getenv("QPROP_SELLD_REAL")) == 0 : 0;
+    bool real_tab = !no_real && gen->h_coef_valid && (int)gen->h_coef.size() == gen->n_ops && gen->n_diag == 0;
+    for (int l = 0; real_tab && l < gen->n_ops; ++l) {
+      const bool re = (gen->dict_has_re >> l) & 1u, im = (gen->dict_has_im >> l) & 1u;
+      const double2 u = gen->h_coef[l];
+      if (re && im) real_tab = false;
+      else if (re) real_tab = u.y == 0.0;
+      else if (im) real_tab = u.x == 0.0;
+    }
+#define QP_SELLD_TAILS(CB, RT)                                         \
+  switch (tail) {                                                      \
+    case 2: return launch_selld<EPI, CB, 2, RT>(gen, m, x, e);         \
+    case 4: return launch_selld<EPI, CB, 4, RT>(gen, m, x, e);         \
+    case 6: return launch_selld<EPI, CB, 6, RT>(gen, m, x, e);         \
+    default: return launch_selld<EPI, CB, 0, RT>(gen, m, x, e);        \
+  }
     if (gen->code_bytes == 1) {
-      switch (tail) {
-        case 2: return launch_selld<EPI, 1, 2>(gen, m, x, e);
-        case 4: return launch_selld<EPI, 1, 4>(gen, m, x, e);
-        case 6: return launch_selld<EPI, 1, 6>(gen, m, x, e);
-        case 10: return launch_selld<EPI, 1, 10>(gen, m, x, e);
-        case 12: return launch_selld<EPI, 1, 12>(gen, m, x, e);
-        case 14: return launch_selld<EPI, 1, 14>(gen, m, x, e);
-        default: return launch_selld<EPI, 1, 0>(gen, m, x, e);
-      }
+      if (real_tab) QP_SELLD_TAILS(1, 1) else QP_SELLD_TAILS(1, 0)
     }
-    switch (tail) {
-      case 2: return launch_selld<EPI, 2, 2>(gen, m, x, e);
-      case 4: return launch_selld<EPI, 2, 4>(gen, m, x, e);
-      case 6: return launch_selld<EPI, 2, 6>(gen, m, x, e);
-      default: return launch_selld<EPI, 2, 0>(gen, m, x, e);
-    }
+    if (real_tab) QP_SELLD_TAILS(2, 1) else QP_SELLD_TAILS(2, 0)
+#undef QP_SELLD_TAILS
   }
   if (gen->format == QP_FORMAT_SELL) {
     MatView m{gen->d_sptr, gen->d_scolop, gen->d_sval, n};

@@ -527,7 +527,7 @@ __device__ __forceinline__ double2 ld_noalloc(const double2* p) {
 
 // NG groups of 8 codes taken from the 32-bit words w[]: all 8*NG gathers are issued before the
 // first one is consumed
-template <int CB, int NC>
+template <int CB, int NC, int REALT>
 __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s_val, const int32_t* s_delta,
                                              const double2* __restrict__ xbase, double& sr, double& si,
                                              double& sr2, double& si2) {
@@ -538,6 +538,20 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s
     code[t] = CB == 1 ? (w[t >> 2] >> (8 * (t & 3))) & 0xffu : (w[t >> 1] >> (16 * (t & 1))) & 0xffffu;
 #pragma unroll
   for (int t = 0; t < NC; ++t) xv[t] = __ldg(xbase + s_delta[code[t]]);
+  if (REALT) {  // every (coefficient x value) of this step is real: 8-byte lookups, 2 DFMA per entry
+#pragma unroll
+    for (int t = 0; t < NC; ++t) {
+      const double v = s_val[code[t]].x;
+      if (t & 1) {
+        sr2 = fma(v, xv[t].x, sr2);
+        si2 = fma(v, xv[t].y, si2);
+      } else {
+        sr = fma(v, xv[t].x, sr);
+        si = fma(v, xv[t].y, si);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int t = 0; t < NC; ++t) {
     // four fused multiply-adds per entry in two accumulator pairs: the plain expression compiles to
@@ -553,36 +567,36 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s
 
 // one 16-byte word of codes: 8 gathers in flight at a time (16 at once was slower on B200:
 // the extra registers cost more latency hiding than the deeper queue buys)
-template <int CB>
+template <int CB, int REALT>
 __device__ __forceinline__ void selld_word(const uint4& c, const double2* s_val, const int32_t* s_delta,
                                            const double2* __restrict__ xbase, double& sr, double& si,
                                            double& sr2, double& si2) {
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   if (CB == 1) {
-    selld_groups<1, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
-    if ((w[2] | w[3]) != 0u) selld_groups<1, 8>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);  // not all padding
+    selld_groups<1, 8, REALT>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    if ((w[2] | w[3]) != 0u) selld_groups<1, 8, REALT>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);  // not all padding
   } else {
-    selld_groups<2, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    selld_groups<2, 8, REALT>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
   }
 }
 
 // the LAST word of a row when the longest row of the matrix leaves TAIL (< codes per word) codes
 // in it: the padding behind them is never decoded (no run-time test: TAIL is a property of the
 // matrix, the last word is where the word loop ends anyway)
-template <int CB, int TAIL>
+template <int CB, int TAIL, int REALT>
 __device__ __forceinline__ void selld_word_tail(const uint4& c, const double2* s_val, const int32_t* s_delta,
                                                 const double2* __restrict__ xbase, double& sr, double& si,
                                                 double& sr2, double& si2) {
   const uint32_t w[4] = {c.x, c.y, c.z, c.w};
   if (CB == 1) {
     if (TAIL <= 8) {
-      selld_groups<1, (TAIL <= 8 ? TAIL : 8)>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+      selld_groups<1, (TAIL <= 8 ? TAIL : 8), REALT>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
     } else {
-      selld_groups<1, 8>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
-      if ((w[2] | w[3]) != 0u) selld_groups<1, (TAIL > 8 ? TAIL - 8 : 8)>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);
+      selld_groups<1, 8, REALT>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+      if ((w[2] | w[3]) != 0u) selld_groups<1, (TAIL > 8 ? TAIL - 8 : 8), REALT>(w + 2, s_val, s_delta, xbase, sr, si, sr2, si2);
     }
   } else {
-    selld_groups<2, (TAIL < 8 ? TAIL : 8)>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
+    selld_groups<2, (TAIL < 8 ? TAIL : 8), REALT>(w, s_val, s_delta, xbase, sr, si, sr2, si2);
   }
 }
 
@@ -601,7 +615,7 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
   }
 }
 
-template <int EPI, int CB, int TAIL>
+template <int EPI, int CB, int TAIL, int REALT>
 __global__ void __launch_bounds__(512, 1)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
              int slices_per_cta) {
@@ -668,10 +682,10 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
         uint4 c_n = c;
         if (more) c_n = ld_stream(m.codes + off_n);  // look one word ahead
         if (TAIL > 0 && !more) {
-          selld_word_tail<CB, (TAIL > 0 ? TAIL : 8)>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
+          selld_word_tail<CB, (TAIL > 0 ? TAIL : 8), REALT>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
           break;
         }
-        selld_word<CB>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
+        selld_word<CB, REALT>(c, s_val, s_delta, xbase, sr, si, sr2, si2);
         if (!more) break;
         c = c_n;
         off = off_n;
