@@ -313,7 +313,8 @@ def main():
         g = p.wrk.gen
         stored_term = g.stored_bytes + 80 * N  # bytes one launch actually has to move
         kernel = {
-            "selld": f"k_spmv_selld<CHEB_MID,{g.code_bytes}> (dictionary-compressed SELL-32, {g.n_dict} table entries)",
+            "selld": f"k_spmv_selld<CHEB_MID,CB={g.code_bytes},TAIL,REALT> (dictionary-compressed SELL-32, {g.n_dict} table entries, "
+                     "programmatic dependent launch)",
             "sell": ("k_spmv_sell_tma<CHEB_MID,16,2,8>" if os.environ.get("QPROP_SELL_KERNEL", "tma") != "ldg" else "k_spmv_sell<CHEB_MID>"),
         }.get(fmt, f"k_spmv_{fmt}<CHEB_MID>")
         out = {
