@@ -892,3 +892,44 @@ def test_edge_shapes_all_formats(qp, ctx, fmt, n):
     wrk = qp.ChebyWrk(dx, gz, 2.0, -1.0, 0.1)
     qp.cheby_(dx, None, 0.1, wrk, coeffs=[])
     assert np.linalg.norm(dx.to_host() - x) < 1e-13
+
+
+@pytest.mark.parametrize("row_len", [2, 4, 6, 10, 12, 18, 20, 22, 23])
+@pytest.mark.parametrize("n_vals", [3, 60])
+def test_selld_uniform_width_tails_and_real_table(qp, ctx, row_len, n_vals):
+    """Matrices whose rows all have the same length (circulant band): the SELL-D kernel is
+    specialised at compile time on the number of codes in the last code word (TAIL = 2 / 4 / 6,
+    or the generic path) for 8-bit (n_vals = 3) and 16-bit (n_vals = 60, longer rows) codes, and on whether
+    every coefficient x value product is real (real operator x real coefficient, imaginary operator
+    x imaginary coefficient) or not."""
+    rng = np.random.default_rng(row_len * 1000 + n_vals)
+    n = 4096
+    table = rng.standard_normal(n_vals)
+    r = np.arange(n)
+
+    def circulant(offsets, phase):
+        rows = np.concatenate([r for _ in offsets])
+        cols = np.concatenate([(r + d) % n for d in offsets])
+        vals = np.concatenate([table[(r * 7 + abs(d)) % n_vals] for d in offsets]) * phase
+        A = sp.csr_matrix((vals.astype(complex), (rows, cols)), shape=(n, n))
+        A.sort_indices()
+        return A
+
+    offs = [0, 1, -1, 5, -5, 33, -33, 64, -64, 200, -200, 777, -777, 1024, -1024, 1500, -1500, 2, -2, 9, -9, 17, -17]
+    n_real = row_len // 2
+    A_real = circulant(offs[:n_real], 1.0)                     # purely real operator
+    A_imag = circulant(offs[n_real:row_len], 1j)               # purely imaginary operator
+    gen = qp.DeviceGenerator(ctx, [A_real, A_imag], 1, "selld")
+    assert gen.format == "selld" and gen.code_bytes == (2 if gen.n_dict > 256 else 1)
+    if n_vals == 60 and row_len >= 6:
+        assert gen.code_bytes == 2
+    x, y0 = rand_state(rng, n), rand_state(rng, n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    # imaginary coefficient on the imaginary operator: all products real; complex / real: not
+    for c in (-0.7j, 0.3 - 0.4j, 1.5):
+        dense = (A_real + c * A_imag).tocsr()
+        for alpha, beta in ((1.0, 0.0), (0.5 - 1j, 2.0)):
+            dy = qp.DeviceState.from_host(ctx, y0)
+            gen.mul(dy, dx, [c], alpha, beta)
+            assert rel(dy.to_host(), beta * y0 + alpha * (dense @ x)) < 1e-13
+        assert abs(gen.expval(dx, [c]) - np.vdot(x, dense @ x)) < 1e-12 * n
