@@ -30,7 +30,15 @@ from .generators import (  # noqa: F401
     liouvillian,
     LeftRightOperator,
 )
-from . import interfaces  # noqa: F401
+from . import interfaces, storage  # noqa: F401
+from .storage import (  # noqa: F401
+    init_storage,
+    map_observables,
+    map_observable,
+    write_to_storage,
+    get_from_storage_,
+    get_from_storage,
+)
 from .interfaces import (  # noqa: F401
     check_amplitude,
     check_control,

@@ -266,3 +266,31 @@ def test_propagate_sequence(qp, ctx):
     assert np.allclose(np.squeeze(stor[0])[..., -1], np.abs(s1) ** 2, atol=1e-10)
     with pytest.raises(TypeError):
         qp.propagate_sequence(psi0, [(Ha, t1)])
+
+
+def test_storage_module_device_states(qp, ctx):
+    """Storage of device-resident states (a list of per-slot copies) and fused expectation values
+    of matrix observables on a DeviceState."""
+    rng = np.random.default_rng(1)
+    n = 50
+    psi = rand_state(rng, n)
+    st = qp.DeviceState.from_host(ctx, psi)
+    tlist = np.linspace(0, 1, 4)
+    slots = qp.init_storage(st, tlist)
+    assert slots == [None] * 4
+    for i in range(1, 5):
+        qp.write_to_storage(slots, i, st)
+        st.lmul(2.0)
+    assert slots[0] is not st and np.allclose(slots[2].to_host(), 4 * psi)
+    back = qp.DeviceState(ctx, n)
+    assert qp.get_from_storage_(back, slots, 2) is back and np.allclose(back.to_host(), 2 * psi)
+    host = np.zeros(n, dtype=complex)
+    qp.get_from_storage_(host, slots, 4)
+    assert np.allclose(host, 8 * psi)
+    O1 = sp.diags(rng.standard_normal(n) + 0j, 0, format="csr")
+    O2 = np.diag(rng.standard_normal(n)).astype(complex)
+    s0 = qp.DeviceState.from_host(ctx, psi)
+    data = qp.map_observables((O1, O2), tlist, 1, s0)
+    assert np.allclose(data, [np.vdot(psi, O1 @ psi), np.vdot(psi, O2 @ psi)], atol=1e-13)
+    assert qp.init_storage(s0, tlist, (O1, O2)).shape == (2, 4)
+    assert abs(qp.map_observable(lambda s: s.norm(), tlist, 1, s0) - 1) < 1e-14

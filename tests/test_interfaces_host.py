@@ -199,3 +199,35 @@ def test_liouvillian_matrix_free_equals_explicit_superoperators():
     assert isinstance(D, qp.LeftRightOperator)
     assert abs(D.tosparse() - qp.liouvillian(None, c_ops, convention="LvN")).max() < 1e-15
     assert abs((2.0 * D).tosparse() - 2.0 * D.tosparse()).max() < 1e-15
+
+
+def test_storage_module_host():
+    """Mirror of the reference's Storage module on host data (src/storage.jl; docs/src/storage.md)."""
+    tlist = np.linspace(0, 1, 5)
+    psi = np.array([1, 1j, 0], dtype=complex) / np.sqrt(2)
+    # states: n x nt matrix, written column by column, read back in place / out of place
+    st = qp.init_storage(psi, tlist)
+    assert st.shape == (3, 5) and st.dtype == psi.dtype
+    for i in range(1, 6):
+        qp.write_to_storage(st, i, i * psi)
+    assert np.array_equal(qp.get_from_storage(st, 3), 3 * psi)
+    buf = np.zeros(3, dtype=complex)
+    assert qp.get_from_storage_(buf, st, 5) is buf and np.array_equal(buf, 5 * psi)
+    # observables: matrices (expectation values), functions of (state) and of (state, tlist, i)
+    Z = np.diag([1.0, -1.0, 0.0]).astype(complex)
+    obs = (Z, sp.csr_matrix(Z @ Z))
+    data = qp.map_observables(obs, tlist, 1, psi)
+    assert isinstance(data, np.ndarray) and np.allclose(data, [0.0, 1.0])
+    assert qp.init_storage(psi, tlist, obs).shape == (2, 5)
+    assert abs(qp.map_observables((lambda s: float(np.linalg.norm(s)),), tlist, 1, psi) - 1.0) < 1e-15
+    assert abs(qp.map_observable(lambda s, tl, i: tl[i - 1] * np.abs(s) ** 2, tlist, 5, psi)[0] - 0.5) < 1e-15
+    mixed = qp.map_observables((Z, lambda s: "label"), tlist, 1, psi)
+    assert isinstance(mixed, tuple) and mixed[1] == "label"
+    slots = qp.init_storage(mixed, 4)
+    assert slots == [None] * 4
+    qp.write_to_storage(slots, 2, mixed)
+    assert qp.get_from_storage(slots, 2) is mixed
+    import pytest
+
+    with pytest.raises(TypeError, match="must take either"):
+        qp.map_observable(lambda a, b: 0, tlist, 1, psi)
