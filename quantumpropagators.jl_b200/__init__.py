@@ -30,7 +30,7 @@ from .generators import (  # noqa: F401
     liouvillian,
     LeftRightOperator,
 )
-from . import interfaces, storage  # noqa: F401
+from . import interfaces, shapes, storage  # noqa: F401
 from .storage import (  # noqa: F401
     init_storage,
     map_observables,

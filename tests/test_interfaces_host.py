@@ -231,3 +231,25 @@ def test_storage_module_host():
 
     with pytest.raises(TypeError, match="must take either"):
         qp.map_observable(lambda a, b: 0, tlist, 1, psi)
+
+
+def test_shapes():
+    """Mirror of the reference's Shapes module (src/shapes.jl; test/test_shapes.jl)."""
+    from qprop_b200.shapes import blackman, box, flattop
+
+    assert box(0.5, 0, 1) == 1.0 and box(1.5, 0, 1) == 0.0 and box(0.0, 0, 1) == 1.0
+    assert abs(blackman(0.5, 0, 1) - 1.0) < 1e-15 and abs(blackman(0.0, 0, 1)) < 1e-15 and blackman(2.0, 0, 1) == 0.0
+    kw = dict(T=10.0, t_rise=2.0)
+    assert flattop(5.0, **kw) == 1.0 and flattop(-1.0, **kw) == 0.0 and flattop(11.0, **kw) == 0.0
+    assert abs(flattop(0.0, **kw)) < 1e-15 and abs(flattop(10.0, **kw)) < 1e-15
+    assert abs(flattop(1.0, **kw) - blackman(1.0, 0.0, 4.0)) < 1e-15          # half a Blackman window
+    assert abs(flattop(1.0, func="sinsq", **kw) - 0.5) < 1e-15               # sin^2(pi/4)
+    assert abs(flattop(9.5, t_fall=1.0, **kw) - blackman(9.5, 8.0, 10.0)) < 1e-15
+    assert flattop(3.0, t0=2.0, **kw) < 1.0 and flattop(4.0, t0=2.0, **kw) == 1.0
+    import pytest
+
+    with pytest.raises(ValueError, match="Unknown func"):
+        flattop(1.0, func="gauss", **kw)
+    # usable as a control: check_control on a shaped pulse
+    tlist = np.linspace(0, 10, 101)
+    assert qp.check_control(lambda t: flattop(t, **kw), tlist)
