@@ -30,7 +30,8 @@ from .generators import (  # noqa: F401
     liouvillian,
     LeftRightOperator,
 )
-from . import interfaces, shapes, storage  # noqa: F401
+from . import amplitudes, interfaces, shapes, storage  # noqa: F401
+from .amplitudes import LockedAmplitude, ShapedAmplitude, GuidedAmplitude  # noqa: F401
 from .storage import (  # noqa: F401
     init_storage,
     map_observables,

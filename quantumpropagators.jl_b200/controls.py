@@ -72,6 +72,8 @@ def _is_vector(obj) -> bool:
 def get_controls(ampl):
     """Controls an amplitude depends on: a function or vector is its own control, a number
     has none (reference ``src/controls.jl:219-258``)."""
+    if getattr(ampl, "is_amplitude", False):  # amplitude objects (amplitudes.py) know their controls
+        return tuple(ampl.get_controls())
     if callable(ampl) or _is_vector(ampl):
         return (ampl,)
     return ()
@@ -149,6 +151,8 @@ def evaluate(obj, *args, vals_dict=None):
     (reference ``src/controls.jl:302-306, 346-397``)."""
     if vals_dict is not None and obj in vals_dict:
         return vals_dict[obj]
+    if getattr(obj, "is_amplitude", False):
+        return obj.evaluate(*args, vals_dict=vals_dict)
     if callable(obj):
         if len(args) == 2:
             return obj(t_mid(args[0], args[1]))
@@ -179,4 +183,6 @@ def substitute(obj, replacements):
     replaced, anything else is returned unchanged."""
     if isinstance(replacements, dict):
         replacements = IdDict(replacements)
+    if getattr(obj, "is_amplitude", False):
+        return obj.substitute(replacements)
     return replacements.get(obj, obj)

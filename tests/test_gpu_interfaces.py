@@ -294,3 +294,30 @@ def test_storage_module_device_states(qp, ctx):
     assert np.allclose(data, [np.vdot(psi, O1 @ psi), np.vdot(psi, O2 @ psi)], atol=1e-13)
     assert qp.init_storage(s0, tlist, (O1, O2)).shape == (2, 4)
     assert abs(qp.map_observable(lambda s: s.norm(), tlist, 1, s0) - 1) < 1e-14
+
+
+def test_propagate_with_shaped_amplitude(qp, ctx):
+    """A Generator whose amplitude is ShapedAmplitude(eps; shape=S) propagates exactly like the plain
+    control u(t) = S(t) eps(t) (the PWC value of eps is what `parameters` holds; the shape is
+    applied at evaluation time), and `parameters` lists the control, not the amplitude."""
+    from qprop_b200.shapes import flattop
+
+    w = qp.workloads.config1_random(N=60, density=0.2, seed=5, nt=41, T=4.0)
+    H0, H1 = w["ops"]
+
+    def eps(t):
+        return float(np.cos(1.3 * t))
+
+    def S(t):
+        return flattop(t, T=4.0, t_rise=1.0)
+
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"], ctx=ctx)
+    G_amp = qp.hamiltonian(H0, (H1, qp.ShapedAmplitude(eps, shape=S)))
+    G_fun = qp.hamiltonian(H0, (H1, lambda t: S(t) * eps(t)))
+    p = qp.init_prop(w["psi0"], G_amp, w["tlist"], "cheby", **kw)
+    assert list(p.parameters.keys()) == [eps] and len(p.parameters[eps]) == 40
+    out_amp = qp.propagate(p)
+    out_fun = qp.propagate(w["psi0"], G_fun, w["tlist"], "cheby", **kw)
+    assert np.linalg.norm(out_amp - out_fun) < 1e-13
+    st = qp.DeviceState.from_host(ctx, w["psi0"])
+    assert qp.check_generator(G_amp, state=st, tlist=w["tlist"], for_time_continuous=True)

@@ -253,3 +253,53 @@ def test_shapes():
     # usable as a control: check_control on a shaped pulse
     tlist = np.linspace(0, 10, 101)
     assert qp.check_control(lambda t: flattop(t, **kw), tlist)
+
+
+def test_amplitudes():
+    """Mirror of the reference's Amplitudes module (src/amplitudes.jl; test/test_amplitudes.jl):
+    locked, shaped and guided amplitudes inside a Generator."""
+    from qprop_b200.shapes import flattop
+
+    tlist = np.linspace(0, 10, 11)
+
+    def eps(t):
+        return 0.5 * t
+
+    def S(t):
+        return flattop(t, T=10.0, t_rise=2.0)
+
+    H0, H1, H2 = np.eye(2, dtype=complex), np.ones((2, 2), dtype=complex), np.diag([1.0, -1.0]).astype(complex)
+    a1 = qp.ShapedAmplitude(eps, shape=S)
+    a2 = qp.LockedAmplitude(S)
+    G = qp.hamiltonian(H0, (H1, a1), (H2, a2))
+    assert qp.get_controls(G) == (eps,)                                   # the locked amplitude has no control
+    assert qp.check_amplitude(a1, tlist) and qp.check_amplitude(a2, tlist)
+    op = qp.evaluate(G, tlist, 4)
+    tm = qp.t_mid(tlist, 4)
+    assert op.coeffs == [S(tm) * eps(tm), S(tm)]
+    op = qp.evaluate(G, tlist, 4, vals_dict=qp.IdDict([(eps, 2.0)]))       # PWC value of the control
+    assert op.coeffs == [S(tm) * 2.0, S(tm)]
+    assert a1(3.0) == S(3.0) * eps(3.0) and qp.controls.evaluate(a1, 3.0) == a1(3.0)
+    # discretised forms
+    ad = qp.ShapedAmplitude(eps, tlist, shape=S)
+    assert np.allclose(np.asarray(ad), qp.discretize_on_midpoints(eps, tlist) * qp.discretize_on_midpoints(S, tlist))
+    assert qp.controls.evaluate(ad, tlist, 4) == np.asarray(ad)[3]
+    assert qp.controls.evaluate(qp.LockedAmplitude(S, tlist), tlist, 2) == qp.discretize_on_midpoints(S, tlist)[1]
+    # guided: a = G + S eps
+    ag = qp.GuidedAmplitude(eps, guide=lambda t: 1.0 + t, shape=S)
+    assert qp.controls.evaluate(ag, tlist, 4) == (1.0 + tm) + S(tm) * eps(tm)
+    assert qp.get_controls(qp.hamiltonian(H0, (H1, ag))) == (eps,)
+    # substitute replaces the control inside the amplitude
+    def eps2(t):
+        return 1.0
+
+    G2 = qp.substitute(G, qp.IdDict([(eps, eps2)]))
+    assert qp.get_controls(G2) == (eps2,) and G2.amplitudes[1] is a2
+    import pytest
+
+    with pytest.raises(ValueError, match="same length"):
+        qp.ShapedAmplitude(np.zeros(3), shape=np.zeros(4))
+    with pytest.raises(ValueError, match="callable"):
+        qp.LockedAmplitude("x")
+    with pytest.raises(ValueError, match="only be evaluated"):
+        qp.controls.evaluate(qp.LockedAmplitude(np.zeros(10)), 0.5)
