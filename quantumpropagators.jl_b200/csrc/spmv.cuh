@@ -380,6 +380,9 @@ k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const do
   int64_t s_end = s_begin + slices_per_cta;
   if (s_end > n_slices) s_end = n_slices;
   const int n_loc = s_end > s_begin ? (int)(s_end - s_begin) : 0;
+  // the rounded-up slices-per-CTA can leave whole CTAs past the last slice: nothing to do, and
+  // their row-pointer reads would lie beyond the array (found by compute-sanitizer memcheck)
+  if (s_begin >= n_slices) return;
 
   if (threadIdx.x < n_ops) s_coef[threadIdx.x] = coef[threadIdx.x];
   for (int i = threadIdx.x; i <= n_loc; i += WARPS * 32) s_ptr[i] = m.ptr[s_begin + i];
