@@ -146,6 +146,13 @@ int32_t qp_state_devptr(qp_state_t st, void** devptr);
 /* host layout [n][nb] (batch fastest), columns b0 .. b0+nb-1 of the state */
 int32_t qp_state_upload(qp_state_t st, const qp_c128* host, int64_t b0, int64_t nb);
 int32_t qp_state_download(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb);
+/* The same transfers enqueued on the context's stream WITHOUT waiting for them: the host buffer
+ * (page-locked, or the copy degrades to a synchronous one) must stay untouched until qp_sync.
+ * Lets a host that keeps its states in host memory (the reference's Vector{ComplexF64} states,
+ * src/propagate.jl:283-344) overlap the copies of one trajectory with the step of another
+ * (one context = one stream per trajectory). */
+int32_t qp_state_upload_async(qp_state_t st, const qp_c128* host, int64_t b0, int64_t nb);
+int32_t qp_state_download_async(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb);
 
 int32_t qp_copy(qp_state_t dst, qp_state_t src);                    /* copyto!(dst, src) */
 int32_t qp_fill(qp_state_t st, qp_c128 value);                      /* fill!            */

@@ -92,6 +92,8 @@ SIGNATURES = {
     "qp_state_devptr": (_i32, [_vp, _P(_vp)]),
     "qp_state_upload": (_i32, [_vp, _vp, _i64, _i64]),
     "qp_state_download": (_i32, [_vp, _vp, _i64, _i64]),
+    "qp_state_upload_async": (_i32, [_vp, _vp, _i64, _i64]),
+    "qp_state_download_async": (_i32, [_vp, _vp, _i64, _i64]),
     "qp_copy": (_i32, [_vp, _vp]),
     "qp_fill": (_i32, [_vp, c128]),
     "qp_scal": (_i32, [_vp, c128]),

@@ -37,7 +37,7 @@ def cheby_coeffs_(coeffs, Delta, dt, limit=1e-12):
     array is returned next to the count."""
     new = cheby_coeffs(Delta, dt, limit)
     n = len(new)
-    size = len(coeffs)
+    size = max(len(coeffs), 1)  # an empty array would never grow under doubling
     while size <= n:
         size *= 2
     if size != len(coeffs):
@@ -56,6 +56,9 @@ class ChebyWrk:
             raise TypeError("ChebyWrk needs a DeviceState")
         self.ctx = Psi.ctx
         self.gen = _device_generator(H, Psi.ctx)
+        # identity of the component operators the workspace is bound to (the device matrices are
+        # immutable for its lifetime, like genop.ops in the reference, src/generators.jl:759)
+        self._op_ids = [id(op) for op in H.ops] if isinstance(H, (Operator, Generator)) else None
         lib = self.ctx._lib
         h = C.c_void_p()
         L.check(lib.qp_cheby_create(self.gen.handle, Psi.handle, C.byref(h)), self.ctx.handle)
@@ -97,14 +100,32 @@ def _device_generator(H, ctx) -> DeviceGenerator:
     return _as_operator(H).to_device(ctx)
 
 
-def cheby_(Psi: DeviceState, H, dt, wrk: ChebyWrk, check_normalization=False, coeffs=None, per_trajectory=False):
+def _upload_table(wrk, E_min):
+    L.check(
+        wrk.ctx._lib.qp_cheby_set_coeffs(wrk.handle, L.ptr(wrk.coeffs), wrk.n_coeffs, wrk.Delta, float(E_min), abs(wrk.dt), wrk.limit),
+        wrk.ctx.handle,
+    )
+
+
+def cheby_(Psi: DeviceState, H, dt, wrk: ChebyWrk, check_normalization=False, coeffs=None, per_trajectory=False,
+           E_min=None):
     """``cheby!(Ψ, H, dt, wrk; check_normalization)`` (reference ``src/cheby.jl:150-213``):
     Ψ ← exp(-i H dt) Ψ in place on the device.
 
     ``H`` is an ``Operator`` (its ``coeffs`` are the per-interval numbers) or a bare matrix;
     ``coeffs`` overrides them, and with ``per_trajectory`` is an [n_coeffs][B] array giving each
-    trajectory of a batched state its own amplitudes.
+    trajectory of a batched state its own amplitudes.  ``E_min`` overrides ``wrk.E_min`` for this
+    call (reference ``src/cheby.jl:152``).  The matrices are the ones the workspace was built
+    with: passing an ``Operator`` over different component matrices is an error.
     """
+    if isinstance(H, Operator) and wrk._op_ids is not None and [id(op) for op in H.ops] != wrk._op_ids:
+        raise ValueError("cheby!: H is made of different operators than the workspace was created with")
+    if E_min is not None and float(E_min) != wrk.E_min:
+        _upload_table(wrk, E_min)
+        try:
+            return cheby_(Psi, H, dt, wrk, check_normalization, coeffs, per_trajectory)
+        finally:
+            _upload_table(wrk, wrk.E_min)
     if coeffs is None:
         coeffs = H.coeffs if isinstance(H, Operator) else []
     c = L.as_c128_array(coeffs)

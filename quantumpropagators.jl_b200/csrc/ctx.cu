@@ -242,7 +242,7 @@ extern "C" int32_t qp_state_devptr(qp_state_t st, void** devptr) {
   return QP_OK;
 }
 
-static int32_t state_xfer(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb, bool upload) {
+static int32_t state_xfer(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb, bool upload, bool sync = true) {
   if (!st) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "null state");
   qp_ctx_t ctx = st->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
@@ -265,8 +265,16 @@ static int32_t state_xfer(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb, 
     QP_CUDA(ctx, cudaMemcpy2DAsync(host, nb * el, st->d + b0, st->batch * el, nb * el, st->n,
                                    cudaMemcpyDeviceToHost, ctx->stream));
   }
-  QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (sync) QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return QP_OK;
+}
+
+extern "C" int32_t qp_state_upload_async(qp_state_t st, const qp_c128* host, int64_t b0, int64_t nb) {
+  return state_xfer(st, const_cast<qp_c128*>(host), b0, nb, true, false);
+}
+
+extern "C" int32_t qp_state_download_async(qp_state_t st, qp_c128* host, int64_t b0, int64_t nb) {
+  return state_xfer(st, host, b0, nb, false, false);
 }
 
 extern "C" int32_t qp_state_upload(qp_state_t st, const qp_c128* host, int64_t b0, int64_t nb) {

@@ -137,7 +137,7 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
 // (DGKS) round is needed -- when the projection removed more than half of |w|^2 -- and the
 // second round adds its correction to the accumulated column
 __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, ColCtl* __restrict__ ctl, int round,
-                              double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec) {
+                              double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec, double norm_min) {
   pdl_sync();
   if (round == 2 && ctl->again == 0.0) return;
   const int lane = threadIdx.x;
@@ -151,7 +151,12 @@ __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, C
     }
   if (lane == 0) {
     ctl->nrm2 = t;
-    ctl->inv = 1.0 / sqrt(t);
+    // Krylov space exhausted (|w| < norm_min, src/arnoldi.jl:92-95): the reference leaves the
+    // residue unnormalised (a vector of norm < 1e-15); here it is zeroed, so that neither this
+    // vector nor the columns computed after it (discarded by the host) ever hold inf / NaN --
+    // the restart vector of newton! combines it with weight R[m+1] (src/newton.jl:360-366)
+    const double nrm = sqrt(t);
+    ctl->inv = (t > 0.0 && nrm >= norm_min) ? 1.0 / nrm : 0.0;
     if (round == 1) ctl->again = (t < 0.5 * ctl->ww && t != 0.0) ? 1.0 : 0.0;
   }
 }
@@ -260,7 +265,7 @@ extern "C" int32_t qp_krylov_destroy(qp_krylov_t K) {
 // column j of K->d_hall receives <q_i|w> (summed over the rounds), K->d_ctl[j] the norms.
 // Classical Gram-Schmidt; the second round always gets launched but is a no-op on the device
 // unless the DGKS criterion fired ("twice is enough").
-static int32_t orthogonalise_async(qp_krylov_t K, int j) {
+static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
   qp_ctx_t ctx = K->ctx;
   const int64_t n = K->n;
   const int nvec = j + 1;
@@ -290,7 +295,7 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j) {
       DISPATCH_NV(nv, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, h + i0, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
     }
-    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec);
+    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec, norm_min);
     QP_LAUNCHED(ctx);
   }
   return QP_OK;
@@ -337,7 +342,7 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
   // computed (on garbage) and simply discarded when the host reads the norms
   for (int j = 0; j < m; ++j) {
     QP_CHECK(krylov_matvec(K, stride, j));
-    QP_CHECK(orthogonalise_async(K, j));
+    QP_CHECK(orthogonalise_async(K, j, norm_min));
     if (j + 1 < m || extended) {  // :88-97
       qp_launch_pdl(k_scale_dev, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(j + 1) * n, K->d_ctl + j, n);
       QP_LAUNCHED(ctx);
@@ -388,7 +393,7 @@ extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, in
   qp_launch_pdl(k_scale_real, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
   QP_LAUNCHED(ctx);
   QP_CHECK(krylov_matvec(K, stride, m - 1));
-  QP_CHECK(orthogonalise_async(K, m - 1));
+  QP_CHECK(orthogonalise_async(K, m - 1, norm_min));
   std::vector<double2> h_all;
   std::vector<ColCtl> ctl;
   QP_CHECK(fetch_columns(K, m - 1, m, h_all, ctl));

@@ -203,7 +203,8 @@ def hamiltonian(*terms, check=True):
                 raise ValueError("time-dependent term must be 2-tuple")
             op, ampl = term
             slot = next(
-                (j for j, a in enumerate(amplitudes) if a is ampl or (_is_number(a) and _is_number(ampl) and a == ampl)),
+                (j for j, a in enumerate(amplitudes) if a is ampl or (_is_number(a) and _is_number(ampl) and a == ampl)
+                 or (isinstance(a, np.ndarray) and isinstance(ampl, np.ndarray) and np.array_equal(a, ampl))),  # `==` of the reference
                 None,
             )
             if slot is None:

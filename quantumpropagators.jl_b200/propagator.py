@@ -340,61 +340,51 @@ def _is_matrix_observable(obs):
     return sp.issparse(obs) or (isinstance(obs, np.ndarray) and obs.ndim == 2)
 
 
-class _ObservableCache:
-    """Device form of matrix observables (uploaded once per propagate call)."""
+def _observable_data(p, observables, i):
+    """Data stored for time slot ``i`` (1-based): the reference's ``_write_to_storage!``
+    (``src/propagate.jl:346-351``) = ``map_observables(observables, tlist, i, state)``; the default
+    observable ``_StoreState`` stores a copy of the state (``src/propagate.jl:14``) -- a host vector
+    when the propagation was started from a host array, else a device-resident copy."""
+    from .storage import map_observables
 
-    def __init__(self, ctx):
-        self.ctx = ctx
-        self.gens = {}
-
-    def gen(self, obs):
-        from .device import DeviceGenerator
-
-        key = id(obs)
-        if key not in self.gens:
-            self.gens[key] = DeviceGenerator(self.ctx, [obs], 0)
-        return self.gens[key]
-
-
-def _observe(observables, state: DeviceState, cache=None):
-    """Default observable: the state itself (downloaded copy); otherwise a tuple whose entries
-    are callables on the DeviceState or matrices, for which the expectation value ⟨Ψ|O|Ψ⟩ is
-    recorded (reference ``src/storage.jl:67-80, 100-123``)."""
     if observables is None:
-        return state.to_host()
-    out = []
-    for obs in observables:
-        if _is_matrix_observable(obs):
-            cache = cache or _ObservableCache(state.ctx)
-            out.append(cache.gen(obs).expval(state))
-        else:
-            out.append(obs(state))
-    return np.array(out)
+        return p.state.to_host() if p._host_io else p.state.copy()
+    return map_observables(observables, p.tlist, i, p.state)
+
+
+def _device_observables(ctx, observables):
+    """Device generators of matrix observables (cached per matrix by ``storage._device_observable``)."""
+    from .storage import _device_observable
+
+    return [_device_observable(o, ctx) for o in observables]
 
 
 def _propagate_on_device(p, observables, storage):
     """Fast path of ``propagate``: the whole remaining grid in ONE library call
     (``qp_cheby_propagate``), matrix observables evaluated on the device; no per-step host work
     and no state download.  Legal because without a callback nothing can change
-    ``propagator.parameters`` between the steps of one ``propagate`` call."""
+    ``propagator.parameters`` between the steps of one ``propagate`` call.  The recorded data go
+    through ``write_to_storage`` slot by slot, so any storage the loop path accepts works here."""
+    from .storage import write_to_storage
+
     tlist = p.tlist
     nt = len(tlist)
     steps = list(range(p.n, 0, -1)) if p.backward else list(range(p.n, nt))
-    gen = p._generator()
     table = np.zeros((len(steps), p.wrk.gen.n_coeffs), dtype=np.complex128)
     for s, n in enumerate(steps):
         H = p._coeffs_for(n)
         if isinstance(H, Operator):
             table[s, :] = H.coeffs
     dt = -p.wrk.dt if p.backward else p.wrk.dt
-    cache = _ObservableCache(p.ctx)
-    obs_gens = [cache.gen(o) for o in observables] if observables else []
+    obs_gens = _device_observables(p.ctx, observables) if observables else []
     ev, _ = cheby_propagate_(p.state, p.wrk, table, dt, observables=obs_gens)
     for _ in steps:
         p._advance_time()
     if storage is not None:
+        single = len(obs_gens) == 1  # map_observables: a single observable gives its bare value
         for s in range(nt):  # storage is written back to front when propagating backward
-            storage[..., (nt - 1 - s) if p.backward else s] = ev[s]
+            slot = (nt - s) if p.backward else s + 1
+            write_to_storage(storage, slot, complex(ev[s][0]) if single else np.array(ev[s]))
     return p.state
 
 
@@ -414,8 +404,15 @@ def propagate(
     the first argument is an initialised propagator.
 
     Returns the final state (a NumPy array if the initial state was one, else the
-    DeviceState), or the storage array when ``storage=True``.  With ``storage`` given, column i
-    holds the observables at ``tlist[i]`` (filled back to front when propagating backward)."""
+    DeviceState), or the storage when ``storage=True``.  Storage follows the reference's
+    ``Storage`` module exactly (``storage.py``): ``init_storage(state, tlist, observables)``
+    allocates it, every slot receives ``map_observables(observables, tlist, i, state)`` through
+    ``write_to_storage`` -- so observables may take ``(state)`` or ``(state, tlist, i)``, a single
+    observable stores its bare value (scalar data: a length-nt vector; vector data: an n x nt
+    matrix), several same-typed ones an n_obs x nt matrix, anything else a list of slots
+    (filled back to front when propagating backward)."""
+    from .storage import init_storage, write_to_storage
+
     if isinstance(state, PWCPropagator):
         p = state
     else:
@@ -423,7 +420,8 @@ def propagate(
     tlist = p.tlist
     nt = len(tlist)
     return_storage = storage is True
-    cache = _ObservableCache(p.ctx)
+    if observables is not None:
+        observables = tuple(observables)
     # whole grid in one library call when nothing has to run on the host between the steps:
     # Chebyshev, in place, no callback, and storage (if any) of matrix observables only
     on_device = (
@@ -432,26 +430,25 @@ def propagate(
         and (storage is None or (observables is not None and len(observables) > 0
                                  and all(_is_matrix_observable(o) for o in observables)))
     )
+    first_slot = nt if p.backward else 1
     if storage is True:
-        if on_device:
-            storage = np.zeros((len(observables), nt), dtype=np.complex128)
-        else:
-            first = _observe(observables, p.state, cache)
-            storage = np.zeros(first.shape + (nt,), dtype=first.dtype)
+        # init_storage(state, tlist, observables), src/propagate.jl:297-300 / src/storage.jl:38-44
+        storage = init_storage(_observable_data(p, observables, 1), nt)
     if on_device:
         _propagate_on_device(p, observables, storage)
         if return_storage:
             return storage
         return p.state.to_host() if p._host_io else p.state
     if storage is not None:
-        storage[..., nt - 1 if p.backward else 0] = _observe(observables, p.state, cache)
+        write_to_storage(storage, first_slot, _observable_data(p, observables, first_slot))
     intervals = range(nt - 1, 0, -1) if p.backward else range(1, nt)
     for i in intervals:
         prop_step(p)
         if callback is not None:
             callback(p, observables)
         if storage is not None:
-            storage[..., (i - 1) if p.backward else i] = _observe(observables, p.state, cache)
+            slot = i if p.backward else i + 1  # i + (backward ? 0 : 1), src/propagate.jl:331
+            write_to_storage(storage, slot, _observable_data(p, observables, slot))
     if return_storage:
         return storage
     return p.state.to_host() if p._host_io else p.state

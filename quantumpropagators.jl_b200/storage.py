@@ -27,11 +27,37 @@ __all__ = [
     "get_from_storage",
 ]
 
-_obs_cache = {}
+_OBS_CACHE_MAX = 32
+_obs_cache = {}  # (id(observable), id(ctx)) -> (observable, data fingerprint, device generator); bounded
 
 
 def _is_matrix(obs) -> bool:
     return sp.issparse(obs) or (isinstance(obs, np.ndarray) and obs.ndim == 2)
+
+
+def _fingerprint(obs):
+    """Cheap content check of a matrix observable, so that a matrix mutated in place after its
+    first use is uploaded again instead of silently using the stale device copy."""
+    data = obs.data if sp.issparse(obs) else obs
+    data = np.asarray(data)
+    step = max(1, data.size // 64)
+    return (data.shape, getattr(obs, "nnz", None), complex(np.sum(data.reshape(-1)[::step])), complex(data.reshape(-1)[-1]) if data.size else 0)
+
+
+def _device_observable(observable, ctx):
+    """Device generator (no free coefficients) of a matrix observable, uploaded once per
+    (matrix, context); the cache is bounded and keyed on identity + a content fingerprint."""
+    from .generators import _as_operator
+
+    key = (id(observable), id(ctx))
+    fp = _fingerprint(observable)
+    hit = _obs_cache.get(key)
+    if hit is None or hit[0] is not observable or hit[1] != fp:
+        if len(_obs_cache) >= _OBS_CACHE_MAX:
+            _obs_cache.pop(next(iter(_obs_cache)))
+        hit = (observable, fp, _as_operator(observable).to_device(ctx))
+        _obs_cache[key] = hit
+    return hit[2]
 
 
 def map_observable(observable, tlist, i, state):
@@ -40,14 +66,7 @@ def map_observable(observable, tlist, i, state):
     ⟨state|O|state⟩ is returned."""
     if _is_matrix(observable):
         if isinstance(state, DeviceState):
-            from .generators import _as_operator
-
-            key = (id(observable), id(state.ctx))
-            gen = _obs_cache.get(key)
-            if gen is None or gen[0] is not observable:
-                gen = (observable, _as_operator(observable).to_device(state.ctx))
-                _obs_cache[key] = gen
-            return gen[1].expval(state, [])
+            return _device_observable(observable, state.ctx).expval(state, [])
         return np.vdot(state, observable @ state)
     if callable(observable):
         try:
@@ -82,10 +101,15 @@ def map_observables(observables, tlist, i, state):
     return vals
 
 
+def _is_scalar(data) -> bool:
+    return isinstance(data, (bool, int, float, complex, np.number))
+
+
 def init_storage(state_or_data, tlist_or_nt, observables=None):
     """``init_storage(state, tlist)``, ``init_storage(state, tlist, observables)`` or
     ``init_storage(data, nt)`` (reference ``src/storage.jl:33-46``): an ``n × nt`` matrix for
-    vector data of length ``n``, otherwise a list of ``nt`` slots."""
+    vector data of length ``n``, a length-``nt`` vector for numbers (``Vector{T}(undef, nt)``),
+    otherwise a list of ``nt`` slots."""
     if observables is not None:
         data = map_observables(observables, tlist_or_nt, 1, state_or_data)
         nt = len(tlist_or_nt)
@@ -94,14 +118,20 @@ def init_storage(state_or_data, tlist_or_nt, observables=None):
         nt = int(tlist_or_nt) if np.isscalar(tlist_or_nt) else len(tlist_or_nt)
     if isinstance(data, np.ndarray) and data.ndim == 1:
         return np.empty((data.shape[0], nt), dtype=data.dtype)
+    if _is_scalar(data):
+        return np.empty(nt, dtype=np.result_type(data))
     return [None] * nt
 
 
 def write_to_storage(storage, i, data):
     """``write_to_storage!(storage, i, data)`` (reference ``src/storage.jl:138-144``): column ``i``
-    of a matrix storage, slot ``i`` of a list (device states are stored as copies)."""
+    of a matrix storage, element ``i`` of a vector, slot ``i`` of a list (device states are stored
+    as copies)."""
     if isinstance(storage, np.ndarray):
-        storage[:, i - 1] = data
+        if storage.ndim == 1:
+            storage[i - 1] = data
+        else:
+            storage[:, i - 1] = data
     else:
         storage[i - 1] = data.copy() if isinstance(data, (DeviceState, np.ndarray)) else data
     return storage
@@ -110,7 +140,7 @@ def write_to_storage(storage, i, data):
 def get_from_storage_(data, storage, i):
     """``get_from_storage!(data, storage, i)`` (reference ``src/storage.jl:168-169``): copies time
     slot ``i`` into ``data`` (a NumPy array or a ``DeviceState``) and returns it."""
-    src = storage[:, i - 1] if isinstance(storage, np.ndarray) else storage[i - 1]
+    src = get_from_storage(storage, i)
     if isinstance(data, DeviceState):
         return data.copyto(src)
     np.copyto(data, src.to_host() if isinstance(src, DeviceState) else src)
@@ -119,4 +149,6 @@ def get_from_storage_(data, storage, i):
 
 def get_from_storage(storage, i):
     """``get_from_storage(storage, i)`` (reference ``src/storage.jl:180-181``)."""
-    return storage[:, i - 1] if isinstance(storage, np.ndarray) else storage[i - 1]
+    if isinstance(storage, np.ndarray) and storage.ndim == 2:
+        return storage[:, i - 1]
+    return storage[i - 1]

@@ -126,3 +126,189 @@ def test_config5_full_size_dense_properties(qp, ctx):
         assert rel(fwd[:, b], s1.to_host()) < RTOL
     qp.cheby_(st, None, -dt, wrk, coeffs=[])
     assert rel(st.to_host(), psi) < RTOL
+
+
+# =========================================================================================
+# Oracle-level parity at BASELINE's full sizes (north_star: relative ‖ψ_gpu − ψ_ref‖ ≤ 1e-10
+# after the FULL tlist, norm conservation 1e-12 per step).  The reference bar these follow:
+# test/test_propagate.jl:153-163, test/test_cheby.jl:47.  The CPU side is the C restatement
+# oracle/cheby_ref.c (pinned against the NumPy oracle in tests/test_oracle_pins.py) for the
+# Chebyshev configs and the NumPy oracle itself for Newton / dense.
+# =========================================================================================
+
+
+@pytest.fixture(scope="module")
+def tfim20_full(qp):
+    return qp.workloads.config2_tfim(n_spins=20, nt=101, dt=0.1)
+
+
+@pytest.fixture(scope="module")
+def tfim20_oracle(tfim20_full):
+    """Config 2 over its full 100-step grid on the CPU (oracle/cheby_ref.c, all host threads);
+    the first two steps are also taken with the faithful single-thread CSC form, which pins the
+    row-parallel variant at this size."""
+    import oracle as O
+    from oracle import cref
+
+    assert cref.available(), "oracle/libcheby_ref.so is not built (run __graft_entry__.build())"
+    w = tfim20_full
+    terms = [w["ops"][0]] + list(zip(w["ops"][1:], w["controls"]))
+    p = O.init_prop(w["psi0"], O.hamiltonian(*terms), w["tlist"], "cheby", E_min=w["E_min"], E_max=w["E_max"])
+    ref = cref.ChebyRef(w["ops"], len(w["controls"]))
+    wrk = p.wrk
+    nt = len(w["tlist"])
+    psi = w["psi0"].copy()
+    psi_csc = w["psi0"].copy()
+    for n in range(1, nt):
+        coeffs = [complex(p.parameters[c][n - 1]) for c in p.controls]
+        ref.step(psi, coeffs, wrk.coeffs, wrk.Delta, wrk.E_min, wrk.dt, threads=cref.max_threads())
+        if n <= 2:
+            ref.step(psi_csc, coeffs, wrk.coeffs, wrk.Delta, wrk.E_min, wrk.dt, threads=0)
+            assert rel(psi, psi_csc) < 1e-13
+    return dict(final=psi, n_coeffs=wrk.n_coeffs)
+
+
+@pytest.mark.parametrize("fmt", ["selld", "sell", "csr"])
+def test_config2_full_tlist_vs_oracle(qp, ctx, tfim20_full, tfim20_oracle, fmt):
+    """Config 2 (TFIM N = 2^20, H0 + 2 PWC controls) over the FULL 100-step tlist for every
+    sparse storage format / kernel against the C oracle: ≤ 1e-10 on the final state, norm
+    conserved to 1e-12 per step (the drift over the whole grid is the reference's own coefficient
+    truncation at limit = 1e-12 per step, so the bound after 100 steps is 100 x that)."""
+    w = tfim20_full
+    p = qp.init_prop(w["psi0"], _gen(qp, w), w["tlist"], "cheby", E_min=w["E_min"], E_max=w["E_max"], ctx=ctx,
+                     matrix_format=fmt)
+    assert p.wrk.gen.format == fmt and p.wrk.n_coeffs == tfim20_oracle["n_coeffs"]
+    norms = [p.state.norm()]
+    while qp.prop_step(p) is not None:
+        norms.append(p.state.norm())
+    norms = np.array(norms)
+    assert len(norms) == 101
+    assert np.max(np.abs(np.diff(norms))) < 1e-12       # per step
+    assert np.max(np.abs(norms - 1)) < 1e-10            # whole grid
+    out = p.state.to_host()
+    err = rel(out, tfim20_oracle["final"])
+    assert err < RTOL, f"config 2 / {fmt}: relative error {err:.3e} after 100 steps"
+
+
+def test_config3_full_ensemble_vs_oracle(qp, ctx):
+    """Config 3 at full size: 1024 trajectories (a different random state and control scale each)
+    of the transmon chain N = 2^16 over the full 100-step tlist on the batched SELL-D kernel; 8
+    sampled trajectories against the C oracle (oracle/cheby_ref.c) propagating them one by one."""
+    import oracle as O
+    from oracle import cref
+    from qprop_b200.ensemble import EnsembleChebyPropagator
+
+    assert cref.available()
+    B = 1024
+    w = qp.workloads.config3_transmon(n_sites=8, levels=4, B=B, nt=101, dt=0.5)
+    H0, H1, H2 = w["ops"]
+    N = H0.shape[0]
+    bound = float((abs(H0) + 0.1 * abs(H1) + 0.1 * abs(H2)).sum(axis=1).max())
+    rng = np.random.default_rng(33)
+    psi0 = rng.standard_normal((N, B)) + 1j * rng.standard_normal((N, B))
+    psi0 /= np.linalg.norm(psi0, axis=0)
+    ens = EnsembleChebyPropagator(w["ops"], w["controls"], w["scales"], psi0, w["tlist"], -bound, bound, ctx)
+    assert ens.gen.format == "selld"
+    n_steps = len(w["tlist"]) - 1
+    nrm0 = np.asarray(ens.state.norm())
+    for _ in range(n_steps):
+        ens.prop_step()
+    nrm1 = np.asarray(ens.state.norm())
+    assert np.max(np.abs(nrm1 - nrm0)) < 1e-10 and np.max(np.abs(nrm0 - 1)) < 1e-13
+    sample = [0, 1, 127, 128, 500, 777, 1022, 1023]
+    ref = cref.ChebyRef(w["ops"], 2)
+    owrk = O.ChebyWrk(psi0[:, 0].copy(), ens.wrk.Delta, ens.wrk.E_min, ens.wrk.dt)
+    assert owrk.n_coeffs == ens.wrk.n_coeffs
+    mids = O.get_tlist_midpoints(w["tlist"])
+    for b in sample:
+        col = np.ascontiguousarray(psi0[:, b])
+        s = w["scales"][b]
+        for k in range(n_steps):
+            coeffs = [s * w["controls"][0](mids[k]), s * w["controls"][1](mids[k])]
+            ref.step(col, coeffs, owrk.coeffs, owrk.Delta, owrk.E_min, owrk.dt, threads=cref.max_threads())
+        got = ens.state.download(b, 1)[:, 0]
+        err = rel(got, col)
+        assert err < RTOL, f"config 3, trajectory {b}: relative error {err:.3e}"
+
+
+def _newton_generators(qp, w):
+    import oracle as O
+
+    (L0, L1), (u1,) = w["ops"], w["controls"]
+    return qp.hamiltonian(L0, (L1, u1)), O.hamiltonian(L0, (L1, u1))
+
+
+def test_config4_nh256_full_tlist_vs_oracle(qp, ctx):
+    """Config 4 at N_H = 256 (8 spins, super-operator dimension 2^16), Newton m_max = 10,
+    relerr = 1e-12, all 20 steps, explicit super-operators and the matrix-free form against
+    oracle.newton."""
+    import oracle as O
+
+    w = qp.workloads.config4_liouvillian(n_spins=8, nt=21, dt=0.05)
+    G, OG = _newton_generators(qp, w)
+    ref = O.propagate(w["psi0"], OG, w["tlist"], "newton", m_max=10, relerr=1e-12)
+    out = qp.propagate(w["psi0"], G, w["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12)
+    assert rel(out, ref) < RTOL
+    wf = qp.workloads.config4_liouvillian(n_spins=8, nt=21, dt=0.05, matrix_free=True)
+    Gf = qp.hamiltonian(wf["ops"][0], (wf["ops"][1], wf["controls"][0]))
+    out_f = qp.propagate(wf["psi0"], Gf, wf["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12)
+    assert rel(out_f, ref) < RTOL
+    rho = out.reshape(256, 256, order="F")
+    assert abs(np.trace(rho) - 1) < 1e-10
+
+
+def test_config4_full_size_explicit_vs_matrix_free_and_oracle(qp, ctx):
+    """Config 4 at FULL size (12 spins, N = 2^24, 9.5 GB of super-operators): two Newton steps
+    with the explicit SELL-D matrices ≡ the matrix-free left/right form to 1e-10, and the first
+    step of both against oracle.newton (NumPy/SciPy on the same host matrices)."""
+    import oracle as O
+
+    w = qp.workloads.config4_liouvillian(n_spins=12, nt=3, dt=0.05)
+    G, OG = _newton_generators(qp, w)
+    p = qp.init_prop(w["psi0"], G, w["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12)
+    step1 = qp.prop_step(p).to_host()
+    step2 = qp.prop_step(p).to_host()
+    del p
+    po = O.init_prop(w["psi0"], OG, w["tlist"], "newton", m_max=10, relerr=1e-12)
+    ref1 = np.array(O.prop_step(po))
+    assert rel(step1, ref1) < RTOL
+    del po, G, OG
+    wf = qp.workloads.config4_liouvillian(n_spins=12, nt=3, dt=0.05, matrix_free=True)
+    Gf = qp.hamiltonian(wf["ops"][0], (wf["ops"][1], wf["controls"][0]))
+    pf = qp.init_prop(wf["psi0"], Gf, wf["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12)
+    f1 = qp.prop_step(pf).to_host()
+    f2 = qp.prop_step(pf).to_host()
+    assert rel(f1, step1) < RTOL and rel(f2, step2) < RTOL and rel(f1, ref1) < RTOL
+    rho = f2.reshape(4096, 4096, order="F")
+    assert abs(np.trace(rho) - 1) < 1e-10
+
+
+def test_config5_dmma_vs_numpy_zgemm_and_oracle(qp, ctx):
+    """Config 5 (dense optomechanics generator, N = 8192): one application of the generator to
+    B = 64 states on the FP64 tensor-core kernel against NumPy's zgemm, and one Chebyshev step
+    (B = 16) against oracle.cheby on the same dense matrix."""
+    import oracle as O
+
+    H = qp.workloads.config5_optomech_dense()
+    N = H.shape[0]
+    gen = qp.DeviceGenerator(ctx, [H], 0)
+    rng = np.random.default_rng(55)
+    X = rng.standard_normal((N, 64)) + 1j * rng.standard_normal((N, 64))
+    x = qp.DeviceState.from_host(ctx, X)
+    y = x.similar()
+    gen.mul(y, x, [])
+    want = H @ X
+    assert np.max(np.linalg.norm(y.to_host() - want, axis=0) / np.linalg.norm(want, axis=0)) < 1e-13
+    ev = float(np.abs(H).sum(axis=1).max())
+    dt = 8.0 / ev
+    B = 16
+    psi = X[:, :B] / np.linalg.norm(X[:, :B], axis=0)
+    st = qp.DeviceState.from_host(ctx, psi)
+    wrk = qp.ChebyWrk(st, gen, 2 * ev, -ev, dt)
+    qp.cheby_(st, None, dt, wrk, coeffs=[])
+    ref = np.ascontiguousarray(psi.copy())
+    owrk = O.ChebyWrk(ref, 2 * ev, -ev, dt)
+    assert owrk.n_coeffs == wrk.n_coeffs
+    O.cheby_inplace(ref, H, dt, owrk)
+    out = st.to_host()
+    assert np.max(np.linalg.norm(out - ref, axis=0) / np.linalg.norm(ref, axis=0)) < RTOL

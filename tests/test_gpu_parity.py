@@ -591,6 +591,44 @@ def test_newton_eigenstate_shortcut_and_max_restarts(qp, ctx):
         qp.init_prop(V[:, 0], (H,), np.linspace(0, 1, 5), "newton", ctx=ctx, inplace=False)
 
 
+@pytest.mark.parametrize("hermitian", [True, False])
+def test_newton_exact_krylov_breakdown(qp, ctx, hermitian):
+    """A basis-state start inside a small invariant block of a sparse generator: the Krylov space
+    is exhausted after 3 vectors with a residue of norm EXACTLY zero (src/arnoldi.jl:92-95).  The
+    restart vector of newton! combines that residue too (src/newton.jl:360-366), so it must stay
+    finite (zero), not inf * 0; a large dt forces restarts."""
+    rng = np.random.default_rng(77)
+    N = 24
+    H = np.zeros((N, N), dtype=complex)
+    blk = np.array([[0.3, 1.0, 0.0], [1.0, -0.2, 0.7], [0.0, 0.7, 0.5]], dtype=complex)
+    if not hermitian:
+        blk = blk + np.array([[0, 0.4j, 0], [-0.1, 0.05j, 0.3], [0, 0.2, -0.1j]])
+    H[:3, :3] = blk
+    rest = rng.standard_normal((N - 3, N - 3)) + 1j * rng.standard_normal((N - 3, N - 3))
+    H[3:, 3:] = rest + rest.conj().T
+    Hs = sp.csr_matrix(H)
+    psi = np.zeros(N, dtype=complex)
+    psi[0] = 1.0
+    dt = 6.0
+    expected = sla.expm(-1j * H * dt) @ psi
+    for host_step in ("library", "python"):
+        st = qp.DeviceState.from_host(ctx, psi)
+        wrk = qp.NewtonWrk(st, Hs, m_max=8)
+        qp.newton_(st, Hs, dt, wrk, max_restarts=200, coeffs=[], host_step=host_step)
+        out = st.to_host()
+        assert np.all(np.isfinite(out))
+        assert rel(out, expected) < RTOL
+        assert wrk.restarts >= 1
+    # the fine-grained Arnoldi reports the reduced dimension and finite vectors
+    st = qp.DeviceState.from_host(ctx, psi)
+    wrk = qp.NewtonWrk(st, Hs, m_max=8)
+    Hess = np.zeros((9, 9), dtype=np.complex128)
+    m = qp.arnoldi_(Hess, wrk.krylov, 8, st, Hs, 1.0, coeffs=[])
+    assert m == 3 and abs(Hess[3, 2]) < 1e-14 and np.all(np.isfinite(Hess))
+    q3 = wrk.krylov.get(3, st.similar()).to_host()
+    assert np.all(np.isfinite(q3)) and np.linalg.norm(q3) < 1e-14
+
+
 def test_specrange_arnoldi_brackets_spectrum(qp, ctx):
     """test/test_specrad.jl:80-144: :arnoldi within 5% of Δ outside the true spectrum;
     :diag exact; :manual / :auto dispatch."""
@@ -765,6 +803,43 @@ def test_expval_dense(qp, ctx):
         dx = qp.DeviceState.from_host(ctx, X)
         ref = np.vdot(X, A @ X) if B == 1 else np.einsum("ib,ib->b", X.conj(), A @ X)
         assert np.allclose(qp.DeviceGenerator(ctx, [A], 0).expval(dx), ref, rtol=1e-12)
+
+
+def test_propagate_storage_follows_storage_module(qp, ctx):
+    """propagate routes its storage through init_storage / map_observables / write_to_storage
+    (reference src/propagate.jl:283-351): observables of (state, tlist, i), a single observable
+    storing its bare value (length-nt vector), list storage for device-resident states, and a
+    caller-supplied storage."""
+    w = qp.workloads.config2_tfim(8, nt=11, dt=0.1)
+    gen = _product_generator(qp, w["ops"], w["controls"])
+    kw = dict(E_min=w["E_min"], E_max=w["E_max"], ctx=ctx)
+    tl = w["tlist"]
+    # 3-argument observable
+    seen = []
+    def obs3(state, tlist, i):
+        seen.append(i)
+        return tlist[i - 1] * state.norm()
+    vec = qp.propagate(w["psi0"], gen, tl, "cheby", storage=True, observables=(obs3,), **kw)
+    assert vec.shape == (11,) and seen[1:] == list(range(1, 12)) and np.allclose(vec, tl, atol=1e-11)
+    # single matrix observable: bare expectation values, fast path == loop path
+    Oz = w["ops"][2]
+    fast = qp.propagate(w["psi0"], gen, tl, "cheby", storage=True, observables=(Oz,), **kw)
+    slow = qp.propagate(w["psi0"], gen, tl, "cheby", storage=True, observables=(Oz,), callback=lambda p, o: None, **kw)
+    assert fast.shape == (11,) and slow.shape == (11,) and np.max(np.abs(fast - slow)) < 1e-11
+    ref = O.propagate(w["psi0"], _oracle_generator(w["ops"], w["controls"]), tl, "cheby", storage=True,
+                      observables=(lambda psi: np.vdot(psi, Oz @ psi),), E_min=w["E_min"], E_max=w["E_max"])
+    assert np.max(np.abs(fast - ref[0])) < 1e-10
+    # device-resident initial state: default storage is a list of per-slot device copies
+    st0 = qp.DeviceState.from_host(ctx, w["psi0"])
+    slots = qp.propagate(st0, gen, tl, "cheby", storage=True, **kw)
+    assert isinstance(slots, list) and len(slots) == 11 and all(isinstance(s, qp.DeviceState) for s in slots)
+    full = qp.propagate(w["psi0"], gen, tl, "cheby", storage=True, **kw)
+    assert full.shape == (w["psi0"].shape[0], 11)
+    assert rel(slots[-1].to_host(), full[:, -1]) < 1e-14 and rel(slots[0].to_host(), w["psi0"]) < 1e-15
+    # caller-supplied list storage with matrix observables on the one-call path
+    mine = [None] * 11
+    qp.propagate(w["psi0"], gen, tl, "cheby", storage=mine, observables=(Oz, Oz), **kw)
+    assert np.allclose([m[0] for m in mine], fast, atol=1e-11)
 
 
 @pytest.mark.parametrize("backward", [False, True])

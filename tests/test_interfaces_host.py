@@ -221,6 +221,11 @@ def test_storage_module_host():
     assert qp.init_storage(psi, tlist, obs).shape == (2, 5)
     assert abs(qp.map_observables((lambda s: float(np.linalg.norm(s)),), tlist, 1, psi) - 1.0) < 1e-15
     assert abs(qp.map_observable(lambda s, tl, i: tl[i - 1] * np.abs(s) ** 2, tlist, 5, psi)[0] - 0.5) < 1e-15
+    # scalar data: Vector{T}(undef, nt) (src/storage.jl:44), element-wise writes
+    vec = qp.init_storage(psi, tlist, (Z,))
+    assert vec.shape == (5,) and vec.dtype == np.complex128
+    qp.write_to_storage(vec, 2, 0.25 + 0j)
+    assert qp.get_from_storage(vec, 2) == 0.25
     mixed = qp.map_observables((Z, lambda s: "label"), tlist, 1, psi)
     assert isinstance(mixed, tuple) and mixed[1] == "label"
     slots = qp.init_storage(mixed, 4)
