@@ -63,6 +63,7 @@ typedef struct qp_gen_s* qp_gen_t;
 typedef struct qp_state_s* qp_state_t;
 typedef struct qp_cheby_s* qp_cheby_t;
 typedef struct qp_krylov_s* qp_krylov_t;
+typedef struct qp_ens_s* qp_ens_t;
 
 typedef struct {
   double re, im;
@@ -132,6 +133,18 @@ int32_t qp_gen_info(qp_gen_t gen, int32_t* format, int64_t* n, int64_t* stored_e
  * be built (used by QP_FORMAT_SELLD and by the trajectory-batched kernel; 0 otherwise).  No reference counterpart:
  * the reference stores SparseMatrixCSC{ComplexF64,Int64} (24 B per entry). */
 int32_t qp_gen_storage(qp_gen_t gen, int64_t* stored_bytes, int32_t* n_dict, int32_t* code_bytes);
+
+/* The two-pass tiled form of the generator used for trajectory-batched states (batch a multiple of
+ * 32; csrc/tile_format.h): rows split as r = hi * split + lo, entries served from a shared-memory
+ * tile of the state when row and column lie in the same block (class A) or at the same position of
+ * different blocks (class B).  Built on first use.  available = 0: the generator does not qualify
+ * (dense / matrix-free, more than 3 operators, complex-valued operators, no split of N with tiles
+ * of <= 256 rows, or more than a quarter of the entries in neither class) and batched states use
+ * the one-pass kernels.  entries[4] = merged entries of class A, B, other, diagonal.  No reference
+ * counterpart (the reference applies one SparseMatrixCSC per operator and state,
+ * src/generators.jl:634-645). */
+int32_t qp_gen_tile_info(qp_gen_t gen, int32_t* available, int32_t* split, int32_t* blocks, int32_t* n_table,
+                         int64_t* entries);
 
 /* ------------------------------------------------------------------ states
  * Replaces: Vector{ComplexF64} states and the level-1 verbs the reference's kernels use
@@ -265,6 +278,46 @@ int32_t qp_extend_leja(qp_c128* leja, int32_t capacity, int32_t* n, qp_c128* new
 int32_t qp_extend_newton_coeffs(qp_c128* a, int32_t capacity, int32_t* n_a, const qp_c128* leja,
                                 int32_t n_leja, int32_t func_id, qp_newton_func_t func, void* user,
                                 double radius);
+
+/* ------------------------------------------------------------------ ensembles / multi-GPU
+ * An ensemble of n_total independent trajectories (same system, different control amplitudes) is
+ * cut into contiguous blocks, one per rank (qp_ens_shard); every rank holds the operators and a
+ * [N][B_local] batched state and steps it with qp_cheby_step / qp_cheby_propagate -- there is NO
+ * communication inside the time loop.  The only collectives are the final gathers below; they run
+ * over NCCL (NVLink / NVSwitch) INSIDE the library, so a host without its own communication layer
+ * (Julia) can use every GPU of a box.  Replaces: the caller-side loop over one propagator per
+ * trajectory that shares a spectral envelope through `control_ranges`
+ * (src/cheby_propagator.jl:59-66) and collects the results.
+ *
+ *   single process, many GPUs:  qp_ens_create(devices, n, &ens); rank i's objects are created on
+ *                               the context qp_ens_ctx(ens, i, ...) returns.  All entries of
+ *                               `devices` distinct: NCCL (ncclCommInitAll).  All entries equal:
+ *                               "fake ranks" on one device, the gathers use device copies (the
+ *                               layout logic can be exercised on a single-GPU box).
+ *   one process per GPU:        rank 0 calls qp_ens_unique_id and hands the 128 bytes to the other
+ *                               processes (MPI, the launcher, a file ...); every process then
+ *                               calls qp_ens_create_rank with its own context.
+ * NCCL (libnccl.so.2) is loaded at first use; without it only single-rank and fake-rank ensembles
+ * work (QP_ERR_UNSUPPORTED otherwise). */
+int32_t qp_ens_shard(int64_t n_total, int32_t rank, int32_t n_ranks, int64_t* b0, int64_t* b1);
+int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens_t* ens);
+int32_t qp_ens_unique_id(uint8_t* id /*[128]*/);
+int32_t qp_ens_create_rank(qp_ctx_t ctx, int32_t rank, int32_t n_ranks, const uint8_t* id /*[128]*/, qp_ens_t* ens);
+int32_t qp_ens_destroy(qp_ens_t ens);
+/* transport: 0 = device copies (one rank, or fake ranks), 1 = NCCL */
+int32_t qp_ens_info(qp_ens_t ens, int32_t* n_ranks, int32_t* n_local, int32_t* transport);
+/* context and world rank of the local_index-th member held by this process */
+int32_t qp_ens_ctx(qp_ens_t ens, int32_t local_index, qp_ctx_t* ctx, int32_t* rank);
+/* Final states of the whole ensemble: local_states[i] is the [N][B_local] state of local member i.
+ * full_states (or NULL): one [N][n_total] state per local member, filled on its device;
+ * host_out (or NULL): [N][n_total] on the host (from the first local member).  Collective: every
+ * process of the ensemble must call it. */
+int32_t qp_ens_gather_states(qp_ens_t ens, const qp_state_t* local_states, int64_t n_total,
+                             const qp_state_t* full_states, qp_c128* host_out);
+/* Per-trajectory numbers (expectation values, norms ...): local_values[i] is member i's host array
+ * [n_values][B_local]; out receives [n_values][n_total] in every process.  Collective. */
+int32_t qp_ens_gather_expvals(qp_ens_t ens, const qp_c128* const* local_values, int32_t n_values,
+                              int64_t n_total, qp_c128* out);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ SIGNATURES = {
     "qp_gen_destroy": (_i32, [_vp]),
     "qp_gen_info": (_i32, [_vp, _P(_i32), _P(_i64), _P(_i64), _P(_i64)]),
     "qp_gen_storage": (_i32, [_vp, _P(_i64), _P(_i32), _P(_i32)]),
+    "qp_gen_tile_info": (_i32, [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32), _vp]),
     "qp_state_create": (_i32, [_vp, _i64, _i64, _P(_vp)]),
     "qp_state_destroy": (_i32, [_vp]),
     "qp_state_info": (_i32, [_vp, _P(_i64), _P(_i64)]),
@@ -118,6 +119,15 @@ SIGNATURES = {
     "qp_diagonalize_hessenberg": (_i32, [_vp, _i32, _i32, _i32, _vp, _P(_i32)]),
     "qp_extend_leja": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32]),
     "qp_extend_newton_coeffs": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32, _vp, _vp, _f64]),
+    "qp_ens_shard": (_i32, [_i64, _i32, _i32, _P(_i64), _P(_i64)]),
+    "qp_ens_create": (_i32, [_vp, _i32, _P(_vp)]),
+    "qp_ens_unique_id": (_i32, [_vp]),
+    "qp_ens_create_rank": (_i32, [_vp, _i32, _i32, _vp, _P(_vp)]),
+    "qp_ens_destroy": (_i32, [_vp]),
+    "qp_ens_info": (_i32, [_vp, _P(_i32), _P(_i32), _P(_i32)]),
+    "qp_ens_ctx": (_i32, [_vp, _i32, _P(_vp), _P(_i32)]),
+    "qp_ens_gather_states": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "qp_ens_gather_expvals": (_i32, [_vp, _vp, _i32, _i64, _vp]),
     "qp_krylov_get": (_i32, [_vp, _i32, _vp]),
     "qp_krylov_set": (_i32, [_vp, _i32, _vp]),
 }

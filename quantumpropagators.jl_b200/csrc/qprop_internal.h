@@ -114,6 +114,10 @@ struct DictView {
   unsigned long long diag_ops;  // operator index of vector i in bits [4i, 4i+4)
 };
 
+// two-pass tiled format of the trajectory-batched path (tile.cu / tile_format.h), built lazily
+struct qp_tile_s;
+void qp_tile_free(qp_tile_s* t);
+
 constexpr int QP_DICT_MAX = 4096;       // table entries incl. the padding entry
 constexpr int QP_DICT_HASH_CAP = 16384; // open-addressing capacity used while building
 
@@ -168,6 +172,7 @@ struct qp_gen_s {
   int64_t lr_n = 0;
   // dense: pointers to the row-major operators
   const double2** d_dense_ops = nullptr;
+  qp_tile_s* tile = nullptr;   // two-pass tiled format for batched states (nullptr: not tried yet)
   // device copy of the effective per-operator coefficients (drift ops = 1), [n_ops][B]
   double2* d_coef = nullptr;
   size_t coef_elems = 0;

@@ -616,6 +616,7 @@ static void gen_free(qp_gen_t g) {
   cudaFree((void*)g->d_dense_ops);
   cudaFree(g->d_lr_terms);
   cudaFree(g->d_coef);
+  qp_tile_free(g->tile);
   delete g;
 }
 
@@ -1340,6 +1341,11 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     k_gemv_dense<EPI><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e);
     QP_LAUNCHED(ctx);
     return QP_OK;
+  }
+  if (batch >= 32) {  // two-pass tiled path (tile.cu): structured generators, batch a multiple of 32
+    bool handled = false;
+    QP_CHECK(qp_launch_tile(gen, EPI, coef_stride, x, batch, e, &handled));
+    if (handled) return QP_OK;
   }
   if (batch >= 16 && gen->n_dict > 0)  // dictionary available: warp per (row, 32 T trajectories)
     return launch_spmm_selld<EPI>(gen, coef_stride, x, batch, e);

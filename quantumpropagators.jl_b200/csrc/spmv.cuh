@@ -995,6 +995,11 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
   }
 }
 
+// two-pass tiled path for batched states (tile.cu); *handled = false: use the one-pass kernels
+int32_t qp_launch_tile(qp_gen_t gen, int epi, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e,
+                       bool* handled);
+int32_t qp_tile_info(qp_gen_t gen, int32_t* available, int32_t* S, int32_t* NH, int32_t* n_table, int64_t* entries);
+
 // host-side dispatcher (defined in sparse.cu)
 int32_t qp_launch_fused(qp_gen_t gen, int epi, int coef_stride, const double2* x, int64_t batch,
                         const EpiArgs& e);

@@ -31,6 +31,16 @@ class Context:
         self._lib = lib
         self._finalizer = weakref.finalize(self, lib.qp_ctx_destroy, h)
 
+    @classmethod
+    def borrowed(cls, handle, device: int):
+        """Wrap a context owned by someone else (the members of a ``qp_ens_t``): never destroyed here."""
+        self = cls.__new__(cls)
+        self.handle = handle
+        self.device = int(device)
+        self._lib = L.load()
+        self._finalizer = None
+        return self
+
     def sync(self):
         L.check(self._lib.qp_sync(self.handle), self.handle)
 
@@ -150,6 +160,16 @@ class DeviceGenerator:
         self.stored_bytes = sb.value  # matrix bytes one application actually streams
         self.n_dict = nd.value  # SELL-D: table entries (0 otherwise)
         self.code_bytes = cb.value
+
+    def tile_info(self):
+        """The two-pass tiled form used for batched states (``qp_gen_tile_info``; built on first
+        use): ``{"available", "split", "blocks", "n_table", "entries": {"A", "B", "other", "diag"}}``."""
+        av, sp_, nb, nt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        ent = np.zeros(4, dtype=np.int64)
+        L.check(self.ctx._lib.qp_gen_tile_info(self.handle, C.byref(av), C.byref(sp_), C.byref(nb), C.byref(nt), L.ptr(ent)),
+                self.ctx.handle)
+        return {"available": bool(av.value), "split": sp_.value, "blocks": nb.value, "n_table": nt.value,
+                "entries": dict(zip(("A", "B", "other", "diag"), (int(v) for v in ent)))}
 
     def _coeffs(self, coeffs):
         c = L.as_c128_array(coeffs if coeffs is not None else [])

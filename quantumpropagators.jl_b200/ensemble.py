@@ -13,11 +13,95 @@ tensors in the host-logic tests).
 
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
+from . import _lib as L
 from .controls import discretize_on_midpoints
 
-__all__ = ["shard_range", "trajectory_coefficients", "gather_blocks", "EnsembleChebyPropagator"]
+__all__ = ["shard_range", "trajectory_coefficients", "gather_blocks", "EnsembleChebyPropagator", "LibraryEnsemble"]
+
+
+class LibraryEnsemble:
+    """Handle of a ``qp_ens_t``: the ensemble communicator INSIDE ``libqprop_b200.so`` (NCCL over
+    NVLink, or device copies for fake ranks) -- what a Julia host uses, no torch.distributed.
+
+    ``LibraryEnsemble.local(devices)``: single process; one context per entry of ``devices`` (all
+    distinct: NCCL; all equal: "fake ranks" on one device).
+    ``LibraryEnsemble.from_rank(ctx, rank, world, id_bytes)``: one process per GPU; ``id_bytes`` are
+    the 128 bytes rank 0 got from ``LibraryEnsemble.unique_id()`` and handed to the other processes.
+    """
+
+    def __init__(self, handle, lib, contexts, ranks):
+        import weakref
+
+        self.handle = handle
+        self._lib = lib
+        self.contexts = contexts  # Context objects of the local members
+        self.ranks = ranks        # their world ranks
+        self._finalizer = weakref.finalize(self, lib.qp_ens_destroy, handle)
+        n, nl, tr = C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(lib.qp_ens_info(handle, C.byref(n), C.byref(nl), C.byref(tr)), None)
+        self.world, self.n_local, self.transport = n.value, nl.value, ("nccl" if tr.value else "device copies")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = L.load()
+        buf = (C.c_uint8 * 128)()
+        L.check(lib.qp_ens_unique_id(buf), None)
+        return bytes(buf)
+
+    @classmethod
+    def local(cls, devices):
+        from .device import Context
+
+        lib = L.load()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        L.check(lib.qp_ens_create(devs, len(devices), C.byref(h)), None)
+        ctxs, ranks = [], []
+        for i in range(len(devices)):
+            ch, rk = C.c_void_p(), C.c_int32()
+            L.check(lib.qp_ens_ctx(h, i, C.byref(ch), C.byref(rk)), None)
+            ctxs.append(Context.borrowed(ch, int(devices[i])))
+            ranks.append(rk.value)
+        return cls(h, lib, ctxs, ranks)
+
+    @classmethod
+    def from_rank(cls, ctx, rank, world, id_bytes=None):
+        lib = ctx._lib
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128)(*id_bytes) if id_bytes is not None else None
+        L.check(lib.qp_ens_create_rank(ctx.handle, int(rank), int(world), buf, C.byref(h)), ctx.handle)
+        return cls(h, lib, [ctx], [int(rank)])
+
+    def shard(self, n_total, rank):
+        b0, b1 = C.c_int64(), C.c_int64()
+        L.check(self._lib.qp_ens_shard(int(n_total), int(rank), self.world, C.byref(b0), C.byref(b1)), None)
+        return b0.value, b1.value
+
+    def gather_states(self, local_states, n_total, to_host=True, full_states=None):
+        """Final states of the whole ensemble.  ``local_states``: one DeviceState per local member.
+        Returns the (N, n_total) host array (``to_host``) and / or fills ``full_states`` (one
+        (N, n_total) DeviceState per local member)."""
+        arr = (C.c_void_p * len(local_states))(*[s.handle for s in local_states])
+        full = (C.c_void_p * len(full_states))(*[s.handle for s in full_states]) if full_states else None
+        out = np.empty((local_states[0].n, int(n_total)), dtype=np.complex128) if to_host else None
+        L.check(self._lib.qp_ens_gather_states(self.handle, arr, int(n_total), full, L.ptr(out) if to_host else None),
+                self.contexts[0].handle)
+        return out
+
+    def gather_expvals(self, local_values, n_total):
+        """``local_values``: one array (..., B_local) per local member; returns (..., n_total)."""
+        vals = [np.ascontiguousarray(v, dtype=np.complex128) for v in local_values]
+        lead = vals[0].shape[:-1]
+        n_values = int(np.prod(lead)) if lead else 1
+        flat = [v.reshape(n_values, v.shape[-1]) for v in vals]
+        ptrs = (C.c_void_p * len(flat))(*[v.ctypes.data for v in flat])
+        out = np.empty((n_values, int(n_total)), dtype=np.complex128)
+        L.check(self._lib.qp_ens_gather_expvals(self.handle, ptrs, n_values, int(n_total), L.ptr(out)), self.contexts[0].handle)
+        return out.reshape(lead + (int(n_total),))
 
 
 def shard_range(n_total: int, rank: int, world: int):
@@ -88,7 +172,7 @@ class EnsembleChebyPropagator:
     """
 
     def __init__(self, ops, controls, scales, psi0, tlist, E_min, E_max, ctx, rank=0, world=1,
-                 specrange_buffer=0.01, limit=1e-12, matrix_format="auto"):
+                 specrange_buffer=0.01, limit=1e-12, matrix_format="auto", library_ensemble=None):
         from .cheby import ChebyWrk
         from .device import DeviceGenerator, DeviceState
 
@@ -97,6 +181,11 @@ class EnsembleChebyPropagator:
         scales = np.asarray(scales, dtype=np.float64)
         self.B_total = scales.shape[-1]
         self.rank, self.world = rank, world
+        # gathers through the communicator inside libqprop_b200.so (qp_ens_*) when one is given,
+        # else through torch.distributed (kept as a cross-check of the library path)
+        self.lib_ens = library_ensemble
+        self.gather_backend = (f"libqprop_b200 qp_ens_* ({library_ensemble.transport})" if library_ensemble is not None
+                               else "torch.distributed")
         self.counts = [shard_range(self.B_total, r, world)[1] - shard_range(self.B_total, r, world)[0] for r in range(world)]
         self.b0, self.b1 = shard_range(self.B_total, rank, world)
         self.B_local = self.b1 - self.b0
@@ -132,6 +221,8 @@ class EnsembleChebyPropagator:
         """Final states of the WHOLE ensemble, (N, B_total), on every rank."""
         import torch
 
+        if self.lib_ens is not None:
+            return self.lib_ens.gather_states([self.state], self.B_total)
         if self.world == 1:
             return self.state.to_host().reshape(self.state.n, -1)
         self.ctx.sync()
@@ -143,6 +234,9 @@ class EnsembleChebyPropagator:
         import torch
 
         values = np.asarray(values)
+        if self.lib_ens is not None:
+            out = self.lib_ens.gather_expvals([values], self.B_total)
+            return out if np.iscomplexobj(values) else out.real
         if self.world == 1:
             return values
         t = torch.from_numpy(np.ascontiguousarray(values)).to(f"cuda:{self.ctx.device}")

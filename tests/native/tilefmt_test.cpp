@@ -1,0 +1,24 @@
+// Test hook for the host-side builder of the two-pass tile format (csrc/tile_format.h): builds the
+// format from a merged CSR matrix and applies it on the CPU exactly the way the kernels traverse it.
+// Compiled by tests/test_tile_format.py with g++ (no CUDA needed).
+#include "tile_format.h"
+
+extern "C" int tilefmt_apply(long long n, int n_ops, const unsigned* mptr, const unsigned* colop, const double* val,
+                             long long B, const double* u, const double* x, double* y, long long* stats, int S_forced) {
+  qptile::TileFormat f;
+  if (!qptile::build(f, n, n_ops, mptr, colop, val, S_forced)) return -1;
+  qptile::apply_host(f, B, u, x, y);
+  stats[0] = f.S;
+  stats[1] = f.NH;
+  stats[2] = f.WA;
+  stats[3] = f.WB;
+  stats[4] = (long long)f.table.size();
+  stats[5] = f.n_A;
+  stats[6] = f.n_B;
+  stats[7] = f.n_O;
+  stats[8] = f.n_diag;
+  stats[9] = f.imag_ops;
+  return 0;
+}
+
+extern "C" int tilefmt_choose_split(long long n) { return qptile::choose_split(n); }

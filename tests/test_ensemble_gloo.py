@@ -27,6 +27,23 @@ def test_shard_range_covers_everything():
         shard_range(4, 2, 2)
 
 
+def test_library_shard_matches_host_shard():
+    """qp_ens_shard (C ABI, no device needed) cuts the ensemble exactly like the host mirror."""
+    import ctypes as C
+
+    from qprop_b200 import _lib
+
+    lib = _lib.load()
+    for n, world in [(1024, 8), (5, 2), (7, 3), (3, 3), (10, 4), (0, 2)]:
+        for r in range(world):
+            b0, b1 = C.c_int64(), C.c_int64()
+            assert lib.qp_ens_shard(n, r, world, C.byref(b0), C.byref(b1)) == 0
+            if n >= world:
+                assert (b0.value, b1.value) == shard_range(n, r, world)
+    b0, b1 = C.c_int64(), C.c_int64()
+    assert lib.qp_ens_shard(4, 2, 2, C.byref(b0), C.byref(b1)) == _lib.QP_ERR_INVALID_ARG
+
+
 def test_trajectory_coefficients():
     tlist = np.linspace(0, 1, 6)
     u1 = lambda t: 1.0 + t  # noqa: E731

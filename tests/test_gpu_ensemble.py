@@ -42,6 +42,50 @@ def test_ensemble_single_gpu_vs_oracle(qp, ctx, B):
     assert ens.prop_step() is None  # past the end of the grid
 
 
+@pytest.mark.parametrize("n_fake,B", [(3, 10), (2, 64), (4, 5), (1, 7)])
+def test_library_ensemble_fake_ranks(qp, n_fake, B):
+    """The ensemble communicator inside libqprop_b200.so (qp_ens_*) with several "fake ranks" on ONE
+    device: ragged trajectory blocks, gather of final states (to the host and into device-resident
+    full states) and of per-trajectory numbers, against the whole ensemble on a single rank."""
+    from qprop_b200.ensemble import LibraryEnsemble
+
+    ens_comm = LibraryEnsemble.local([0] * n_fake)
+    assert ens_comm.world == n_fake and ens_comm.n_local == n_fake and ens_comm.transport == "device copies"
+    w = qp.workloads.config3_transmon(n_sites=4, levels=4, B=B, nt=5, dt=0.5)
+    bound = _envelope(w["ops"])
+    rng = np.random.default_rng(B)
+    N = w["ops"][0].shape[0]
+    psi0 = rng.standard_normal((N, B)) + 1j * rng.standard_normal((N, B))
+    psi0 /= np.linalg.norm(psi0, axis=0)
+    members = [EnsembleChebyPropagator(w["ops"], w["controls"], w["scales"], psi0, w["tlist"], -bound, bound,
+                                       ens_comm.contexts[i], rank=ens_comm.ranks[i], world=n_fake)
+               for i in range(n_fake)]
+    assert [m.B_local for m in members] == [ens_comm.shard(B, r)[1] - ens_comm.shard(B, r)[0] for r in range(n_fake)]
+    for m in members:
+        m.propagate()
+    states = ens_comm.gather_states([m.state for m in members], B)
+    ref = EnsembleChebyPropagator(w["ops"], w["controls"], w["scales"], psi0, w["tlist"], -bound, bound, ens_comm.contexts[0])
+    ref.propagate()
+    full = ref.state.to_host().reshape(N, B)
+    assert states.shape == (N, B) and np.linalg.norm(states - full) / np.linalg.norm(full) < 1e-13
+    # device-resident gather: every member receives the whole ensemble
+    fulls = [qp.DeviceState(ens_comm.contexts[i], N, B) for i in range(n_fake)]
+    ens_comm.gather_states([m.state for m in members], B, to_host=False, full_states=fulls)
+    for f in fulls:
+        assert np.array_equal(f.to_host().reshape(N, B), states)
+    # per-trajectory numbers: populations of |0> and norms, two values per trajectory
+    vals = [np.stack([np.abs(m.state.to_host().reshape(N, -1)[0]) ** 2, np.asarray(m.state.norm()).reshape(-1)]) for m in members]
+    got = ens_comm.gather_expvals(vals, B)
+    assert got.shape == (2, B)
+    assert np.allclose(got[0].real, np.abs(full[0]) ** 2, atol=1e-15) and np.allclose(got[1].real, 1.0, atol=1e-12)
+    # the propagator-level route (library_ensemble=...) on a single rank
+    solo = EnsembleChebyPropagator(w["ops"], w["controls"], w["scales"], psi0, w["tlist"], -bound, bound, ens_comm.contexts[0],
+                                   library_ensemble=LibraryEnsemble.from_rank(ens_comm.contexts[0], 0, 1))
+    solo.propagate()
+    assert np.array_equal(solo.gather_states(), full)
+    assert np.allclose(solo.gather_expvals(np.asarray(solo.state.norm())), 1.0, atol=1e-12)
+
+
 def test_ensemble_two_ranks_nccl(qp, ctx):
     import torch
 

@@ -377,6 +377,106 @@ def test_cheby_batched_per_trajectory(qp, ctx, B):
         assert rel(out[:, b], ref[:, b]) < RTOL
 
 
+# ---------------------------------------------------------------------------------------
+# two-pass tiled path for batched states (csrc/tile.cu): batch a multiple of 32
+# ---------------------------------------------------------------------------------------
+
+
+def _dense_apply(ops, u, X):
+    """sum_l u[l, b] (H_l X)[:, b]"""
+    return sum(np.asarray(u[l])[None, :] * (ops[l] @ X) for l in range(len(ops)))
+
+
+@pytest.mark.parametrize("sites,levels,B", [(2, 4, 32), (3, 4, 64), (4, 4, 96), (4, 3, 32), (4, 4, 256)])
+def test_tiled_batched_operator_verbs(qp, ctx, sites, levels, B):
+    """mul! (alpha, beta), the fused expectation value and 3-argument dot on the tiled path against
+    NumPy, for splits S x N/S = 4x4 ... 16x16 and 1 ... 8 trajectory chunks; then the same generator
+    with other batch sizes (the completion counters start a new epoch)."""
+    rng = np.random.default_rng(sites * 100 + B)
+    H0, H1, H2 = qp.workloads.transmon_chain(sites, levels)
+    N = H0.shape[0]
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    info = gen.tile_info()
+    if levels == 4:
+        assert info["available"] and info["split"] * info["blocks"] == N and info["entries"]["other"] > 0
+    ops = [H0, H1, H2]
+    for Bk in (B, 32, B):
+        X = rand_state(rng, N, Bk)
+        Y0 = rand_state(rng, N, Bk)
+        c = [0.3 - 0.2j, -1.1 + 0.4j]
+        alpha, beta = 0.7 - 0.1j, -0.4 + 0.9j
+        x = qp.DeviceState.from_host(ctx, X)
+        y = qp.DeviceState.from_host(ctx, Y0)
+        gen.mul(y, x, c, alpha, beta)
+        u = np.array([[1.0] * Bk, [c[0]] * Bk, [c[1]] * Bk])
+        want = beta * Y0 + alpha * _dense_apply(ops, u, X)
+        assert np.max(np.abs(y.to_host() - want)) < 1e-13 * np.max(np.abs(want)) * N ** 0.5
+        gen.mul(y, x, c, 1.0, 0.0)
+        assert np.max(np.abs(y.to_host() - _dense_apply(ops, u, X))) < 1e-13 * N ** 0.5
+        ev = gen.expval(x, c)
+        assert np.max(np.abs(ev - np.einsum("nb,nb->b", X.conj(), _dense_apply(ops, u, X)))) < 1e-12
+        d = gen.dot(y, x, c)
+        assert np.max(np.abs(d - np.einsum("nb,nb->b", y.to_host().conj(), _dense_apply(ops, u, X)))) < 1e-11
+
+
+@pytest.mark.parametrize("B", [64, 160])
+@pytest.mark.parametrize("backward", [False, True])
+def test_tiled_cheby_per_trajectory(qp, ctx, B, backward):
+    """Ensemble on the tiled path: per-trajectory amplitudes, all Chebyshev epilogues (FIRST / MID /
+    LAST), forward and backward, the normalization check, against the oracle trajectory by trajectory."""
+    rng = np.random.default_rng(5 + B)
+    w = qp.workloads.config3_transmon(n_sites=4, levels=4, B=B, nt=6, dt=0.5)
+    H0, H1, H2 = w["ops"]
+    tl = w["tlist"]
+    dt = (tl[1] - tl[0]) * (-1 if backward else 1)
+    psi0 = rand_state(rng, H0.shape[0], B)
+    scales = w["scales"]
+    bound = float((abs(H0) + 0.1 * abs(H1) + 0.1 * abs(H2)).sum(axis=1).max())
+    Delta, E_min = 2 * bound, -bound
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    assert gen.tile_info()["available"]
+    st = qp.DeviceState.from_host(ctx, psi0)
+    wrk = qp.ChebyWrk(st, gen, Delta, E_min, abs(dt))
+    assert wrk.n_coeffs > 3
+    mids = O.get_tlist_midpoints(tl)
+    ref = psi0.copy()
+    owrk = O.ChebyWrk(ref[:, 0].copy(), Delta, E_min, abs(dt))
+    for k in range(len(tl) - 1):
+        u = np.array([[w["controls"][0](mids[k]) * s for s in scales], [w["controls"][1](mids[k]) * s for s in scales]])
+        qp.cheby_(st, None, dt, wrk, coeffs=u, per_trajectory=True, check_normalization=(k == 0))
+        for b in range(0, B, 7):
+            Hb = O.Operator([H0, H1, H2], [u[0, b], u[1, b]])
+            col = ref[:, b].copy()
+            O.cheby_inplace(col, Hb, dt, owrk)
+            ref[:, b] = col
+    out = st.to_host()
+    for b in range(0, B, 7):
+        assert rel(out[:, b], ref[:, b]) < RTOL
+    assert np.max(np.abs(st.norm() - 1)) < 1e-12
+
+
+def test_tiled_real_operators_and_unqualified_generators(qp, ctx):
+    """TFIM (real operators, two diagonals, XOR couplings) on the tiled path; an unstructured random
+    generator does not qualify and silently uses the one-pass kernels -- same results."""
+    rng = np.random.default_rng(8)
+    H0, H1, H2 = qp.workloads.tfim_chain(8)
+    N, B = 256, 64
+    X = rand_state(rng, N, B)
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    info = gen.tile_info()
+    assert info["available"] and info["entries"]["other"] == 0 and info["entries"]["diag"] == N
+    x = qp.DeviceState.from_host(ctx, X)
+    y = x.similar()
+    gen.mul(y, x, [0.6, -0.3])
+    u = np.array([[1.0] * B, [0.6] * B, [-0.3] * B])
+    assert np.max(np.abs(y.to_host() - _dense_apply([H0, H1, H2], u, X))) < 1e-12
+    R = rand_sparse(rng, 256, 0.1)
+    g2 = qp.DeviceGenerator(ctx, [R], 0)
+    assert not g2.tile_info()["available"]
+    g2.mul(y, x, [])
+    assert np.max(np.abs(y.to_host() - R @ X)) < 1e-12
+
+
 def test_cheby_check_normalization_and_errors(qp, ctx):
     rng = np.random.default_rng(4)
     n = 200
