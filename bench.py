@@ -613,17 +613,30 @@ def run_ensemble(args, qp, torch, ctx, rank, world, local_rank, barrier, max_ove
     """BASELINE configs[2]: B trajectories (varied control amplitudes) of the N = 2^16 transmon chain,
     sharded by contiguous trajectory blocks over the ranks; no collective inside the time loop, one
     gather of expectation values and one of the final states at the end."""
-    from qprop_b200.ensemble import EnsembleChebyPropagator
+    from qprop_b200.ensemble import EnsembleChebyPropagator, LibraryEnsemble
 
     B, k = args.ensemble_B, args.ensemble_steps
     if B < world:
         return None
+    # the communicator INSIDE libqprop_b200.so (qp_ens_*: NCCL over NVLink); the launcher's process
+    # group only hands the 128-byte id from rank 0 to the other ranks
+    ident = None
+    if world > 1:
+        import torch.distributed as dist
+
+        t_id = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t_id = torch.tensor(list(LibraryEnsemble.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t_id, 0)
+        ident = bytes(t_id.cpu().tolist())
+    comm = LibraryEnsemble.from_rank(ctx, rank, world, ident)
     w = qp.workloads.config3_transmon(n_sites=8, levels=4, B=B, nt=201, dt=0.5)
     H0, H1, H2 = w["ops"]
     N = H0.shape[0]
     bound = float((abs(H0) + 0.1 * abs(H1) + 0.1 * abs(H2)).sum(axis=1).max())
     ens = EnsembleChebyPropagator(w["ops"], w["controls"], w["scales"], w["psi0"], w["tlist"], -bound, bound, ctx,
-                                  rank=rank, world=world)
+                                  rank=rank, world=world, library_ensemble=comm)
+    tile = ens.gen.tile_info()
     n_grid = len(w["tlist"]) - 1
     for _ in range(2):
         ens.prop_step()
@@ -642,11 +655,15 @@ def run_ensemble(args, qp, torch, ctx, rank, world, local_rank, barrier, max_ove
     barrier()
     t_exp = time.perf_counter() - t0
     t0 = time.perf_counter()
-    full = ens.gather_states()
+    # final states: gathered over NVLink into a device-resident (N, B) state on every rank
+    full = qp.DeviceState(ctx, N, B) if world > 1 else None
+    if world > 1:
+        comm.gather_states([ens.state], B, to_host=False, full_states=[full])
+    ctx.sync()
     barrier()
     t_states = time.perf_counter() - t0
     gathered = int(np.asarray(pops).shape[-1])
-    n_states = int(full.shape[-1]) if hasattr(full, "shape") else None
+    n_states = B if world > 1 else ens.B_local
     del full
     med, mn, mx, t_exp, t_states = max_over_ranks([t["median_ms"], t["min_ms"], t["max_ms"], t_exp, t_states])
     peak, _ = measured_peak()
@@ -658,11 +675,15 @@ def run_ensemble(args, qp, torch, ctx, rank, world, local_rank, barrier, max_ove
         "scaling": "strong", "n_gpus": world, "steps": k, "blocks": t["n_blocks"], "ms_per_step": med / k,
         "ms_per_step_min": mn / k, "ms_per_step_max": mx / k,
         "workload": f"transmon chain 8x4 levels (N=2^16), B={B} trajectories with their own control amplitudes, B_local={ens.B_local}, "
-                    f"n_coeffs={n_c}, matrix_format={ens.gen.format}",
+                    f"n_coeffs={n_c}",
+        "kernel": (f"k_spmm_tile<CHEB_MID,3> (two-pass tiled, split {tile['split']} x {tile['blocks']}, {tile['n_table']} table entries; "
+                   f"entries per class {tile['entries']})" if tile["available"] and ens.B_local % 32 == 0 else
+                   "k_spmm_selld_pairs / k_spmm_selld (one-pass dictionary kernels)"),
         "achieved_gbs_per_gpu": per_gpu, "roofline_frac_per_gpu": per_gpu / peak,
         "bytes_per_term_per_gpu": term_bytes, "ms_per_term": med / k / (n_c - 1),
         "gather": {"expvals_s": t_exp, "states_s": t_states, "trajectories_gathered": gathered, "states_gathered": n_states,
-                   "states_bytes": 16 * N * B, "backend": getattr(ens, "gather_backend", "torch.distributed (NCCL)")},
+                   "states_bytes": 16 * N * B if world > 1 else 0, "backend": ens.gather_backend,
+                   "note": "expvals: host numbers -> every rank; states: device-resident (N, B) on every rank (skipped at 1 GPU)"},
         "norm_dev_max": float(np.max(np.abs(np.asarray(pops) - 1))),
     }
     del ens

@@ -86,7 +86,10 @@ int32_t qp_ctx_launch_count(qp_ctx_t ctx, int64_t* n_launches);
 
 /* Timers under the reference's TimerOutputs labels (src/timings.jl; labels
  * "prop_step!", "matrix-vector product", "arnoldi!", src/cheby.jl:175,
- * src/arnoldi.jl:81, src/cheby_propagator.jl:349).  CUDA-event based, off by default. */
+ * src/arnoldi.jl:81, src/cheby_propagator.jl:349 -- CUDA-event based -- and the host-side
+ * sections of newton!, "diagonalize_hessenberg_matrix", "get Leja points",
+ * "get Newton coeffs", "evaluate polynomial", src/newton.jl:297-343 -- wall clock).
+ * Off by default. */
 int32_t qp_timer_enable(qp_ctx_t ctx, int32_t on);
 int32_t qp_timer_get(qp_ctx_t ctx, const char* label, int64_t* ncalls, double* seconds);
 int32_t qp_timer_reset(qp_ctx_t ctx);
@@ -264,6 +267,12 @@ typedef void (*qp_newton_func_t)(const qp_c128* z, qp_c128* f_of_z, void* user);
 int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, const qp_c128* op_coeffs, double dt,
                        int32_t func_id, qp_newton_func_t func, void* user, double norm_min, double relerr,
                        int32_t max_restarts, int32_t* restarts_out);
+
+/* NewtonWrk bookkeeping after the last qp_newton_step on this workspace (the reference sets
+ * wrk.n_a, wrk.n_leja, wrk.radius and fills wrk.a, wrk.leja; src/newton.jl:381-383): counts,
+ * radius and up to `capacity` coefficients / Leja points (a, leja may be NULL). */
+int32_t qp_newton_last(qp_krylov_t K, int32_t* n_a, int32_t* n_leja, double* radius, qp_c128* a, qp_c128* leja,
+                       int32_t capacity);
 
 /* The host-side pieces of newton! on their own (pure host code, no device needed):
  *   diagonalize_hessenberg_matrix(Hess, m; accumulate)   src/arnoldi.jl:143-170

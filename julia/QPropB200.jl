@@ -33,6 +33,7 @@ using QuantumPropagators.Arnoldi: diagonalize_hessenberg_matrix
 using QuantumPropagators.Newton: extend_leja!, extend_newton_coeffs!, leja_radius
 
 export ChebyB200, NewtonB200, DeviceState, to_device, to_host, propagate_on_device!, expval
+export EnsembleB200, BatchedState, ensemble_propagate!, gather_states, gather_expvals, device_specrange
 
 const libqprop = get(ENV, "QPROP_B200_LIB", joinpath(@__DIR__, "..", "quantumpropagators.jl_b200",
                                                       "csrc", "libqprop_b200.so"))
@@ -64,6 +65,8 @@ mutable struct Context
         ctx = new(h[])
         finalizer(c -> ccall((:qp_ctx_destroy, libqprop), Int32, (Ptr{Cvoid},), c.handle), ctx)
     end
+    # a context owned by someone else (the members of an ensemble): no finalizer
+    Context(handle::Ptr{Cvoid}, owned::Bool) = new(handle)
 end
 
 const _default_ctx = Ref{Union{Nothing,Context}}(nothing)
@@ -278,8 +281,21 @@ function init_prop(state, generator, tlist, ::Val{:ChebyB200};
     end
     # spectral envelope exactly as the reference (specrange on host operators; :arnoldi can be
     # redirected to the device by passing DeviceState start vectors)
-    E_min, E_max = cheby_get_spectral_envelope(generator, tlist, control_ranges, specrange_method;
-                                               specrange_kwargs...)
+    dstate = state isa DeviceState ? (inplace ? copy(state) : state) : to_device(Vector{ComplexF64}(state))
+    ctx = dstate.ctx
+    devgen = DeviceGenerator(ctx, G)
+    if specrange_method == :arnoldi_device
+        # the envelope of the reference (src/cheby_propagator.jl:331-345: extremal control values)
+        # with the Arnoldi runs on the device operators that were just uploaded
+        lo = ComplexF64[control_ranges[c][1] for c in controls]
+        hi = ComplexF64[control_ranges[c][2] for c in controls]
+        r1 = device_specrange(devgen, lo, ctx, dstate.n; specrange_kwargs...)
+        r2 = device_specrange(devgen, hi, ctx, dstate.n; specrange_kwargs...)
+        E_min, E_max = min(r1[1], r2[1]), max(r1[2], r2[2])
+    else
+        E_min, E_max = cheby_get_spectral_envelope(generator, tlist, control_ranges, specrange_method;
+                                                   specrange_kwargs...)
+    end
     Δ = E_max - E_min
     @assert Δ > 0.0
     δ = specrange_buffer * Δ
@@ -287,9 +303,6 @@ function init_prop(state, generator, tlist, ::Val{:ChebyB200};
     Δ += δ
     dt = _get_uniform_dt(tlist; tol=uniform_dt_tolerance, warn=true)
     isnothing(dt) && error("Chebychev propagation only works on a uniform time grid")
-    dstate = state isa DeviceState ? (inplace ? copy(state) : state) : to_device(Vector{ComplexF64}(state))
-    ctx = dstate.ctx
-    devgen = DeviceGenerator(ctx, G)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:qp_cheby_create, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
                 devgen.handle, dstate.handle, h), ctx.handle)
@@ -485,6 +498,180 @@ function prop_step!(p::NewtonB200Propagator)
     end
     _pwc_advance_time!(p)
     return p.state
+end
+
+# ---------------------------------------------------------------------------------------
+# Device spectral range (SURVEY.md §8f-2): `specrange(H; method=:arnoldi)` (reference
+# src/specrad.jl:88-112, 170-220) with the Krylov vectors on the GPU -- the Ritz values of an
+# m-step Arnoldi run started from a random state, enlarged by the usual buffer.  Use it through
+# `init_prop(...; method=ChebyB200, specrange_method=:arnoldi_device)`; the host route of the
+# reference (`cheby_get_spectral_envelope` on SparseMatrixCSC operators) stays the default.
+# ---------------------------------------------------------------------------------------
+function device_specrange(devgen::DeviceGenerator, coeffs::Vector{ComplexF64}, ctx::Context, n::Integer;
+                          m_max::Integer=60, enlarge::Bool=true, norm_min=1e-15)
+    Ψ = randn(ComplexF64, n)
+    v = to_device(Ψ / norm(Ψ); ctx=ctx)
+    m = min(m_max, n - 1)
+    K = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_krylov_create, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}),
+                devgen.handle, v.handle, m, K), ctx.handle)
+    Hess = zeros(ComplexF64, m + 1, m + 1)
+    m_out = Ref{Int32}(0)
+    try
+        check(ccall((:qp_arnoldi, libqprop), Int32,
+                    (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Int32, Float64, Int32, Float64, Ptr{ComplexF64}, Int32, Ref{Int32}),
+                    K[], coeffs, v.handle, m, 1.0, false, norm_min, Hess, size(Hess, 1), m_out), ctx.handle)
+    finally
+        ccall((:qp_krylov_destroy, libqprop), Int32, (Ptr{Cvoid},), K[])
+    end
+    mm = Int(m_out[])
+    ritz = sort(real.(eigvals(Hess[1:mm, 1:mm])))
+    E_min, E_max = ritz[1], ritz[end]
+    if enlarge && mm > 1                      # src/specrad.jl:103-107
+        E_min -= ritz[2] - ritz[1]
+        E_max += ritz[end] - ritz[end-1]
+    end
+    return E_min, E_max
+end
+
+# ---------------------------------------------------------------------------------------
+# Ensembles of trajectories on all GPUs of a box (C ABI group `qp_ens_*`, SURVEY.md §8b / §8e):
+# trajectory b scales control l by `scales[l, b]`; the trajectories are cut into contiguous
+# blocks, one per GPU; every GPU steps its [N][B_local] batched state with ONE qp_cheby_step per
+# time interval (per-trajectory coefficients); nothing is communicated inside the time loop, and
+# the final gathers run over NCCL/NVLink inside the library.  The shared spectral envelope is
+# the `control_ranges` hook of the reference (src/cheby_propagator.jl:59-66) evaluated over the
+# whole ensemble.
+# ---------------------------------------------------------------------------------------
+mutable struct BatchedState
+    ctx::Context
+    handle::Ptr{Cvoid}
+    n::Int64
+    batch::Int64
+    function BatchedState(ctx::Context, n::Integer, batch::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qp_state_create, libqprop), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    ctx.handle, n, batch, h), ctx.handle)
+        st = new(ctx, h[], n, batch)
+        finalizer(s -> ccall((:qp_state_destroy, libqprop), Int32, (Ptr{Cvoid},), s.handle), st)
+    end
+end
+
+# host layout of a batched state: Matrix{ComplexF64} of size (batch, N) -- trajectory index fastest,
+# i.e. the library's [N][B] row-major layout seen by column-major Julia
+function upload!(st::BatchedState, Ψ::Matrix{ComplexF64})
+    @assert size(Ψ) == (st.batch, st.n)
+    check(ccall((:qp_state_upload, libqprop), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64, Int64),
+                st.handle, Ψ, 0, st.batch), st.ctx.handle)
+    return st
+end
+
+mutable struct EnsembleMember
+    ctx::Context
+    rank::Int
+    b0::Int
+    b1::Int
+    gen::DeviceGenerator
+    state::BatchedState
+    wrk::Ptr{Cvoid}
+end
+
+mutable struct EnsembleB200
+    handle::Ptr{Cvoid}
+    members::Vector{EnsembleMember}
+    n_total::Int
+    tlist::Vector{Float64}
+    coeffs::Array{ComplexF64,3}     # (B_total, L, nt-1): u[b, l, n] = scales[l, b] * ε_l(t_n) on the midpoints
+    n::Int
+    dt::Float64
+end
+
+"""
+    EnsembleB200(devices, H::Generator, scales, Ψ₀, tlist; E_min, E_max, specrange_buffer=0.01, limit=1e-12)
+
+`devices`: CUDA device indices (all distinct: NCCL; all equal: several ranks on one GPU).
+`scales`: `L × B_total` matrix of amplitude scales.  `Ψ₀`: `Vector` (shared) or `B_total × N` matrix.
+"""
+function EnsembleB200(devices::Vector{<:Integer}, H::Generator, scales::Matrix{Float64}, Ψ₀, tlist;
+                      E_min::Float64, E_max::Float64, specrange_buffer=0.01, limit=1e-12)
+    tlist = convert(Vector{Float64}, tlist)
+    controls = get_controls(H)
+    L, B = size(scales)
+    @assert L == length(controls)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qp_ens_create, libqprop), Int32, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                Int32.(devices), length(devices), h))
+    mid = [QuantumPropagators.Controls.discretize_on_midpoints(c, tlist) for c in controls]
+    coeffs = [ComplexF64(scales[l, b] * mid[l][n]) for b = 1:B, l = 1:L, n = 1:(length(tlist)-1)]
+    Δ = E_max - E_min
+    δ = specrange_buffer * Δ
+    dt = tlist[2] - tlist[1]
+    a = cheby_coeffs(Δ + δ, dt; limit=limit)
+    G = _pwc_get_max_genop(H, controls, tlist)
+    N = size(G.ops[1], 1)
+    members = EnsembleMember[]
+    for i = 0:(length(devices)-1)
+        ch, rk = Ref{Ptr{Cvoid}}(C_NULL), Ref{Int32}(0)
+        check(ccall((:qp_ens_ctx, libqprop), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ref{Int32}), h[], i, ch, rk))
+        ctx = Context(ch[], false)             # borrowed: owned by the ensemble
+        b0, b1 = Ref{Int64}(0), Ref{Int64}(0)
+        check(ccall((:qp_ens_shard, libqprop), Int32, (Int64, Int32, Int32, Ref{Int64}, Ref{Int64}),
+                    B, rk[], length(devices), b0, b1))
+        gen = DeviceGenerator(ctx, G)
+        st = BatchedState(ctx, N, b1[] - b0[])
+        local_Ψ = Ψ₀ isa AbstractVector ? repeat(transpose(ComplexF64.(Ψ₀)), b1[] - b0[], 1) :
+                  Matrix{ComplexF64}(Ψ₀[(b0[]+1):b1[], :])
+        upload!(st, local_Ψ)
+        w = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qp_cheby_create, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), gen.handle, st.handle, w), ctx.handle)
+        check(ccall((:qp_cheby_set_coeffs, libqprop), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Float64, Float64, Float64),
+                    w[], a, length(a), Δ + δ, E_min - δ / 2, abs(dt), limit), ctx.handle)
+        push!(members, EnsembleMember(ctx, rk[], b0[], b1[], gen, st, w[]))
+    end
+    ens = EnsembleB200(h[], members, B, tlist, coeffs, 1, dt)
+    finalizer(ens) do e
+        foreach(m -> ccall((:qp_cheby_destroy, libqprop), Int32, (Ptr{Cvoid},), m.wrk), e.members)
+        ccall((:qp_ens_destroy, libqprop), Int32, (Ptr{Cvoid},), e.handle)
+    end
+    return ens
+end
+
+"One `prop_step!` of every trajectory: one batched `qp_cheby_step` per GPU, enqueued back to back (the GPUs run concurrently)."
+function prop_step!(ens::EnsembleB200)
+    (0 < ens.n < length(ens.tlist)) || return nothing
+    for m in ens.members
+        c = ens.coeffs[(m.b0+1):m.b1, :, ens.n]                 # (B_local, L): [l][b] with b fastest
+        check(ccall((:qp_cheby_step, libqprop), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Float64, Int32),
+                    m.wrk, m.state.handle, c, 1, ens.dt, 0), m.ctx.handle)
+    end
+    ens.n += 1
+    return ens
+end
+
+function ensemble_propagate!(ens::EnsembleB200)
+    while !isnothing(prop_step!(ens)) end
+    return ens
+end
+
+"Final states of the whole ensemble as a `B_total × N` matrix (NCCL gather inside the library)."
+function gather_states(ens::EnsembleB200)
+    N = ens.members[1].state.n
+    out = Matrix{ComplexF64}(undef, ens.n_total, N)
+    hs = [m.state.handle for m in ens.members]
+    check(ccall((:qp_ens_gather_states, libqprop), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int64, Ptr{Ptr{Cvoid}}, Ptr{ComplexF64}),
+                ens.handle, hs, ens.n_total, C_NULL, out), ens.members[1].ctx.handle)
+    return out
+end
+
+"Per-trajectory numbers: `values[i]` is member i's `B_local × n_values` matrix; returns `B_total × n_values`."
+function gather_expvals(ens::EnsembleB200, values::Vector{Matrix{ComplexF64}})
+    nv = size(values[1], 2)
+    out = Matrix{ComplexF64}(undef, ens.n_total, nv)
+    ptrs = [pointer(v) for v in values]
+    GC.@preserve values check(ccall((:qp_ens_gather_expvals, libqprop), Int32,
+                                    (Ptr{Cvoid}, Ptr{Ptr{ComplexF64}}, Int32, Int64, Ptr{ComplexF64}),
+                                    ens.handle, ptrs, nv, ens.n_total, out), ens.members[1].ctx.handle)
+    return out
 end
 
 end # module

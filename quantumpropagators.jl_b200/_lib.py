@@ -116,6 +116,7 @@ SIGNATURES = {
     "qp_arnoldi_extend": (_i32, [_vp, _vp, _i32, _f64, _f64, _vp, _i32, _P(_i32)]),
     "qp_krylov_combine": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32]),
     "qp_newton_step": (_i32, [_vp, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _f64, _f64, _i32, _P(_i32)]),
+    "qp_newton_last": (_i32, [_vp, _P(_i32), _P(_i32), _P(_f64), _vp, _vp, _i32]),
     "qp_diagonalize_hessenberg": (_i32, [_vp, _i32, _i32, _i32, _vp, _P(_i32)]),
     "qp_extend_leja": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32]),
     "qp_extend_newton_coeffs": (_i32, [_vp, _i32, _P(_i32), _vp, _i32, _i32, _vp, _vp, _f64]),

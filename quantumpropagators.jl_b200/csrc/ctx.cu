@@ -87,8 +87,16 @@ extern "C" int32_t qp_ctx_create(int32_t device, qp_ctx_t* out) {
   return QP_OK;
 }
 
+void qp_ctx_release(qp_ctx_t ctx) {
+  if (--ctx->refs == 0 && ctx->destroy_requested) qp_ctx_destroy(ctx);
+}
+
 extern "C" int32_t qp_ctx_destroy(qp_ctx_t ctx) {
   if (!ctx) return QP_OK;
+  if (ctx->refs > 0) {  // objects still live on it: freed with the last of them
+    ctx->destroy_requested = true;
+    return QP_OK;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_red) cudaFree(ctx->d_red);
@@ -322,7 +330,7 @@ static inline int grid_for(qp_ctx_t ctx, int64_t total, int block) {
 }
 
 static int32_t same_shape(qp_state_t a, qp_state_t b, const char* what) {
-  if (!a || !b) return qp_fail(a ? a->ctx : nullptr, QP_ERR_INVALID_ARG, "%s: null state", what);
+  if (!a || !b) return qp_fail(a ? (qp_ctx_t)a->ctx : (qp_ctx_t) nullptr, QP_ERR_INVALID_ARG, "%s: null state", what);
   QP_REQUIRE(a->ctx, a->ctx == b->ctx, "%s: states belong to different contexts", what);
   QP_REQUIRE(a->ctx, a->n == b->n && a->batch == b->batch,
              "%s: shape mismatch (%lld x %lld) vs (%lld x %lld)", what, (long long)a->n,

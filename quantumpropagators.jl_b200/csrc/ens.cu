@@ -78,7 +78,7 @@ NcclApi* nccl_api() {
 struct qp_ens_s {
   int n_ranks = 0;                 // world size
   std::vector<int> local_rank;     // world rank of local member i
-  std::vector<qp_ctx_t> ctx;       // context of local member i
+  std::vector<CtxHandle> ctx;      // context of local member i (holds a reference)
   std::vector<bool> own_ctx;       // created by qp_ens_create (destroyed with the ensemble)
   std::vector<ncclComm_t> comm;    // empty: local-copy transport
   bool use_nccl = false;
@@ -114,11 +114,12 @@ extern "C" int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens
     qp_ctx_t c = nullptr;
     int32_t rc = qp_ctx_create(devices[i], &c);
     if (rc != QP_OK) {
-      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);
+      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);  /* deferred until E releases them */
       delete E;
       return rc;
     }
-    E->ctx.push_back(c);
+    E->ctx.emplace_back();
+    E->ctx.back() = c;
     E->own_ctx.push_back(true);
     E->local_rank.push_back(i);
   }
@@ -128,7 +129,7 @@ extern "C" int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens
     NcclApi* api = nccl_api();
     if (!api) {
       int32_t rc = qp_fail(E->ctx[0], QP_ERR_UNSUPPORTED, "qp_ens_create: NCCL is not available (libnccl.so.2 could not be loaded)");
-      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);
+      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);  /* deferred until E releases them */
       delete E;
       return rc;
     }
@@ -137,7 +138,7 @@ extern "C" int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens
     ncclResult_t r = api->CommInitAll(E->comm.data(), n_ranks, devs.data());
     if (r != ncclSuccess) {
       int32_t rc = qp_fail(E->ctx[0], QP_ERR_CUDA, "ncclCommInitAll failed: %s", api->GetErrorString(r));
-      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);
+      for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);  /* deferred until E releases them */
       delete E;
       return rc;
     }
@@ -145,7 +146,7 @@ extern "C" int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens
   } else if (n_ranks > 1 && !distinct) {
     for (int i = 1; i < n_ranks; ++i)
       if (devices[i] != devices[0]) {
-        for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);
+        for (qp_ctx_t cc : E->ctx) qp_ctx_destroy(cc);  /* deferred until E releases them */
         delete E;
         return qp_fail(nullptr, QP_ERR_UNSUPPORTED,
                        "qp_ens_create: ranks must sit on distinct devices (NCCL) or all on the same device (fake ranks)");
@@ -174,7 +175,8 @@ extern "C" int32_t qp_ens_create_rank(qp_ctx_t ctx, int32_t rank, int32_t n_rank
   QP_CHECK(qp_ctx_bind(ctx));
   qp_ens_t E = new qp_ens_s();
   E->n_ranks = n_ranks;
-  E->ctx.push_back(ctx);
+  E->ctx.emplace_back();
+  E->ctx.back() = ctx;
   E->own_ctx.push_back(false);
   E->local_rank.push_back(rank);
   E->d_stage.assign(1, nullptr);
@@ -210,7 +212,7 @@ extern "C" int32_t qp_ens_destroy(qp_ens_t E) {
     if (NcclApi* api = nccl_api())
       for (ncclComm_t c : E->comm) api->CommDestroy(c);
   for (size_t i = 0; i < E->ctx.size(); ++i)
-    if (E->own_ctx[i]) qp_ctx_destroy(E->ctx[i]);
+    if (E->own_ctx[i]) qp_ctx_destroy(E->ctx[i]);  // deferred while objects (or this ensemble) still hold it
   delete E;
   return QP_OK;
 }

@@ -9,6 +9,7 @@
 // hosts that want to keep this step themselves (julia/QPropB200.jl does, reusing the
 // reference's own functions).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -197,6 +198,21 @@ static bool extend_newton_coeffs(std::vector<cplx>& a, int& n_a, const std::vect
   return true;
 }
 
+// host-side sections of newton! under the reference's TimerOutputs labels (src/newton.jl:297-343;
+// test/test_timings.jl:8-39 is the contract): wall clock, they run between two device phases
+struct HostTimer {
+  qp_ctx_t ctx;
+  const char* label;
+  std::chrono::steady_clock::time_point t0;
+  HostTimer(qp_ctx_t c, const char* l) : ctx(c), label(l), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() {
+    if (!ctx->timers_on) return;
+    qp_timer_rec& r = ctx->timers[label];
+    r.ncalls += 1;
+    r.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
 extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, const qp_c128* op_coeffs, double dt,
                                   int32_t func_id, qp_newton_func_t func_cb, void* user, double norm_min,
                                   double relerr, int32_t max_restarts, int32_t* restarts_out) {
@@ -234,8 +250,11 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
       QP_CHECK(qp_scal(psi, qp_c128{f.real(), f.imag()}));
       break;
     }
-    if (!ritz_accumulated(hess, ld, m, ritz))
-      return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: QR iteration for the Ritz values did not converge");
+    {
+      HostTimer t(ctx, "diagonalize_hessenberg_matrix");  // :297-299
+      if (!ritz_accumulated(hess, ld, m, ritz))
+        return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: QR iteration for the Ritz values did not converge");
+    }
     if (s == 0) {  // leja_radius, :67-70
       double mx = 0.0;
       for (const cplx& z : ritz) mx = std::max(mx, std::abs(z));
@@ -243,9 +262,15 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
     }
     QP_REQUIRE(ctx, radius > 0.0, "qp_newton_step: Leja radius must be positive");
     const int n_s = n_leja;
-    extend_leja(leja, n_leja, ritz, m);
-    if (!extend_newton_coeffs(a, n_a, leja, func, n_leja, radius))
-      return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: Divided differences too small");
+    {
+      HostTimer t(ctx, "get Leja points");  // :307-311
+      extend_leja(leja, n_leja, ritz, m);
+    }
+    {
+      HostTimer t(ctx, "get Newton coeffs");  // :314-317
+      if (!extend_newton_coeffs(a, n_a, leja, func, n_leja, radius))
+        return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: Divided differences too small");
+    }
 
     // Newton polynomial in the extended (m+1) x (m+1) Hessenberg block (:330-343)
     auto Hm = [&](int i, int j) { return hess[(size_t)j * ld + i]; };
@@ -257,12 +282,15 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
       }
       std::swap(R, R2);
     };
-    std::fill(R.begin(), R.end(), cplx(0.0, 0.0));
-    R[0] = beta;
-    for (int i = 0; i <= m; ++i) P[i] = a[n_s] * R[i];
-    for (int k = 1; k < m; ++k) {
-      step_R(leja[n_s + k - 1]);
-      for (int i = 0; i <= m; ++i) P[i] += a[n_s + k] * R[i];
+    {
+      HostTimer t(ctx, "evaluate polynomial");  // :330-343
+      std::fill(R.begin(), R.end(), cplx(0.0, 0.0));
+      R[0] = beta;
+      for (int i = 0; i <= m; ++i) P[i] = a[n_s] * R[i];
+      for (int k = 1; k < m; ++k) {
+        step_R(leja[n_s + k - 1]);
+        for (int i = 0; i <= m; ++i) P[i] += a[n_s + k] * R[i];
+      }
     }
     // Psi (+)= sum_{i<m} P_i q_i   (:346-352)
     QP_CHECK(qp_krylov_combine(K, reinterpret_cast<const qp_c128*>(P.data()), 0, m, psi, s > 0 ? 1 : 0));
@@ -282,6 +310,24 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
       return qp_fail(ctx, QP_ERR_NOT_CONVERGED, "newton!: no convergence within max_restarts=%d", max_restarts);
   }
   if (restarts_out) *restarts_out = s;
+  // NewtonWrk bookkeeping of the reference (wrk.n_a, wrk.n_leja, wrk.radius, wrk.a, wrk.leja;
+  // src/newton.jl:381-383), readable through qp_newton_last
+  K->last_n_a = n_a;
+  K->last_n_leja = n_leja;
+  K->last_radius = radius;
+  K->last_a.assign(reinterpret_cast<const qp_c128*>(a.data()), reinterpret_cast<const qp_c128*>(a.data()) + n_a);
+  K->last_leja.assign(reinterpret_cast<const qp_c128*>(leja.data()), reinterpret_cast<const qp_c128*>(leja.data()) + n_leja);
+  return QP_OK;
+}
+
+extern "C" int32_t qp_newton_last(qp_krylov_t K, int32_t* n_a, int32_t* n_leja, double* radius, qp_c128* a, qp_c128* leja,
+                                  int32_t capacity) {
+  if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_newton_last: null workspace");
+  if (n_a) *n_a = K->last_n_a;
+  if (n_leja) *n_leja = K->last_n_leja;
+  if (radius) *radius = K->last_radius;
+  if (a) memcpy(a, K->last_a.data(), sizeof(qp_c128) * std::min<size_t>(K->last_a.size(), (size_t)std::max(capacity, 0)));
+  if (leja) memcpy(leja, K->last_leja.data(), sizeof(qp_c128) * std::min<size_t>(K->last_leja.size(), (size_t)std::max(capacity, 0)));
   return QP_OK;
 }
 

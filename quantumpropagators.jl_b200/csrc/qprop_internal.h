@@ -29,6 +29,11 @@ struct qp_timer_rec {
 };
 
 struct qp_ctx_s {
+  // objects created on the context keep it alive: qp_ctx_destroy on a context that still has
+  // objects only marks it, the resources go with the last object (hosts with finalizers -- Julia,
+  // Python -- destroy things in no particular order)
+  int refs = 0;
+  bool destroy_requested = false;
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
@@ -46,6 +51,25 @@ struct qp_ctx_s {
   qp_c128* h_stage = nullptr;
   size_t stage_elems = 0;
   std::set<const void*> smem_configured;  // kernels already opted in to large dynamic smem
+};
+
+void qp_ctx_release(qp_ctx_t ctx);  // drops one object reference; frees a context whose destruction was requested
+
+// the `ctx` member of every object: a context pointer that holds a reference
+struct CtxHandle {
+  qp_ctx_t c = nullptr;
+  CtxHandle() = default;
+  CtxHandle(const CtxHandle& o) : c(o.c) { if (c) c->refs++; }
+  CtxHandle& operator=(const CtxHandle& o) { return *this = o.c; }
+  CtxHandle& operator=(qp_ctx_t ctx) {
+    if (ctx) ctx->refs++;
+    if (c) qp_ctx_release(c);
+    c = ctx;
+    return *this;
+  }
+  ~CtxHandle() { if (c) qp_ctx_release(c); }
+  operator qp_ctx_t() const { return c; }
+  qp_ctx_t operator->() const { return c; }
 };
 
 // one term c * P rho Q of a matrix-free left/right operator (qp_op_create_leftright)
@@ -72,7 +96,7 @@ struct LRTerm {
 };
 
 struct qp_op_s {
-  qp_ctx_t ctx = nullptr;
+  CtxHandle ctx;
   bool dense = false;
   bool leftright = false;        // matrix-free: nrows = ncols = lr_n^2, no matrix arrays
   int64_t lr_n = 0;
@@ -122,7 +146,7 @@ constexpr int QP_DICT_MAX = 4096;       // table entries incl. the padding entry
 constexpr int QP_DICT_HASH_CAP = 16384; // open-addressing capacity used while building
 
 struct qp_gen_s {
-  qp_ctx_t ctx = nullptr;
+  CtxHandle ctx;
   int n_ops = 0, n_coeffs = 0, drift = 0;
   int64_t n = 0;
   int format = QP_FORMAT_CSR;
@@ -179,13 +203,13 @@ struct qp_gen_s {
 };
 
 struct qp_state_s {
-  qp_ctx_t ctx = nullptr;
+  CtxHandle ctx;
   int64_t n = 0, batch = 1;
   double2* d = nullptr;
 };
 
 struct qp_cheby_s {
-  qp_ctx_t ctx = nullptr;
+  CtxHandle ctx;
   qp_gen_t gen = nullptr;
   int64_t n = 0, batch = 1;
   double2* w1 = nullptr;
@@ -197,7 +221,7 @@ struct qp_cheby_s {
 };
 
 struct qp_krylov_s {
-  qp_ctx_t ctx = nullptr;
+  CtxHandle ctx;
   qp_gen_t gen = nullptr;
   int64_t n = 0;
   int m_max = 0;
@@ -205,6 +229,10 @@ struct qp_krylov_s {
   double2* d_h = nullptr;  // device Hessenberg column (m_max + 2 complex): correction of a second GS round
   double2* d_hall = nullptr;      // all columns, [m_max + 1][m_max + 2]
   struct ColCtl* d_ctl = nullptr; // per-column norms / DGKS flag, [m_max + 1] (krylov.cu)
+  // diagnostics of the last qp_newton_step (NewtonWrk.n_a / n_leja / radius / a / leja)
+  int last_n_a = 0, last_n_leja = 0;
+  double last_radius = 0.0;
+  std::vector<qp_c128> last_a, last_leja;
 };
 
 // ---------------------------------------------------------------------------------------

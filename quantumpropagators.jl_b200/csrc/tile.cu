@@ -39,8 +39,9 @@ struct TileView {
   int n_tab;
   const uint4* codesA;  // [n][WA8] words of eight 16-bit codes
   const uint4* codesB;  // [n][WB8]
-  const double* diag;   // [n][3]
-  int WA8, WB8;
+  const uint4* codesO;  // [n][WO8] class-O entries (gathered from global memory in pass B)
+  const double* diag;   // [n][4] (3 used; 32-byte rows for 16-byte copies)
+  int WA8, WB8, WO8;
   int S, NH, n_ops;
   unsigned imag_ops;
   int64_t n;
@@ -57,6 +58,7 @@ struct qp_tile_s {
   TileEntry* d_tab = nullptr;
   uint4* d_codesA = nullptr;
   uint4* d_codesB = nullptr;
+  uint4* d_codesO = nullptr;
   double* d_diag = nullptr;
   double2* d_ring = nullptr;
   unsigned long long* d_done = nullptr;  // [2][chunk capacity]
@@ -95,14 +97,74 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsi
   }
 }
 
-template <int NOPS>
-__device__ __forceinline__ void tile_acc(const TileEntry& en, const double2 xv, double (&pr)[NOPS], double (&pi)[NOPS]) {
+// shared-memory accesses with 32-bit addresses (no generic-address arithmetic in the entry loop)
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+struct TabLo {  // first 16 bytes of a TileEntry
+  double v0;
+  int32_t off;
+  uint32_t km;
+};
+__device__ __forceinline__ TabLo lds_tablo(uint32_t addr) {
+  TabLo r;
+  int lo, hi;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(r.off), "=r"(r.km) : "r"(addr));
+  r.v0 = __hiloint2double(hi, lo);
+  return r;
+}
+
+// One 16-byte word = eight 16-bit codes of a row, four at a time: table look-ups (warp-uniform
+// broadcasts), then the four loads of X, then the multiply-adds -- unconditionally for every
+// operator (an absent operator has v = 0), no per-entry branches.  GLOBAL: class-O entries, X from
+// global memory at row + off.
+template <int NOPS, bool GLOBAL>
+__device__ __forceinline__ void tile_word(const uint4 w, const uint32_t tab_base, const uint32_t xs_row,
+                                          const double2* __restrict__ xg_row, const int64_t batch,
+                                          double (&pr)[NOPS], double (&pi)[NOPS]) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-  for (int l = 0; l < NOPS; ++l)
-    if ((en.km >> l) & 1u) {  // warp-uniform
-      pr[l] = fma(en.v[l], xv.x, pr[l]);
-      pi[l] = fma(en.v[l], xv.y, pi[l]);
+  for (int h = 0; h < 2; ++h) {
+    if ((ww[2 * h] | ww[2 * h + 1]) == 0u) continue;  // padding only (warp-uniform)
+    uint32_t ta[4];
+    TabLo lo[4];
+    double2 hi[4], xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t code = (q & 1) ? (ww[2 * h + (q >> 1)] >> 16) : (ww[2 * h + (q >> 1)] & 0xffffu);
+      ta[q] = tab_base + code * 32u;
+      lo[q] = lds_tablo(ta[q]);
     }
+    if (NOPS > 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hi[q] = lds_f64x2(ta[q] + 16u);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (GLOBAL) xv[q] = __ldg(xg_row + (int64_t)lo[q].off * batch);
+      else xv[q] = lds_f64x2(xs_row + (uint32_t)lo[q].off);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pr[0] = fma(lo[q].v0, xv[q].x, pr[0]);
+      pi[0] = fma(lo[q].v0, xv[q].y, pi[0]);
+      if (NOPS > 1) {
+        pr[1] = fma(hi[q].x, xv[q].x, pr[1]);
+        pi[1] = fma(hi[q].x, xv[q].y, pi[1]);
+      }
+      if (NOPS > 2) {
+        pr[2] = fma(hi[q].y, xv[q].x, pr[2]);
+        pi[2] = fma(hi[q].y, xv[q].y, pi[2]);
+      }
+    }
+  }
 }
 
 template <int EPI, int NOPS>
@@ -113,6 +175,11 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
   double2* s_x = reinterpret_cast<double2*>(smem_raw);  // [rows][32]
   const int max_rows = tv.S > tv.NH ? tv.S : tv.NH;
   TileEntry* s_tab = reinterpret_cast<TileEntry*>(smem_raw + (size_t)max_rows * 512);
+  // per tile: the rows' code words (pass A: WA8 words; pass B: WB8 + WO8 words) and, in pass A, the diagonals
+  uint4* s_codes = reinterpret_cast<uint4*>(smem_raw + (size_t)max_rows * 512 + (((size_t)tv.n_tab * sizeof(TileEntry) + 15) & ~(size_t)15));
+  const int cwA = tv.WA8, cwB = tv.WB8 + tv.WO8;
+  const int code_words = tv.S * cwA > tv.NH * cwB ? tv.S * cwA : tv.NH * cwB;
+  double* s_diag = reinterpret_cast<double*>(s_codes + code_words);  // [S][4] (3 used)
   for (int j = threadIdx.x; j < tv.n_tab; j += TILE_THREADS) s_tab[j] = tv.tab[j];
   __syncthreads();
 
@@ -150,6 +217,26 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
       const int s = idx >> 5, j = idx & 31;
       cp_async16(s_x + idx, x + (row0 + s * rstep) * batch + c0 + j);
     }
+    // ... and the code words of its rows (and the diagonals in pass A)
+    {
+      const int W8 = pass == 0 ? tv.WA8 : tv.WB8;
+      const int WT = pass == 0 ? cwA : cwB;
+      const uint4* src = pass == 0 ? tv.codesA : tv.codesB;
+      for (int idx = threadIdx.x; idx < rows * W8; idx += TILE_THREADS) {
+        const int s = idx / W8, k = idx - s * W8;
+        cp_async16(s_codes + s * WT + k, src + (row0 + s * rstep) * W8 + k);
+      }
+      if (pass == 1)
+        for (int idx = threadIdx.x; idx < rows * tv.WO8; idx += TILE_THREADS) {
+          const int s = idx / tv.WO8, k = idx - s * tv.WO8;
+          cp_async16(s_codes + s * WT + W8 + k, tv.codesO + (row0 + s * rstep) * tv.WO8 + k);
+        }
+      if (pass == 0)
+        for (int idx = threadIdx.x; idx < rows * 2; idx += TILE_THREADS) {  // 32 bytes per row: d0 d1 | d2 pad
+          const int s = idx >> 1, k = idx & 1;
+          cp_async16(s_diag + s * 4 + 2 * k, tv.diag + (row0 + s) * 4 + 2 * k);
+        }
+    }
     // 2. this lane's coefficients (times i for a purely imaginary operator)
     double2 u[NOPS];
 #pragma unroll
@@ -169,64 +256,64 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
     __syncthreads();
 
     double2* tbuf = tv.tring + (g % TILE_RING) * ring_elems;
-    const uint4* codes = pass == 0 ? tv.codesA : tv.codesB;
+    const uint32_t tab_base = smem_u32(s_tab);
+    const uint32_t xs_base = smem_u32(s_x) + (uint32_t)lane * 16u;
     const int W8 = pass == 0 ? tv.WA8 : tv.WB8;
     double dr = 0.0, di = 0.0, nn = 0.0;
 
-    for (int s = warp; s < rows; s += TILE_WARPS) {
-      const int64_t row = row0 + s * rstep;
-      const int64_t idx = row * batch + c0 + lane;
-      const double2 xown = s_x[s * 32 + lane];
-      // epilogue operands requested before the row is decoded
-      double2 tv_in = make_double2(0.0, 0.0), yv = tv_in, av = tv_in;
+    // Software pipeline over this warp's rows: the epilogue operands of the NEXT row (global / L2
+    // loads) are requested before the current row is decoded; everything else a row needs -- X,
+    // its code words, the table, the diagonal -- is in shared memory.  All row-dependent global
+    // addresses advance by constant strides.
+    const int64_t row_stride = (int64_t)TILE_WARPS * rstep;            // rows between two of this warp's rows
+    const int64_t row_w = row0 + (int64_t)warp * rstep;
+    const double2* xg_row = x + row_w * batch + c0 + lane;             // x[row][c0 + lane]
+    const int64_t el_stride = row_stride * batch;
+    int64_t idx = row_w * batch + c0 + lane;
+    const double2* t_ptr = tbuf + row_w * 32 + lane;
+    const int64_t t_stride = row_stride * 32;
+    const int WT = pass == 0 ? cwA : cwB;
+    const uint32_t codes_base = smem_u32(s_codes);
+    const uint32_t diag_base = smem_u32(s_diag);
+
+    double2 n_t = make_double2(0.0, 0.0), n_y = n_t, n_a = n_t;
+    auto prefetch = [&](const double2* tp, int64_t ix) {
       if (pass == 1) {
-        tv_in = ld_cg(tbuf + row * 32 + lane);
+        n_t = ld_cg(tp);
         if (EPI == EPI_MUL) {
-          if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + idx);
+          if (e.betac.x != 0.0 || e.betac.y != 0.0) n_y = ld_noalloc(e.y + ix);
         } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
-          yv = ld_noalloc(e.y + idx);
-          av = ld_noalloc(e.acc + idx);
+          n_y = ld_noalloc(e.y + ix);
+          n_a = ld_noalloc(e.acc + ix);
         }
       }
+    };
+    if (warp < rows) prefetch(t_ptr, idx);
+    for (int s = warp; s < rows; s += TILE_WARPS) {
+      const double2 tv_in = n_t, yv = n_y, av = n_a;
+      if (s + TILE_WARPS < rows) prefetch(t_ptr + t_stride, idx + el_stride);
+      const uint32_t xs_row = xs_base + (uint32_t)s * 512u;
+      const uint32_t cw = codes_base + (uint32_t)(s * WT) * 16u;
+      const double2 xown = lds_f64x2(xs_row);
       double pr[NOPS], pi[NOPS];
 #pragma unroll
       for (int l = 0; l < NOPS; ++l) pr[l] = pi[l] = 0.0;
-      const unsigned char* xs_row = reinterpret_cast<const unsigned char*>(s_x) + (size_t)s * 512 + lane * 16;
-      const double2* xg_row = x + row * batch + c0 + lane;
-      const uint4* cw = codes + row * W8;
-      uint4 w_next = make_uint4(0u, 0u, 0u, 0u);
-      if (W8 > 0) w_next = __ldg(cw);
-      for (int k = 0; k < W8; ++k) {
-        const uint4 w = w_next;
-        if (k + 1 < W8) w_next = __ldg(cw + k + 1);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // four codes at a time: all loads issued before the first use
-          if ((ww[2 * h] | ww[2 * h + 1]) == 0u) continue;  // padding only (warp-uniform)
-          TileEntry en[4];
-          double2 xv[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t code = (ww[2 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-            en[q] = s_tab[code];
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (en[q].km & qptile::TILE_KIND_O)
-              xv[q] = __ldg(xg_row + (int64_t)en[q].off * batch);
-            else
-              xv[q] = *reinterpret_cast<const double2*>(xs_row + en[q].off);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) tile_acc<NOPS>(en[q], xv[q], pr, pi);
+      for (int k = 0; k < W8; ++k) tile_word<NOPS, false>(lds_u32x4(cw + 16u * k), tab_base, xs_row, xg_row, batch, pr, pi);
+      if (pass == 1) {  // class O: the few couplings that straddle the split, from global memory
+        for (int k = 0; k < tv.WO8; ++k)
+          tile_word<NOPS, true>(lds_u32x4(cw + 16u * (W8 + k)), tab_base, xs_row, xg_row, batch, pr, pi);
+      } else {          // explicit diagonals
+        const double2 d01 = lds_f64x2(diag_base + (uint32_t)s * 32u);
+        pr[0] = fma(d01.x, xown.x, pr[0]);
+        pi[0] = fma(d01.x, xown.y, pi[0]);
+        if (NOPS > 1) {
+          pr[1] = fma(d01.y, xown.x, pr[1]);
+          pi[1] = fma(d01.y, xown.y, pi[1]);
         }
-      }
-      if (pass == 0) {  // explicit diagonals
-#pragma unroll
-        for (int l = 0; l < NOPS; ++l) {
-          const double d = __ldg(tv.diag + row * qptile::TILE_MAX_OPS + l);
-          pr[l] = fma(d, xown.x, pr[l]);
-          pi[l] = fma(d, xown.y, pi[l]);
+        if (NOPS > 2) {
+          const double2 d2 = lds_f64x2(diag_base + (uint32_t)s * 32u + 16u);
+          pr[2] = fma(d2.x, xown.x, pr[2]);
+          pi[2] = fma(d2.x, xown.y, pi[2]);
         }
       }
       double2 hx = tv_in;
@@ -235,8 +322,11 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
         hx.x += u[l].x * pr[l] - u[l].y * pi[l];
         hx.y += u[l].x * pi[l] + u[l].y * pr[l];
       }
-      if (pass == 0) st_cg(tbuf + row * 32 + lane, hx);
+      if (pass == 0) st_cg(const_cast<double2*>(t_ptr), hx);
       else epi_apply<EPI>(e, idx, hx, xown, yv, av, dr, di, nn);
+      xg_row += el_stride;
+      idx += el_stride;
+      t_ptr += t_stride;
     }
     if (pass == 1 && epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, c0 + lane, dr, di, nn);
 
@@ -253,11 +343,19 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
 // host side
 // ---------------------------------------------------------------------------------------
 
+// shared memory of one CTA: X tile + table + the tile's code words + the diagonals (pass A)
+static size_t tile_smem_bytes(const qptile::TileFormat& f, int n_tab) {
+  const size_t rows = (size_t)std::max(f.S, f.NH);
+  const size_t code_words = std::max((size_t)f.S * (f.WA / 8), (size_t)f.NH * (f.WB / 8 + f.WO / 8));
+  return rows * 512 + (((size_t)n_tab * sizeof(TileEntry) + 15) & ~(size_t)15) + code_words * 16 + (size_t)f.S * 32;
+}
+
 void qp_tile_free(qp_tile_s* t) {
   if (!t) return;
   cudaFree(t->d_tab);
   cudaFree(t->d_codesA);
   cudaFree(t->d_codesB);
+  cudaFree(t->d_codesO);
   cudaFree(t->d_diag);
   cudaFree(t->d_ring);
   cudaFree(t->d_done);
@@ -292,8 +390,7 @@ static int32_t tile_ensure(qp_gen_t gen) {
     t->why = "more than a quarter of the entries straddle the split";
     return QP_OK;
   }
-  const int max_rows = std::max(f.S, f.NH);
-  if ((size_t)max_rows * 512 + f.table.size() * sizeof(TileEntry) > (size_t)220 * 1024) { t->why = "table too large for shared memory"; return QP_OK; }
+  if (tile_smem_bytes(f, (int)f.table.size()) > (size_t)224 * 1024) { t->why = "tile + table + code words exceed shared memory"; return QP_OK; }
   auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e1 = cudaMalloc(dst, bytes ? bytes : 16);
     if (e1 == cudaSuccess && bytes) e1 = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
@@ -302,12 +399,19 @@ static int32_t tile_ensure(qp_gen_t gen) {
   QP_CUDA(ctx, up((void**)&t->d_tab, f.table.data(), f.table.size() * sizeof(TileEntry)));
   QP_CUDA(ctx, up((void**)&t->d_codesA, f.codesA.data(), f.codesA.size() * sizeof(uint16_t)));
   QP_CUDA(ctx, up((void**)&t->d_codesB, f.codesB.data(), f.codesB.size() * sizeof(uint16_t)));
-  QP_CUDA(ctx, up((void**)&t->d_diag, f.diag.data(), f.diag.size() * sizeof(double)));
+  QP_CUDA(ctx, up((void**)&t->d_codesO, f.codesO.data(), f.codesO.size() * sizeof(uint16_t)));
+  {
+    std::vector<double> d4((size_t)n * 4, 0.0);
+    for (int64_t r = 0; r < n; ++r)
+      for (int l = 0; l < qptile::TILE_MAX_OPS; ++l) d4[(size_t)r * 4 + l] = f.diag[(size_t)r * qptile::TILE_MAX_OPS + l];
+    QP_CUDA(ctx, up((void**)&t->d_diag, d4.data(), d4.size() * sizeof(double)));
+  }
   QP_CUDA(ctx, cudaMalloc(&t->d_ring, sizeof(double2) * (size_t)TILE_RING * (size_t)n * 32));
   t->n_tab = (int)f.table.size();
   // the big host arrays are not needed any more
   std::vector<uint16_t>().swap(f.codesA);
   std::vector<uint16_t>().swap(f.codesB);
+  std::vector<uint16_t>().swap(f.codesO);
   std::vector<double>().swap(f.diag);
   t->ok = true;
   return QP_OK;
@@ -338,9 +442,11 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   tv.n_tab = t->n_tab;
   tv.codesA = t->d_codesA;
   tv.codesB = t->d_codesB;
+  tv.codesO = t->d_codesO;
   tv.diag = t->d_diag;
   tv.WA8 = f.WA / 8;
   tv.WB8 = f.WB / 8;
+  tv.WO8 = f.WO / 8;
   tv.S = f.S;
   tv.NH = f.NH;
   tv.n_ops = f.n_ops;
@@ -351,7 +457,7 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   tv.doneB = t->d_done + t->chunk_cap;
   tv.epoch = ++t->epoch;
   auto kern = k_spmm_tile<EPI, NOPS>;
-  const size_t smem = (size_t)std::max(f.S, f.NH) * 512 + (size_t)t->n_tab * sizeof(TileEntry);
+  const size_t smem = tile_smem_bytes(f, t->n_tab);
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     ctx->smem_configured.insert((const void*)kern);

@@ -40,11 +40,13 @@ constexpr int TILE_MAX_ROWS = 256;     // rows per tile: 256 x 32 x 16 B = 128 K
 constexpr int TILE_MAX_TABLE = 2048;   // 16-bit codes; 2048 x 32 B = 64 KB of shared memory next to the 128 KB tile
 constexpr uint32_t TILE_KIND_O = 1u << 8;
 
-struct TileEntry {      // 32 bytes, read with two 16-byte shared-memory loads
-  double v[TILE_MAX_OPS];  // real representation of the value per operator (0: operator absent)
+struct TileEntry {      // 32 bytes, read with two 16-byte shared-memory loads: {v0, off, km} {v1, v2}
+  double v0;               // real representation of the value of operator 0 (0: operator absent)
   int32_t off;             // class A / B: byte offset inside the shared-memory tile (slot delta * 512);
                            // class O: row delta (c - r)
   uint32_t km;             // bits 0..2: operators present; TILE_KIND_O: class O
+  double v1, v2;           // operators 1 and 2
+  double v(int l) const { return l == 0 ? v0 : l == 1 ? v1 : v2; }
 };
 static_assert(sizeof(TileEntry) == 32, "TileEntry must be 32 bytes");
 
@@ -52,10 +54,11 @@ struct TileFormat {
   int64_t n = 0;
   int S = 0, NH = 0, n_ops = 0;
   unsigned imag_ops = 0;            // bit l: operator l is purely imaginary (v = Im)
-  int WA = 0, WB = 0;               // codes per row in pass A / pass B (multiples of 8)
+  int WA = 0, WB = 0, WO = 0;       // codes per row: class A (pass A), class B and class O (pass B); multiples of 8
   std::vector<TileEntry> table;     // [n_table], entry 0 = padding
   std::vector<uint16_t> codesA;     // [n][WA]
   std::vector<uint16_t> codesB;     // [n][WB]
+  std::vector<uint16_t> codesO;     // [n][WO]
   std::vector<double> diag;         // [n][TILE_MAX_OPS] real representation of the main diagonals
   int64_t n_A = 0, n_B = 0, n_O = 0, n_diag = 0;  // merged entries per class
   std::string why;                  // reason when build() returns false
@@ -89,7 +92,30 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
   f.n = n;
   f.n_ops = n_ops;
   if (n_ops < 1 || n_ops > TILE_MAX_OPS) { f.why = "more than 3 operators"; return false; }
-  const int S = S_forced > 0 ? S_forced : choose_split(n);
+  int S = S_forced > 0 ? S_forced : choose_split(n);
+  if (S_forced <= 0 && S > 0) {
+    // among all admissible splits take the one with the fewest class-O entries (a split between two
+    // tensor factors: 4-level sites want S = 4^k); ties go to the most balanced one (choose_split)
+    // (reasonably balanced splits only: both tile heights <= 4 sqrt(N), so that neither pass
+    // degenerates into tiles of a few rows)
+    int64_t best_o = -1;
+    const int balanced = S;
+    for (int cand = TILE_MAX_ROWS; cand >= 2; cand >>= 1) {
+      if (n % cand != 0) continue;
+      if (n / cand > TILE_MAX_ROWS) break;
+      if (cand != balanced && (double)std::max<int64_t>(cand, n / cand) > 4.0 * std::sqrt((double)n)) continue;
+      int64_t n_o = 0;
+      for (int64_t r = 0; r < n; ++r)
+        for (uint32_t k = mptr[r]; k < mptr[r + 1]; ++k) {
+          const int64_t c = (int64_t)(colop[k] & COL_MASK);
+          if (c != r && c / cand != r / cand && c % cand != r % cand) ++n_o;
+        }
+      if (best_o < 0 || n_o < best_o || (n_o == best_o && cand == balanced)) {
+        best_o = n_o;
+        S = cand;
+      }
+    }
+  }
   if (S <= 0 || n % S != 0 || n / S > TILE_MAX_ROWS || S > TILE_MAX_ROWS) { f.why = "no two-level split of N with tiles of <= 256 rows"; return false; }
   f.S = S;
   f.NH = (int)(n / S);
@@ -105,11 +131,11 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
   if (has_re & has_im) { f.why = "an operator has both real and imaginary values"; return false; }
   f.imag_ops = has_im;
 
-  f.table.assign(1, TileEntry{{0.0, 0.0, 0.0}, 0, 0u});
+  f.table.assign(1, TileEntry{0.0, 0, 0u, 0.0, 0.0});
   f.diag.assign((size_t)n * TILE_MAX_OPS, 0.0);
   using Key = std::tuple<uint32_t, int32_t, uint64_t, uint64_t, uint64_t>;
   std::map<Key, uint16_t> dict;
-  std::vector<std::vector<uint16_t>> rowsA((size_t)n), rowsB((size_t)n);
+  std::vector<std::vector<uint16_t>> rowsA((size_t)n), rowsB((size_t)n), rowsO((size_t)n);
   struct Ent { int64_t col; int op; double v; };
   std::vector<Ent> row;
   auto bits = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
@@ -137,7 +163,7 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
       }
       uint32_t km = mask;
       int32_t off;
-      bool passA = false;
+      bool passA = false, isO = false;
       if (c / S == r / S) {  // class A: same block of S rows
         off = (int32_t)(c - r) * (TILE_TRAJ * 16);
         passA = true;
@@ -148,6 +174,7 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
       } else {
         off = (int32_t)(c - r);
         km |= TILE_KIND_O;
+        isO = true;
         ++f.n_O;
       }
       // pass A and pass B entries never share a table entry (their offsets mean different things)
@@ -157,26 +184,30 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
       if (it == dict.end()) {
         if ((int)f.table.size() >= TILE_MAX_TABLE) { f.why = "more than 2047 distinct (offset, values) entries"; return false; }
         code = (uint16_t)f.table.size();
-        f.table.push_back(TileEntry{{v[0], v[1], v[2]}, off, km});
+        f.table.push_back(TileEntry{v[0], off, km, v[1], v[2]});
         dict.emplace(key, code);
       } else {
         code = it->second;
       }
-      (passA ? rowsA : rowsB)[(size_t)r].push_back(code);
+      (passA ? rowsA : isO ? rowsO : rowsB)[(size_t)r].push_back(code);
     }
   }
-  size_t wa = 0, wb = 0;
+  size_t wa = 0, wb = 0, wo = 0;
   for (int64_t r = 0; r < n; ++r) {
     wa = std::max(wa, rowsA[(size_t)r].size());
     wb = std::max(wb, rowsB[(size_t)r].size());
+    wo = std::max(wo, rowsO[(size_t)r].size());
   }
   f.WA = (int)((wa + 7) / 8 * 8);
   f.WB = (int)((wb + 7) / 8 * 8);
+  f.WO = (int)((wo + 7) / 8 * 8);
   f.codesA.assign((size_t)n * f.WA, 0);
   f.codesB.assign((size_t)n * f.WB, 0);
+  f.codesO.assign((size_t)n * f.WO, 0);
   for (int64_t r = 0; r < n; ++r) {
     std::copy(rowsA[(size_t)r].begin(), rowsA[(size_t)r].end(), f.codesA.begin() + (size_t)r * f.WA);
     std::copy(rowsB[(size_t)r].begin(), rowsB[(size_t)r].end(), f.codesB.begin() + (size_t)r * f.WB);
+    std::copy(rowsO[(size_t)r].begin(), rowsO[(size_t)r].end(), f.codesO.begin() + (size_t)r * f.WO);
   }
   return true;
 }
@@ -198,30 +229,31 @@ inline void apply_host(const TileFormat& f, int64_t B, const double* u_reim /*[n
     }
   };
   for (int pass = 0; pass < 2; ++pass) {
-    const int W = pass == 0 ? f.WA : f.WB;
-    const std::vector<uint16_t>& codes = pass == 0 ? f.codesA : f.codesB;
     for (int64_t r = 0; r < n; ++r) {
-      // slot of row r in its tile and the row of slot 0
+      // slot of row r in its tile
       const int64_t slot = pass == 0 ? r % S : r / S;
       for (int64_t b = 0; b < B; ++b) {
         double pr[TILE_MAX_OPS] = {0, 0, 0}, pi[TILE_MAX_OPS] = {0, 0, 0};
-        for (int j = 0; j < W; ++j) {
-          const uint16_t code = codes[(size_t)r * W + j];
-          if (code == 0) continue;
-          const TileEntry& e = f.table[code];
-          int64_t c;
-          if (e.km & TILE_KIND_O) {
-            c = r + e.off;
-          } else {
-            const int64_t s2 = slot + e.off / (TILE_TRAJ * 16);
-            c = pass == 0 ? (r / S) * S + s2 : s2 * S + r % S;
-          }
-          const double xr = x_reim[2 * ((size_t)c * B + b)], xi = x_reim[2 * ((size_t)c * B + b) + 1];
-          for (int l = 0; l < f.n_ops; ++l)
-            if ((e.km >> l) & 1u) {
-              pr[l] += e.v[l] * xr;
-              pi[l] += e.v[l] * xi;
+        for (int list = 0; list < (pass == 0 ? 1 : 2); ++list) {
+          const int W = pass == 0 ? f.WA : list == 0 ? f.WB : f.WO;
+          const std::vector<uint16_t>& codes = pass == 0 ? f.codesA : list == 0 ? f.codesB : f.codesO;
+          for (int j = 0; j < W; ++j) {
+            const uint16_t code = codes[(size_t)r * W + j];
+            if (code == 0) continue;
+            const TileEntry& e = f.table[code];
+            int64_t c;
+            if (e.km & TILE_KIND_O) {
+              c = r + e.off;
+            } else {
+              const int64_t s2 = slot + e.off / (TILE_TRAJ * 16);
+              c = pass == 0 ? (r / S) * S + s2 : s2 * S + r % S;
             }
+            const double xr = x_reim[2 * ((size_t)c * B + b)], xi = x_reim[2 * ((size_t)c * B + b) + 1];
+            for (int l = 0; l < f.n_ops; ++l) {  // absent operators have v = 0 (the kernels multiply unconditionally)
+              pr[l] += e.v(l) * xr;
+              pi[l] += e.v(l) * xi;
+            }
+          }
         }
         if (pass == 0) {
           const double xr = x_reim[2 * ((size_t)r * B + b)], xi = x_reim[2 * ((size_t)r * B + b) + 1];

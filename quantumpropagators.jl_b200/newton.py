@@ -260,6 +260,16 @@ def _newton_library(Psi, H, dt, wrk, func, norm_min, relerr, max_restarts, coeff
         K.ctx.handle,
     )
     wrk.restarts = restarts.value
+    # NewtonWrk bookkeeping like the reference (src/newton.jl:381-383)
+    n_a, n_leja, radius = C.c_int32(), C.c_int32(), C.c_double()
+    L.check(K.ctx._lib.qp_newton_last(K.handle, C.byref(n_a), C.byref(n_leja), C.byref(radius), None, None, 0), K.ctx.handle)
+    if n_a.value > len(wrk.a):
+        wrk.a = np.zeros(2 * n_a.value, dtype=np.complex128)
+    if n_leja.value > len(wrk.leja):
+        wrk.leja = np.zeros(2 * n_leja.value, dtype=np.complex128)
+    cap = min(len(wrk.a), len(wrk.leja))
+    L.check(K.ctx._lib.qp_newton_last(K.handle, None, None, None, L.ptr(wrk.a), L.ptr(wrk.leja), cap), K.ctx.handle)
+    wrk.n_a, wrk.n_leja, wrk.radius = n_a.value, n_leja.value, radius.value
     return Psi
 
 

@@ -83,6 +83,17 @@ def test_transmon_chain_classes(lib):
     assert n_tab < 400
 
 
+def test_split_follows_the_tensor_structure(lib):
+    """3 sites x 4 levels (N = 64): the balanced split 8 x 8 cuts a site in half; the builder takes
+    16 x 4 (or 4 x 16), where only the hop across the split is class O."""
+    import qprop_b200 as qp
+
+    H0, H1, H2 = qp.workloads.transmon_chain(3, 4)
+    err, st = run(lib, [H0, H1, H2], 4, np.random.default_rng(2))
+    assert err < 1e-14 and st[0] in (4, 16) and st[0] * st[1] == 64
+    assert 4 * st[7] <= st[5] + st[6] + st[7]        # qualifies for the tiled path (<= a quarter class O)
+
+
 @pytest.mark.parametrize("n,B,S", [(64, 3, 0), (256, 5, 0), (256, 2, 64), (1000, 4, 0), (512, 1, 2)])
 def test_unstructured_matrices(lib, n, B, S):
     """Random sparse operators (mostly class O), one purely imaginary, duplicates of columns across
