@@ -137,7 +137,8 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
 // (DGKS) round is needed -- when the projection removed more than half of |w|^2 -- and the
 // second round adds its correction to the accumulated column
 __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, ColCtl* __restrict__ ctl, int round,
-                              double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec, double norm_min) {
+                              double2* __restrict__ h_acc, const double2* __restrict__ h_corr, int nvec, double norm_min,
+                              double eta2) {
   pdl_sync();
   if (round == 2 && ctl->again == 0.0) return;
   const int lane = threadIdx.x;
@@ -157,7 +158,13 @@ __global__ void k_norm_decide(const double* __restrict__ partial, int nblocks, C
     // the restart vector of newton! combines it with weight R[m+1] (src/newton.jl:360-366)
     const double nrm = sqrt(t);
     ctl->inv = (t > 0.0 && nrm >= norm_min) ? 1.0 / nrm : 0.0;
-    if (round == 1) ctl->again = (t < 0.5 * ctl->ww && t != 0.0) ? 1.0 : 0.0;
+    // second (DGKS) round when the projection removed more than a fraction 1 - eta^2 of |w|^2, with
+    // the textbook eta = 1/sqrt(2).  A laxer eta = 0.1 saves 7-9 % of a Newton step on config 4 (measured:
+    // 9.89 -> 9.22 ms at N = 2^22, 40.2 -> 36.5 ms at N = 2^24) but classical Gram-Schmidt then loses
+    // orthogonality like eps (|w| / |w'|)^2 per column and the optomech parity pin (Newton == Cheby to 1e-10
+    // after 250 steps, test/test_propagate.jl:153-163) degrades to 1.2e-10: parity first.  QPROP_DGKS_ETA
+    // overrides.
+    if (round == 1) ctl->again = (t < eta2 * ctl->ww && t != 0.0) ? 1.0 : 0.0;
   }
 }
 
@@ -277,6 +284,8 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
   double2* h_acc = K->d_hall + (size_t)j * (K->m_max + 2);
   double2* h_corr = K->d_h;  // this round's coefficients
   ColCtl* ctl = K->d_ctl + j;
+  static const double eta = getenv("QPROP_DGKS_ETA") ? atof(getenv("QPROP_DGKS_ETA")) : 0.70710678118654752;
+  const double eta2 = eta * eta;
   for (int round = 1; round <= 2; ++round) {
     const double* gate = round == 2 ? &ctl->again : nullptr;
     double2* h = round == 1 ? h_acc : h_corr;
@@ -295,7 +304,7 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
       DISPATCH_NV(nv, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, h + i0, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
     }
-    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec, norm_min);
+    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec, norm_min, eta2);
     QP_LAUNCHED(ctx);
   }
   return QP_OK;

@@ -28,20 +28,23 @@
 #include "spmv.cuh"
 #include "tile_format.h"
 
-using qptile::TileEntry;
+using qptile::Entry16;
+using qptile::Entry32;
+using qptile::N_KINDS;
 
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 constexpr int TILE_RING = 3;
 
 struct TileView {
-  const TileEntry* tab;
-  int n_tab;
-  const uint4* codesA;  // [n][WA8] words of eight 16-bit codes
-  const uint4* codesB;  // [n][WB8]
-  const uint4* codesO;  // [n][WO8] class-O entries (gathered from global memory in pass B)
-  const double* diag;   // [n][4] (3 used; 32-byte rows for 16-byte copies)
-  int WA8, WB8, WO8;
+  const Entry16* tab16;
+  const Entry32* tab32;
+  int n16, n32;
+  const uint4* codes[2];       // per pass: [n][WT] words of eight 16-bit codes, the kinds' lists back to back
+  int WT[2];                   // words per row
+  int w0[2][N_KINDS];          // first word of a kind's list
+  int nw[2][N_KINDS];          // words of a kind's list (0: the generator has no such entries)
+  const double* diag;          // [n][4] (3 used; 32-byte rows for 16-byte copies)
   int S, NH, n_ops;
   unsigned imag_ops;
   int64_t n;
@@ -55,17 +58,16 @@ struct qp_tile_s {
   bool ok = false;
   std::string why;
   qptile::TileFormat meta;  // host copy without the big arrays (cleared after upload)
-  TileEntry* d_tab = nullptr;
-  uint4* d_codesA = nullptr;
-  uint4* d_codesB = nullptr;
-  uint4* d_codesO = nullptr;
+  Entry16* d_tab16 = nullptr;
+  Entry32* d_tab32 = nullptr;
+  uint4* d_codes[2] = {nullptr, nullptr};
   double* d_diag = nullptr;
   double2* d_ring = nullptr;
   unsigned long long* d_done = nullptr;  // [2][chunk capacity]
   int64_t chunk_cap = 0;
   int64_t chunks_cur = 0;  // chunk count the counters have been counting with since their last reset
   unsigned long long epoch = 0;
-  int n_tab = 0;
+  int n16 = 0, n32 = 0;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -97,7 +99,7 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsi
   }
 }
 
-// shared-memory accesses with 32-bit addresses (no generic-address arithmetic in the entry loop)
+// shared-memory accesses with 32-bit addresses (no generic-address arithmetic in the entry loops)
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 r;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
@@ -108,79 +110,187 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
-struct TabLo {  // first 16 bytes of a TileEntry
-  double v0;
+struct Tab16 {  // an Entry16 / the first half of an Entry32 in registers
+  double v;
   int32_t off;
-  uint32_t km;
+  uint32_t flag;
 };
-__device__ __forceinline__ TabLo lds_tablo(uint32_t addr) {
-  TabLo r;
+__device__ __forceinline__ Tab16 lds_tab16(uint32_t addr) {
+  Tab16 r;
   int lo, hi;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(r.off), "=r"(r.km) : "r"(addr));
-  r.v0 = __hiloint2double(hi, lo);
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(r.off), "=r"(r.flag) : "r"(addr));
+  r.v = __hiloint2double(hi, lo);
   return r;
 }
 
-// One 16-byte word = eight 16-bit codes of a row, four at a time: table look-ups (warp-uniform
-// broadcasts), then the four loads of X, then the multiply-adds -- unconditionally for every
-// operator (an absent operator has v = 0), no per-entry branches.  GLOBAL: class-O entries, X from
-// global memory at row + off.
-template <int NOPS, bool GLOBAL>
-__device__ __forceinline__ void tile_word(const uint4 w, const uint32_t tab_base, const uint32_t xs_row,
+// The entry loops.  A list = the words [cw, cw + nw) of one kind in the row's code words (shared
+// memory); codes are packed at the front, so the first all-zero group of four ends the list.  Per
+// group: table look-ups (warp-uniform broadcasts), then the loads of X, then the multiply-adds; no
+// per-entry decisions.  MODE 0: kind S_L (one operator, 2 FMA); MODE 1: kind P (operators NOPS-2 and
+// NOPS-1, second value = +-v, 4 FMA); MODE 2: kind G (32-byte entries, every operator); MODE 3:
+// kind O (as G, X from global memory at row + off).
+template <int NOPS, int MODE, int L>
+__device__ __forceinline__ void tile_list(uint32_t cw, const int nw, const uint32_t tab_base, const uint32_t xs_row,
                                           const double2* __restrict__ xg_row, const int64_t batch,
                                           double (&pr)[NOPS], double (&pi)[NOPS]) {
-  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  constexpr uint32_t ESZ = MODE >= 2 ? 32u : 16u;
+  for (int k = 0; k < nw; ++k, cw += 16u) {
+    const uint4 w = lds_u32x4(cw);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if ((ww[2 * h] | ww[2 * h + 1]) == 0u) continue;  // padding only (warp-uniform)
-    uint32_t ta[4];
-    TabLo lo[4];
-    double2 hi[4], xv[4];
+    for (int h = 0; h < 2; ++h) {
+      if ((ww[2 * h] | ww[2 * h + 1]) == 0u) return;  // end of the list (warp-uniform)
+      uint32_t ta[4];
+      Tab16 lo[4];
+      double2 hi[4], xv[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t code = (q & 1) ? (ww[2 * h + (q >> 1)] >> 16) : (ww[2 * h + (q >> 1)] & 0xffffu);
-      ta[q] = tab_base + code * 32u;
-      lo[q] = lds_tablo(ta[q]);
-    }
-    if (NOPS > 1) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) hi[q] = lds_f64x2(ta[q] + 16u);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (GLOBAL) xv[q] = __ldg(xg_row + (int64_t)lo[q].off * batch);
-      else xv[q] = lds_f64x2(xs_row + (uint32_t)lo[q].off);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      pr[0] = fma(lo[q].v0, xv[q].x, pr[0]);
-      pi[0] = fma(lo[q].v0, xv[q].y, pi[0]);
-      if (NOPS > 1) {
-        pr[1] = fma(hi[q].x, xv[q].x, pr[1]);
-        pi[1] = fma(hi[q].x, xv[q].y, pi[1]);
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t code = (q & 1) ? (ww[2 * h + (q >> 1)] >> 16) : (ww[2 * h + (q >> 1)] & 0xffffu);
+        ta[q] = tab_base + code * ESZ;
+        lo[q] = lds_tab16(ta[q]);
       }
-      if (NOPS > 2) {
-        pr[2] = fma(hi[q].y, xv[q].x, pr[2]);
-        pi[2] = fma(hi[q].y, xv[q].y, pi[2]);
+      if (MODE >= 2 && NOPS > 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hi[q] = lds_f64x2(ta[q] + 16u);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (MODE == 3) xv[q] = __ldg(xg_row + (int64_t)lo[q].off * batch);
+        else xv[q] = lds_f64x2(xs_row + (uint32_t)lo[q].off);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (MODE == 0) {
+          pr[L] = fma(lo[q].v, xv[q].x, pr[L]);
+          pi[L] = fma(lo[q].v, xv[q].y, pi[L]);
+        } else if (MODE == 1) {
+          constexpr int P1 = NOPS >= 2 ? NOPS - 2 : 0, P2 = NOPS >= 2 ? NOPS - 1 : 0;
+          const double v2 = __hiloint2double(__double2hiint(lo[q].v) ^ (int)lo[q].flag, __double2loint(lo[q].v));
+          pr[P1] = fma(lo[q].v, xv[q].x, pr[P1]);
+          pi[P1] = fma(lo[q].v, xv[q].y, pi[P1]);
+          pr[P2] = fma(v2, xv[q].x, pr[P2]);
+          pi[P2] = fma(v2, xv[q].y, pi[P2]);
+        } else {
+          pr[0] = fma(lo[q].v, xv[q].x, pr[0]);
+          pi[0] = fma(lo[q].v, xv[q].y, pi[0]);
+          if (NOPS > 1) {
+            pr[1] = fma(hi[q].x, xv[q].x, pr[1]);
+            pi[1] = fma(hi[q].x, xv[q].y, pi[1]);
+          }
+          if (NOPS > 2) {
+            pr[2] = fma(hi[q].y, xv[q].x, pr[2]);
+            pi[2] = fma(hi[q].y, xv[q].y, pi[2]);
+          }
+        }
       }
     }
   }
 }
 
+struct TileRowArgs {
+  int rows, warp, lane;
+  int64_t row0, rstep, c0, batch;
+  double2* tbuf;
+  uint32_t tab16_base, tab32_base, xs_base, codes_base, diag_base;
+};
+
+// The rows of one tile, PASS known at compile time (list positions and widths are read once per
+// tile, not per row).  Software pipeline over this warp's rows: the epilogue operands of the NEXT row
+// (global / L2 loads) are requested before the current row is decoded; everything else a row needs
+// -- X, its code words, the tables, the diagonal -- is in shared memory.  All row-dependent global
+// addresses advance by constant strides.
+template <int EPI, int NOPS, int PASS>
+__device__ __forceinline__ void tile_rows(const TileView& tv, const TileRowArgs& ra, const double2* __restrict__ x,
+                                          const EpiArgs& e, const double2 (&u)[NOPS], double& dr, double& di, double& nn) {
+  const int rows = ra.rows, warp = ra.warp;
+  const int64_t batch = ra.batch;
+  const int WT = tv.WT[PASS];
+  int w0[N_KINDS], nw[N_KINDS];
+#pragma unroll
+  for (int k = 0; k < N_KINDS; ++k) {
+    w0[k] = tv.w0[PASS][k] * 16;
+    nw[k] = tv.nw[PASS][k];
+  }
+  const int64_t row_stride = (int64_t)TILE_WARPS * ra.rstep;  // rows between two of this warp's rows
+  const int64_t row_w = ra.row0 + (int64_t)warp * ra.rstep;
+  const double2* xg_row = x + row_w * batch + ra.c0 + ra.lane;  // x[row][c0 + lane]
+  const int64_t el_stride = row_stride * batch;
+  int64_t idx = row_w * batch + ra.c0 + ra.lane;
+  double2* t_ptr = ra.tbuf + row_w * 32 + ra.lane;
+  const int64_t t_stride = row_stride * 32;
+
+  double2 n_t = make_double2(0.0, 0.0), n_y = n_t, n_a = n_t;
+  auto prefetch = [&](const double2* tp, int64_t ix) {
+    if (PASS == 1) {
+      n_t = ld_cg(tp);
+      if (EPI == EPI_MUL) {
+        if (e.betac.x != 0.0 || e.betac.y != 0.0) n_y = ld_noalloc(e.y + ix);
+      } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
+        n_y = ld_noalloc(e.y + ix);
+        n_a = ld_noalloc(e.acc + ix);
+      }
+    }
+  };
+  if (warp < rows) prefetch(t_ptr, idx);
+  for (int s = warp; s < rows; s += TILE_WARPS) {
+    const double2 tv_in = n_t, yv = n_y, av = n_a;
+    if (s + TILE_WARPS < rows) prefetch(t_ptr + t_stride, idx + el_stride);
+    const uint32_t xs_row = ra.xs_base + (uint32_t)s * 512u;
+    const uint32_t cw = ra.codes_base + (uint32_t)(s * WT) * 16u;
+    const double2 xown = lds_f64x2(xs_row);
+    double pr[NOPS], pi[NOPS];
+#pragma unroll
+    for (int l = 0; l < NOPS; ++l) pr[l] = pi[l] = 0.0;
+    tile_list<NOPS, 0, 0>(cw + w0[0], nw[0], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 1) tile_list<NOPS, 0, (NOPS > 1 ? 1 : 0)>(cw + w0[1], nw[1], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 2) tile_list<NOPS, 0, (NOPS > 2 ? 2 : 0)>(cw + w0[2], nw[2], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 1) tile_list<NOPS, 1, 0>(cw + w0[3], nw[3], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    tile_list<NOPS, 2, 0>(cw + w0[4], nw[4], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+    if (PASS == 1) {  // class O: the few couplings that straddle the split, from global memory
+      tile_list<NOPS, 3, 0>(cw + w0[5], nw[5], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+    } else {          // explicit diagonals
+      const double2 d01 = lds_f64x2(ra.diag_base + (uint32_t)s * 32u);
+      pr[0] = fma(d01.x, xown.x, pr[0]);
+      pi[0] = fma(d01.x, xown.y, pi[0]);
+      if (NOPS > 1) {
+        pr[1] = fma(d01.y, xown.x, pr[1]);
+        pi[1] = fma(d01.y, xown.y, pi[1]);
+      }
+      if (NOPS > 2) {
+        const double2 d2 = lds_f64x2(ra.diag_base + (uint32_t)s * 32u + 16u);
+        pr[2] = fma(d2.x, xown.x, pr[2]);
+        pi[2] = fma(d2.x, xown.y, pi[2]);
+      }
+    }
+    double2 hx = tv_in;
+#pragma unroll
+    for (int l = 0; l < NOPS; ++l) {
+      hx.x += u[l].x * pr[l] - u[l].y * pi[l];
+      hx.y += u[l].x * pi[l] + u[l].y * pr[l];
+    }
+    if (PASS == 0) st_cg(t_ptr, hx);
+    else epi_apply<EPI>(e, idx, hx, xown, yv, av, dr, di, nn);
+    xg_row += el_stride;
+    idx += el_stride;
+    t_ptr += t_stride;
+  }
+}
+
 template <int EPI, int NOPS>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
-k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int64_t batch,
+k_spmm_tile(const __grid_constant__ TileView tv, const double2* __restrict__ coef, int coef_stride, int64_t batch,
             const double2* __restrict__ x, EpiArgs e) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // shared memory: X tile | 16-byte table | 32-byte table | the tile's code words | diagonals (pass A)
   double2* s_x = reinterpret_cast<double2*>(smem_raw);  // [rows][32]
   const int max_rows = tv.S > tv.NH ? tv.S : tv.NH;
-  TileEntry* s_tab = reinterpret_cast<TileEntry*>(smem_raw + (size_t)max_rows * 512);
-  // per tile: the rows' code words (pass A: WA8 words; pass B: WB8 + WO8 words) and, in pass A, the diagonals
-  uint4* s_codes = reinterpret_cast<uint4*>(smem_raw + (size_t)max_rows * 512 + (((size_t)tv.n_tab * sizeof(TileEntry) + 15) & ~(size_t)15));
-  const int cwA = tv.WA8, cwB = tv.WB8 + tv.WO8;
-  const int code_words = tv.S * cwA > tv.NH * cwB ? tv.S * cwA : tv.NH * cwB;
+  Entry16* s_tab16 = reinterpret_cast<Entry16*>(smem_raw + (size_t)max_rows * 512);
+  Entry32* s_tab32 = reinterpret_cast<Entry32*>(s_tab16 + tv.n16);
+  uint4* s_codes = reinterpret_cast<uint4*>(s_tab32 + tv.n32);
+  const int code_words = tv.S * tv.WT[0] > tv.NH * tv.WT[1] ? tv.S * tv.WT[0] : tv.NH * tv.WT[1];
   double* s_diag = reinterpret_cast<double*>(s_codes + code_words);  // [S][4] (3 used)
-  for (int j = threadIdx.x; j < tv.n_tab; j += TILE_THREADS) s_tab[j] = tv.tab[j];
+  for (int j = threadIdx.x; j < tv.n16; j += TILE_THREADS) s_tab16[j] = tv.tab16[j];
+  for (int j = threadIdx.x; j < tv.n32; j += TILE_THREADS) s_tab32[j] = tv.tab32[j];
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,6 +302,10 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
   const int64_t ring_elems = tv.n * 32;
   const unsigned long long tgtA = tv.epoch * (unsigned long long)tilesA;
   const unsigned long long tgtB = tv.epoch * (unsigned long long)tilesB;
+  const uint32_t tab16_base = smem_u32(s_tab16), tab32_base = smem_u32(s_tab32);
+  const uint32_t xs_base = smem_u32(s_x) + (uint32_t)lane * 16u;
+  const uint32_t codes_base = smem_u32(s_codes);
+  const uint32_t diag_base = smem_u32(s_diag);
 
   for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
     // decode the item: pass, trajectory chunk, tile
@@ -211,31 +325,23 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
     // row of slot s of this tile: pass A: tile * S + s; pass B: s * S + tile
     const int64_t row0 = pass == 0 ? (int64_t)tile * tv.S : tile;
     const int64_t rstep = pass == 0 ? 1 : tv.S;
+    const int WT = tv.WT[pass];
 
-    // 1. the tile of X -> shared memory (a warp copies one row's 512 B per instruction)
+    // 1. the tile of X -> shared memory (a warp copies one row's 512 B per instruction) ...
     for (int idx = threadIdx.x; idx < rows * 32; idx += TILE_THREADS) {
       const int s = idx >> 5, j = idx & 31;
       cp_async16(s_x + idx, x + (row0 + s * rstep) * batch + c0 + j);
     }
     // ... and the code words of its rows (and the diagonals in pass A)
     {
-      const int W8 = pass == 0 ? tv.WA8 : tv.WB8;
-      const int WT = pass == 0 ? cwA : cwB;
-      const uint4* src = pass == 0 ? tv.codesA : tv.codesB;
-      for (int idx = threadIdx.x; idx < rows * W8; idx += TILE_THREADS) {
-        const int s = idx / W8, k = idx - s * W8;
-        cp_async16(s_codes + s * WT + k, src + (row0 + s * rstep) * W8 + k);
+      const uint4* src = tv.codes[pass];
+      for (int idx = threadIdx.x; idx < rows * WT; idx += TILE_THREADS) {
+        const int s = idx / WT, k = idx - s * WT;
+        cp_async16(s_codes + idx, src + (row0 + s * rstep) * WT + k);
       }
-      if (pass == 1)
-        for (int idx = threadIdx.x; idx < rows * tv.WO8; idx += TILE_THREADS) {
-          const int s = idx / tv.WO8, k = idx - s * tv.WO8;
-          cp_async16(s_codes + s * WT + W8 + k, tv.codesO + (row0 + s * rstep) * tv.WO8 + k);
-        }
       if (pass == 0)
-        for (int idx = threadIdx.x; idx < rows * 2; idx += TILE_THREADS) {  // 32 bytes per row: d0 d1 | d2 pad
-          const int s = idx >> 1, k = idx & 1;
-          cp_async16(s_diag + s * 4 + 2 * k, tv.diag + (row0 + s) * 4 + 2 * k);
-        }
+        for (int idx = threadIdx.x; idx < rows * 2; idx += TILE_THREADS)  // 32 bytes per row: d0 d1 | d2 pad
+          cp_async16(s_diag + idx * 2, tv.diag + row0 * 4 + idx * 2);
     }
     // 2. this lane's coefficients (times i for a purely imaginary operator)
     double2 u[NOPS];
@@ -256,78 +362,23 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
     __syncthreads();
 
     double2* tbuf = tv.tring + (g % TILE_RING) * ring_elems;
-    const uint32_t tab_base = smem_u32(s_tab);
-    const uint32_t xs_base = smem_u32(s_x) + (uint32_t)lane * 16u;
-    const int W8 = pass == 0 ? tv.WA8 : tv.WB8;
     double dr = 0.0, di = 0.0, nn = 0.0;
-
-    // Software pipeline over this warp's rows: the epilogue operands of the NEXT row (global / L2
-    // loads) are requested before the current row is decoded; everything else a row needs -- X,
-    // its code words, the table, the diagonal -- is in shared memory.  All row-dependent global
-    // addresses advance by constant strides.
-    const int64_t row_stride = (int64_t)TILE_WARPS * rstep;            // rows between two of this warp's rows
-    const int64_t row_w = row0 + (int64_t)warp * rstep;
-    const double2* xg_row = x + row_w * batch + c0 + lane;             // x[row][c0 + lane]
-    const int64_t el_stride = row_stride * batch;
-    int64_t idx = row_w * batch + c0 + lane;
-    const double2* t_ptr = tbuf + row_w * 32 + lane;
-    const int64_t t_stride = row_stride * 32;
-    const int WT = pass == 0 ? cwA : cwB;
-    const uint32_t codes_base = smem_u32(s_codes);
-    const uint32_t diag_base = smem_u32(s_diag);
-
-    double2 n_t = make_double2(0.0, 0.0), n_y = n_t, n_a = n_t;
-    auto prefetch = [&](const double2* tp, int64_t ix) {
-      if (pass == 1) {
-        n_t = ld_cg(tp);
-        if (EPI == EPI_MUL) {
-          if (e.betac.x != 0.0 || e.betac.y != 0.0) n_y = ld_noalloc(e.y + ix);
-        } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
-          n_y = ld_noalloc(e.y + ix);
-          n_a = ld_noalloc(e.acc + ix);
-        }
-      }
-    };
-    if (warp < rows) prefetch(t_ptr, idx);
-    for (int s = warp; s < rows; s += TILE_WARPS) {
-      const double2 tv_in = n_t, yv = n_y, av = n_a;
-      if (s + TILE_WARPS < rows) prefetch(t_ptr + t_stride, idx + el_stride);
-      const uint32_t xs_row = xs_base + (uint32_t)s * 512u;
-      const uint32_t cw = codes_base + (uint32_t)(s * WT) * 16u;
-      const double2 xown = lds_f64x2(xs_row);
-      double pr[NOPS], pi[NOPS];
-#pragma unroll
-      for (int l = 0; l < NOPS; ++l) pr[l] = pi[l] = 0.0;
-      for (int k = 0; k < W8; ++k) tile_word<NOPS, false>(lds_u32x4(cw + 16u * k), tab_base, xs_row, xg_row, batch, pr, pi);
-      if (pass == 1) {  // class O: the few couplings that straddle the split, from global memory
-        for (int k = 0; k < tv.WO8; ++k)
-          tile_word<NOPS, true>(lds_u32x4(cw + 16u * (W8 + k)), tab_base, xs_row, xg_row, batch, pr, pi);
-      } else {          // explicit diagonals
-        const double2 d01 = lds_f64x2(diag_base + (uint32_t)s * 32u);
-        pr[0] = fma(d01.x, xown.x, pr[0]);
-        pi[0] = fma(d01.x, xown.y, pi[0]);
-        if (NOPS > 1) {
-          pr[1] = fma(d01.y, xown.x, pr[1]);
-          pi[1] = fma(d01.y, xown.y, pi[1]);
-        }
-        if (NOPS > 2) {
-          const double2 d2 = lds_f64x2(diag_base + (uint32_t)s * 32u + 16u);
-          pr[2] = fma(d2.x, xown.x, pr[2]);
-          pi[2] = fma(d2.x, xown.y, pi[2]);
-        }
-      }
-      double2 hx = tv_in;
-#pragma unroll
-      for (int l = 0; l < NOPS; ++l) {
-        hx.x += u[l].x * pr[l] - u[l].y * pi[l];
-        hx.y += u[l].x * pi[l] + u[l].y * pr[l];
-      }
-      if (pass == 0) st_cg(const_cast<double2*>(t_ptr), hx);
-      else epi_apply<EPI>(e, idx, hx, xown, yv, av, dr, di, nn);
-      xg_row += el_stride;
-      idx += el_stride;
-      t_ptr += t_stride;
-    }
+    TileRowArgs ra;
+    ra.rows = rows;
+    ra.warp = warp;
+    ra.lane = lane;
+    ra.row0 = row0;
+    ra.rstep = rstep;
+    ra.c0 = c0;
+    ra.batch = batch;
+    ra.tbuf = tbuf;
+    ra.tab16_base = tab16_base;
+    ra.tab32_base = tab32_base;
+    ra.xs_base = xs_base;
+    ra.codes_base = codes_base;
+    ra.diag_base = diag_base;
+    if (pass == 0) tile_rows<EPI, NOPS, 0>(tv, ra, x, e, u, dr, di, nn);
+    else tile_rows<EPI, NOPS, 1>(tv, ra, x, e, u, dr, di, nn);
     if (pass == 1 && epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, c0 + lane, dr, di, nn);
 
     // every warp is done with the tile (the next item overwrites it) and has issued its stores
@@ -344,18 +395,18 @@ k_spmm_tile(TileView tv, const double2* __restrict__ coef, int coef_stride, int6
 // ---------------------------------------------------------------------------------------
 
 // shared memory of one CTA: X tile + table + the tile's code words + the diagonals (pass A)
-static size_t tile_smem_bytes(const qptile::TileFormat& f, int n_tab) {
+static size_t tile_smem_bytes(const qptile::TileFormat& f, size_t n16, size_t n32) {
   const size_t rows = (size_t)std::max(f.S, f.NH);
-  const size_t code_words = std::max((size_t)f.S * (f.WA / 8), (size_t)f.NH * (f.WB / 8 + f.WO / 8));
-  return rows * 512 + (((size_t)n_tab * sizeof(TileEntry) + 15) & ~(size_t)15) + code_words * 16 + (size_t)f.S * 32;
+  const size_t code_words = std::max((size_t)f.S * f.WT[0], (size_t)f.NH * f.WT[1]);
+  return rows * 512 + n16 * sizeof(Entry16) + n32 * sizeof(Entry32) + code_words * 16 + (size_t)f.S * 32;
 }
 
 void qp_tile_free(qp_tile_s* t) {
   if (!t) return;
-  cudaFree(t->d_tab);
-  cudaFree(t->d_codesA);
-  cudaFree(t->d_codesB);
-  cudaFree(t->d_codesO);
+  cudaFree(t->d_tab16);
+  cudaFree(t->d_tab32);
+  cudaFree(t->d_codes[0]);
+  cudaFree(t->d_codes[1]);
   cudaFree(t->d_diag);
   cudaFree(t->d_ring);
   cudaFree(t->d_done);
@@ -385,21 +436,20 @@ static int32_t tile_ensure(qp_gen_t gen) {
   }
   qptile::TileFormat& f = t->meta;
   if (!qptile::build(f, n, gen->n_ops, h_ptr.data(), h_col.data(), h_val.data())) { t->why = f.why; return QP_OK; }
-  const int64_t off_diag = f.n_A + f.n_B + f.n_O;
-  if (4 * f.n_O > off_diag) {  // mostly unstructured: the tiles would serve too few of the loads
+  const int64_t off_diag = f.n_A() + f.n_B() + f.n_O();
+  if (4 * f.n_O() > off_diag) {  // mostly unstructured: the tiles would serve too few of the loads
     t->why = "more than a quarter of the entries straddle the split";
     return QP_OK;
   }
-  if (tile_smem_bytes(f, (int)f.table.size()) > (size_t)224 * 1024) { t->why = "tile + table + code words exceed shared memory"; return QP_OK; }
+  if (tile_smem_bytes(f, f.tab16.size(), f.tab32.size()) > (size_t)224 * 1024) { t->why = "tile + table + code words exceed shared memory"; return QP_OK; }
   auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e1 = cudaMalloc(dst, bytes ? bytes : 16);
     if (e1 == cudaSuccess && bytes) e1 = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     return e1;
   };
-  QP_CUDA(ctx, up((void**)&t->d_tab, f.table.data(), f.table.size() * sizeof(TileEntry)));
-  QP_CUDA(ctx, up((void**)&t->d_codesA, f.codesA.data(), f.codesA.size() * sizeof(uint16_t)));
-  QP_CUDA(ctx, up((void**)&t->d_codesB, f.codesB.data(), f.codesB.size() * sizeof(uint16_t)));
-  QP_CUDA(ctx, up((void**)&t->d_codesO, f.codesO.data(), f.codesO.size() * sizeof(uint16_t)));
+  QP_CUDA(ctx, up((void**)&t->d_tab16, f.tab16.data(), f.tab16.size() * sizeof(Entry16)));
+  QP_CUDA(ctx, up((void**)&t->d_tab32, f.tab32.data(), f.tab32.size() * sizeof(Entry32)));
+  for (int p = 0; p < 2; ++p) QP_CUDA(ctx, up((void**)&t->d_codes[p], f.codes[p].data(), f.codes[p].size() * sizeof(uint16_t)));
   {
     std::vector<double> d4((size_t)n * 4, 0.0);
     for (int64_t r = 0; r < n; ++r)
@@ -407,11 +457,11 @@ static int32_t tile_ensure(qp_gen_t gen) {
     QP_CUDA(ctx, up((void**)&t->d_diag, d4.data(), d4.size() * sizeof(double)));
   }
   QP_CUDA(ctx, cudaMalloc(&t->d_ring, sizeof(double2) * (size_t)TILE_RING * (size_t)n * 32));
-  t->n_tab = (int)f.table.size();
+  t->n16 = (int)f.tab16.size();
+  t->n32 = (int)f.tab32.size();
   // the big host arrays are not needed any more
-  std::vector<uint16_t>().swap(f.codesA);
-  std::vector<uint16_t>().swap(f.codesB);
-  std::vector<uint16_t>().swap(f.codesO);
+  std::vector<uint16_t>().swap(f.codes[0]);
+  std::vector<uint16_t>().swap(f.codes[1]);
   std::vector<double>().swap(f.diag);
   t->ok = true;
   return QP_OK;
@@ -438,15 +488,19 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
     t->epoch = 0;
   }
   TileView tv;
-  tv.tab = t->d_tab;
-  tv.n_tab = t->n_tab;
-  tv.codesA = t->d_codesA;
-  tv.codesB = t->d_codesB;
-  tv.codesO = t->d_codesO;
+  tv.tab16 = t->d_tab16;
+  tv.tab32 = t->d_tab32;
+  tv.n16 = t->n16;
+  tv.n32 = t->n32;
+  for (int p = 0; p < 2; ++p) {
+    tv.codes[p] = t->d_codes[p];
+    tv.WT[p] = f.WT[p];
+    for (int k = 0; k < N_KINDS; ++k) {
+      tv.w0[p][k] = f.word0[p][k];
+      tv.nw[p][k] = f.W[p][k] / 8;
+    }
+  }
   tv.diag = t->d_diag;
-  tv.WA8 = f.WA / 8;
-  tv.WB8 = f.WB / 8;
-  tv.WO8 = f.WO / 8;
   tv.S = f.S;
   tv.NH = f.NH;
   tv.n_ops = f.n_ops;
@@ -457,7 +511,7 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   tv.doneB = t->d_done + t->chunk_cap;
   tv.epoch = ++t->epoch;
   auto kern = k_spmm_tile<EPI, NOPS>;
-  const size_t smem = tile_smem_bytes(f, t->n_tab);
+  const size_t smem = tile_smem_bytes(f, (size_t)t->n16, (size_t)t->n32);
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     ctx->smem_configured.insert((const void*)kern);
@@ -521,11 +575,11 @@ int32_t qp_tile_info(qp_gen_t gen, int32_t* available, int32_t* S, int32_t* NH, 
   if (available) *available = t->ok ? 1 : 0;
   if (S) *S = t->meta.S;
   if (NH) *NH = t->meta.NH;
-  if (n_table) *n_table = t->n_tab;
+  if (n_table) *n_table = t->n16 + t->n32;
   if (entries) {
-    entries[0] = t->meta.n_A;
-    entries[1] = t->meta.n_B;
-    entries[2] = t->meta.n_O;
+    entries[0] = t->meta.n_A();
+    entries[1] = t->meta.n_B();
+    entries[2] = t->meta.n_O();
     entries[3] = t->meta.n_diag;
   }
   return QP_OK;

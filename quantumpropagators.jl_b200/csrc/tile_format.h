@@ -3,8 +3,8 @@
 // The batched application  Y[r, b] = sum_l u_l^(b) sum_c (H_l)[r, c] X[c, b]  of a generator whose
 // matrices come from tensor products of few-level operators is bounded by how often a value of X is
 // fetched again (every column is referenced by ~30 rows; through L1/L2 that was 6 x
-// the algorithmic traffic on config 3).  Here the index is split  r = hi * S + lo  (S a power of two
-// near sqrt(N)) and every off-diagonal entry (r, c) is put in one of three classes:
+// the algorithmic traffic on config 3).  Here the index is split  r = hi * S + lo  (S a power of two,
+// chosen between two tensor factors) and every off-diagonal entry (r, c) is put in one of three classes:
 //
 //   A  r and c lie in the same block of S consecutive rows        (c / S == r / S)
 //   B  r and c have the same position inside their blocks         (c % S == r % S)
@@ -14,10 +14,18 @@
 // N/S rows {hi * S + lo : hi} of one lo x 32 trajectories).  A tile of X is brought into shared
 // memory ONCE and every class-A (pass A) or class-B (pass B) reference is served from there; class
 // O entries are gathered from global memory in pass B; the diagonals are kept as explicit vectors.
-// Entries of different operators that sit in the same column are merged: one table entry holds the
-// column offset and one real number per operator (generators whose operators are purely real or
-// purely imaginary -- the factor i of an imaginary operator moves into its coefficient), so a
-// shared column costs one load.  A row is a list of 16-bit codes into that table (code 0 = padding).
+//
+// Entries of different operators that sit in the same column are merged (one load of X serves them
+// all); operators must be purely real or purely imaginary (the factor i of an imaginary operator
+// moves into its coefficient), so a value is ONE real number.  A merged entry has a KIND, and every
+// row keeps one list of 16-bit codes per kind (code 0 = padding), so that the inner loops of the
+// kernels contain no per-entry decisions:
+//
+//   S_l   one operator l only                        table entry 16 B {v, off}:   2 FMA into sum l
+//   P     the operator pair (p1, p2) with |v2| = |v1| (quadrature controls: a + a^+ and i(a^+ - a))
+//                                                    table entry 16 B {v, off, sign}: 4 FMA
+//   G     anything else                              table entry 32 B {v0, off, v1, v2}: 2 n_ops FMA
+//   O     class-O entries (always the 32-byte form), X from global memory
 //
 // Replaces (for B > 1 states sharing one generator): mul!(C, A::Operator, B, alpha, beta) of the
 // reference, src/generators.jl:634-645, called once per Chebyshev term from src/cheby.jl:175,189.
@@ -37,31 +45,44 @@ namespace qptile {
 constexpr int TILE_MAX_OPS = 3;
 constexpr int TILE_TRAJ = 32;          // trajectories per tile = one warp
 constexpr int TILE_MAX_ROWS = 256;     // rows per tile: 256 x 32 x 16 B = 128 KB of shared memory
-constexpr int TILE_MAX_TABLE = 2048;   // 16-bit codes; 2048 x 32 B = 64 KB of shared memory next to the 128 KB tile
-constexpr uint32_t TILE_KIND_O = 1u << 8;
+constexpr int TILE_MAX_TABLE = 2048;   // entries per table (16-bit codes; bounded by shared memory)
+constexpr int TILE_ROW_BYTES = TILE_TRAJ * 16;
 
-struct TileEntry {      // 32 bytes, read with two 16-byte shared-memory loads: {v0, off, km} {v1, v2}
-  double v0;               // real representation of the value of operator 0 (0: operator absent)
-  int32_t off;             // class A / B: byte offset inside the shared-memory tile (slot delta * 512);
-                           // class O: row delta (c - r)
-  uint32_t km;             // bits 0..2: operators present; TILE_KIND_O: class O
-  double v1, v2;           // operators 1 and 2
+// kinds = lists of a row; pass A uses S0 S1 S2 P G, pass B the same plus O
+enum Kind { K_S0 = 0, K_S1 = 1, K_S2 = 2, K_P = 3, K_G = 4, K_O = 5, N_KINDS = 6 };
+
+struct Entry16 {   // kinds S_l and P
+  double v;
+  int32_t off;     // byte offset inside the shared-memory tile (slot delta * 512)
+  uint32_t neg2;   // kind P: 0x80000000 if the second operator's value is -v (XORed into the sign), else 0
+};
+struct Entry32 {   // kinds G and O: {v0, off, pad} {v1, v2}
+  double v0;
+  int32_t off;     // G: byte offset inside the tile; O: row delta (c - r)
+  uint32_t pad;
+  double v1, v2;
   double v(int l) const { return l == 0 ? v0 : l == 1 ? v1 : v2; }
 };
-static_assert(sizeof(TileEntry) == 32, "TileEntry must be 32 bytes");
+static_assert(sizeof(Entry16) == 16 && sizeof(Entry32) == 32, "table entry sizes");
 
 struct TileFormat {
   int64_t n = 0;
   int S = 0, NH = 0, n_ops = 0;
   unsigned imag_ops = 0;            // bit l: operator l is purely imaginary (v = Im)
-  int WA = 0, WB = 0, WO = 0;       // codes per row: class A (pass A), class B and class O (pass B); multiples of 8
-  std::vector<TileEntry> table;     // [n_table], entry 0 = padding
-  std::vector<uint16_t> codesA;     // [n][WA]
-  std::vector<uint16_t> codesB;     // [n][WB]
-  std::vector<uint16_t> codesO;     // [n][WO]
+  int p1 = 0, p2 = 1;               // the operator pair of kind P
+  int W[2][N_KINDS] = {{0}};        // codes per row, per pass and kind (multiples of 8; pass A has no O)
+  int WT[2] = {0, 0};               // 16-byte code words per row and pass (all kinds back to back)
+  int word0[2][N_KINDS] = {{0}};    // first word of a kind's list inside the row's words
+  std::vector<Entry16> tab16;       // entry 0 = padding
+  std::vector<Entry32> tab32;       // entry 0 = padding
+  std::vector<uint16_t> codes[2];   // [n][WT * 8] per pass
   std::vector<double> diag;         // [n][TILE_MAX_OPS] real representation of the main diagonals
-  int64_t n_A = 0, n_B = 0, n_O = 0, n_diag = 0;  // merged entries per class
+  int64_t count[2][N_KINDS] = {{0}};  // merged entries per pass and kind
+  int64_t n_diag = 0;
   std::string why;                  // reason when build() returns false
+  int64_t n_A() const { int64_t s = 0; for (int k = 0; k < K_O; ++k) s += count[0][k]; return s; }
+  int64_t n_B() const { int64_t s = 0; for (int k = 0; k < K_O; ++k) s += count[1][k]; return s; }
+  int64_t n_O() const { return count[1][K_O]; }
 };
 
 inline int choose_split(int64_t n) {
@@ -130,12 +151,21 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
   }
   if (has_re & has_im) { f.why = "an operator has both real and imaginary values"; return false; }
   f.imag_ops = has_im;
+  // the pair of kind P: the last two operators (drift first, controls last: the quadrature pair)
+  f.p1 = n_ops >= 2 ? n_ops - 2 : 0;
+  f.p2 = n_ops >= 2 ? n_ops - 1 : 0;
+  const uint32_t pair_mask = n_ops >= 2 ? ((1u << f.p1) | (1u << f.p2)) : 0u;
 
-  f.table.assign(1, TileEntry{0.0, 0, 0u, 0.0, 0.0});
+  f.tab16.assign(1, Entry16{0.0, 0, 0u});
+  f.tab32.assign(1, Entry32{0.0, 0, 0u, 0.0, 0.0});
   f.diag.assign((size_t)n * TILE_MAX_OPS, 0.0);
-  using Key = std::tuple<uint32_t, int32_t, uint64_t, uint64_t, uint64_t>;
-  std::map<Key, uint16_t> dict;
-  std::vector<std::vector<uint16_t>> rowsA((size_t)n), rowsB((size_t)n), rowsO((size_t)n);
+  using Key16 = std::tuple<int32_t, uint64_t, uint32_t>;
+  using Key32 = std::tuple<int, int32_t, uint64_t, uint64_t, uint64_t>;
+  std::map<Key16, uint16_t> dict16;
+  std::map<Key32, uint16_t> dict32;
+  std::vector<std::vector<uint16_t>> lists[2][N_KINDS];
+  for (int p = 0; p < 2; ++p)
+    for (int k = 0; k < N_KINDS; ++k) lists[p][k].resize((size_t)n);
   struct Ent { int64_t col; int op; double v; };
   std::vector<Ent> row;
   auto bits = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
@@ -151,63 +181,84 @@ inline bool build(TileFormat& f, int64_t n, int n_ops, const uint32_t* mptr, con
     while (i < row.size()) {
       const int64_t c = row[i].col;
       double v[TILE_MAX_OPS] = {0.0, 0.0, 0.0};
+      for (; i < row.size() && row[i].col == c; ++i) v[row[i].op] += row[i].v;  // duplicates add up (SparseArrays semantics)
       uint32_t mask = 0;
-      for (; i < row.size() && row[i].col == c; ++i) {
-        v[row[i].op] += row[i].v;  // duplicates within one operator add up (SparseArrays semantics)
-        mask |= 1u << row[i].op;
-      }
+      for (int l = 0; l < TILE_MAX_OPS; ++l)
+        if (v[l] != 0.0) mask |= 1u << l;
       if (c == r) {
         for (int l = 0; l < TILE_MAX_OPS; ++l) f.diag[(size_t)r * TILE_MAX_OPS + l] += v[l];
         ++f.n_diag;
         continue;
       }
-      uint32_t km = mask;
+      if (mask == 0) continue;  // stored zeros
+      int pass, kind;
       int32_t off;
-      bool passA = false, isO = false;
       if (c / S == r / S) {  // class A: same block of S rows
-        off = (int32_t)(c - r) * (TILE_TRAJ * 16);
-        passA = true;
-        ++f.n_A;
+        pass = 0;
+        off = (int32_t)(c - r) * TILE_ROW_BYTES;
+        kind = -1;
       } else if (c % S == r % S) {  // class B: same position in another block
-        off = (int32_t)((c - r) / S) * (TILE_TRAJ * 16);
-        ++f.n_B;
+        pass = 1;
+        off = (int32_t)((c - r) / S) * TILE_ROW_BYTES;
+        kind = -1;
       } else {
+        pass = 1;
         off = (int32_t)(c - r);
-        km |= TILE_KIND_O;
-        isO = true;
-        ++f.n_O;
+        kind = K_O;
       }
-      // pass A and pass B entries never share a table entry (their offsets mean different things)
-      const Key key{km | (passA ? 1u << 16 : 0u), off, bits(v[0]), bits(v[1]), bits(v[2])};
-      auto it = dict.find(key);
       uint16_t code;
-      if (it == dict.end()) {
-        if ((int)f.table.size() >= TILE_MAX_TABLE) { f.why = "more than 2047 distinct (offset, values) entries"; return false; }
-        code = (uint16_t)f.table.size();
-        f.table.push_back(TileEntry{v[0], off, km, v[1], v[2]});
-        dict.emplace(key, code);
-      } else {
-        code = it->second;
+      if (kind != K_O) {
+        const bool single = (mask & (mask - 1)) == 0;
+        const bool pair = !single && mask == pair_mask && std::fabs(v[f.p1]) == std::fabs(v[f.p2]);
+        if (single || pair) {
+          const int l = single ? (mask == 1 ? 0 : mask == 2 ? 1 : 2) : f.p1;
+          kind = single ? K_S0 + l : K_P;
+          const uint32_t neg2 = (pair && (std::signbit(v[f.p1]) != std::signbit(v[f.p2]))) ? 0x80000000u : 0u;
+          const Key16 key{off, bits(v[l]), neg2};
+          auto it = dict16.find(key);
+          if (it == dict16.end()) {
+            if ((int)f.tab16.size() >= TILE_MAX_TABLE) { f.why = "more than 2047 distinct (offset, value) entries"; return false; }
+            code = (uint16_t)f.tab16.size();
+            f.tab16.push_back(Entry16{v[l], off, neg2});
+            dict16.emplace(key, code);
+          } else {
+            code = it->second;
+          }
+        } else {
+          kind = K_G;
+        }
       }
-      (passA ? rowsA : isO ? rowsO : rowsB)[(size_t)r].push_back(code);
+      if (kind == K_G || kind == K_O) {
+        const Key32 key{kind, off, bits(v[0]), bits(v[1]), bits(v[2])};
+        auto it = dict32.find(key);
+        if (it == dict32.end()) {
+          if ((int)f.tab32.size() >= TILE_MAX_TABLE) { f.why = "more than 2047 distinct (offset, values) entries"; return false; }
+          code = (uint16_t)f.tab32.size();
+          f.tab32.push_back(Entry32{v[0], off, 0u, v[1], v[2]});
+          dict32.emplace(key, code);
+        } else {
+          code = it->second;
+        }
+      }
+      lists[pass][kind][(size_t)r].push_back(code);
+      ++f.count[pass][kind];
     }
   }
-  size_t wa = 0, wb = 0, wo = 0;
-  for (int64_t r = 0; r < n; ++r) {
-    wa = std::max(wa, rowsA[(size_t)r].size());
-    wb = std::max(wb, rowsB[(size_t)r].size());
-    wo = std::max(wo, rowsO[(size_t)r].size());
-  }
-  f.WA = (int)((wa + 7) / 8 * 8);
-  f.WB = (int)((wb + 7) / 8 * 8);
-  f.WO = (int)((wo + 7) / 8 * 8);
-  f.codesA.assign((size_t)n * f.WA, 0);
-  f.codesB.assign((size_t)n * f.WB, 0);
-  f.codesO.assign((size_t)n * f.WO, 0);
-  for (int64_t r = 0; r < n; ++r) {
-    std::copy(rowsA[(size_t)r].begin(), rowsA[(size_t)r].end(), f.codesA.begin() + (size_t)r * f.WA);
-    std::copy(rowsB[(size_t)r].begin(), rowsB[(size_t)r].end(), f.codesB.begin() + (size_t)r * f.WB);
-    std::copy(rowsO[(size_t)r].begin(), rowsO[(size_t)r].end(), f.codesO.begin() + (size_t)r * f.WO);
+  for (int p = 0; p < 2; ++p) {
+    int words = 0;
+    for (int k = 0; k < N_KINDS; ++k) {
+      size_t w = 0;
+      for (int64_t r = 0; r < n; ++r) w = std::max(w, lists[p][k][(size_t)r].size());
+      f.W[p][k] = (int)((w + 7) / 8 * 8);
+      f.word0[p][k] = words;
+      words += f.W[p][k] / 8;
+    }
+    f.WT[p] = words;
+    f.codes[p].assign((size_t)n * words * 8, 0);
+    for (int k = 0; k < N_KINDS; ++k)
+      for (int64_t r = 0; r < n; ++r)
+        std::copy(lists[p][k][(size_t)r].begin(), lists[p][k][(size_t)r].end(),
+                  f.codes[p].begin() + ((size_t)r * words + f.word0[p][k]) * 8);
   }
   return true;
 }
@@ -230,28 +281,40 @@ inline void apply_host(const TileFormat& f, int64_t B, const double* u_reim /*[n
   };
   for (int pass = 0; pass < 2; ++pass) {
     for (int64_t r = 0; r < n; ++r) {
-      // slot of row r in its tile
-      const int64_t slot = pass == 0 ? r % S : r / S;
+      const int64_t slot = pass == 0 ? r % S : r / S;  // slot of row r in its tile
+      auto tile_col = [&](int32_t off) {
+        const int64_t s2 = slot + off / TILE_ROW_BYTES;
+        return pass == 0 ? (r / S) * S + s2 : s2 * S + r % S;
+      };
       for (int64_t b = 0; b < B; ++b) {
         double pr[TILE_MAX_OPS] = {0, 0, 0}, pi[TILE_MAX_OPS] = {0, 0, 0};
-        for (int list = 0; list < (pass == 0 ? 1 : 2); ++list) {
-          const int W = pass == 0 ? f.WA : list == 0 ? f.WB : f.WO;
-          const std::vector<uint16_t>& codes = pass == 0 ? f.codesA : list == 0 ? f.codesB : f.codesO;
-          for (int j = 0; j < W; ++j) {
-            const uint16_t code = codes[(size_t)r * W + j];
-            if (code == 0) continue;
-            const TileEntry& e = f.table[code];
-            int64_t c;
-            if (e.km & TILE_KIND_O) {
-              c = r + e.off;
+        for (int kind = 0; kind < N_KINDS; ++kind) {
+          const uint16_t* cw = f.codes[pass].data() + ((size_t)r * f.WT[pass] + f.word0[pass][kind]) * 8;
+          for (int j = 0; j < f.W[pass][kind]; ++j) {
+            const uint16_t code = cw[j];
+            if (code == 0) break;  // lists are packed at the front
+            if (kind <= K_P) {
+              const Entry16& e = f.tab16[code];
+              const int64_t c = tile_col(e.off);
+              const double xr = x_reim[2 * ((size_t)c * B + b)], xi = x_reim[2 * ((size_t)c * B + b) + 1];
+              if (kind == K_P) {
+                const double v2 = e.neg2 ? -e.v : e.v;
+                pr[f.p1] += e.v * xr;
+                pi[f.p1] += e.v * xi;
+                pr[f.p2] += v2 * xr;
+                pi[f.p2] += v2 * xi;
+              } else {
+                pr[kind] += e.v * xr;
+                pi[kind] += e.v * xi;
+              }
             } else {
-              const int64_t s2 = slot + e.off / (TILE_TRAJ * 16);
-              c = pass == 0 ? (r / S) * S + s2 : s2 * S + r % S;
-            }
-            const double xr = x_reim[2 * ((size_t)c * B + b)], xi = x_reim[2 * ((size_t)c * B + b) + 1];
-            for (int l = 0; l < f.n_ops; ++l) {  // absent operators have v = 0 (the kernels multiply unconditionally)
-              pr[l] += e.v(l) * xr;
-              pi[l] += e.v(l) * xi;
+              const Entry32& e = f.tab32[code];
+              const int64_t c = kind == K_O ? r + e.off : tile_col(e.off);
+              const double xr = x_reim[2 * ((size_t)c * B + b)], xi = x_reim[2 * ((size_t)c * B + b) + 1];
+              for (int l = 0; l < f.n_ops; ++l) {  // absent operators have v = 0 (the kernels multiply unconditionally)
+                pr[l] += e.v(l) * xr;
+                pi[l] += e.v(l) * xi;
+              }
             }
           }
         }
@@ -269,13 +332,12 @@ inline void apply_host(const TileFormat& f, int64_t B, const double* u_reim /*[n
           hr += ur * pr[l] - ui * pi[l];
           hi += ur * pi[l] + ui * pr[l];
         }
-        double* dst = pass == 0 ? &t[2 * ((size_t)r * B + b)] : &y_reim[2 * ((size_t)r * B + b)];
         if (pass == 0) {
-          dst[0] = hr;
-          dst[1] = hi;
+          t[2 * ((size_t)r * B + b)] = hr;
+          t[2 * ((size_t)r * B + b) + 1] = hi;
         } else {
-          dst[0] = t[2 * ((size_t)r * B + b)] + hr;
-          dst[1] = t[2 * ((size_t)r * B + b) + 1] + hi;
+          y_reim[2 * ((size_t)r * B + b)] = t[2 * ((size_t)r * B + b)] + hr;
+          y_reim[2 * ((size_t)r * B + b) + 1] = t[2 * ((size_t)r * B + b) + 1] + hi;
         }
       }
     }

@@ -10,14 +10,16 @@ extern "C" int tilefmt_apply(long long n, int n_ops, const unsigned* mptr, const
   qptile::apply_host(f, B, u, x, y);
   stats[0] = f.S;
   stats[1] = f.NH;
-  stats[2] = f.WA;
-  stats[3] = f.WB;
-  stats[4] = (long long)f.table.size();
-  stats[5] = f.n_A;
-  stats[6] = f.n_B;
-  stats[7] = f.n_O;
+  stats[2] = f.WT[0];
+  stats[3] = f.WT[1];
+  stats[4] = (long long)(f.tab16.size() + f.tab32.size());
+  stats[5] = f.n_A();
+  stats[6] = f.n_B();
+  stats[7] = f.n_O();
   stats[8] = f.n_diag;
   stats[9] = f.imag_ops;
+  stats[10] = f.count[0][qptile::K_P] + f.count[1][qptile::K_P];
+  stats[11] = f.count[0][qptile::K_G] + f.count[1][qptile::K_G];
   return 0;
 }
 

@@ -47,7 +47,7 @@ def run(lib, ops, B, rng, S=0):
     u = rng.standard_normal((len(ops), B)) + 1j * rng.standard_normal((len(ops), B))
     x = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
     y = np.zeros((n, B), dtype=np.complex128)
-    stats = (C.c_longlong * 10)()
+    stats = (C.c_longlong * 12)()
     P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     rc = lib.tilefmt_apply(C.c_longlong(n), len(ops), P(ptr), P(colop), P(val), C.c_longlong(B), P(u), P(x), P(y), stats, S)
     if rc != 0:
@@ -75,8 +75,9 @@ def test_transmon_chain_classes(lib):
     H0, H1, H2 = qp.workloads.transmon_chain(4, 4)
     err, st = run(lib, [H0, H1, H2], 8, np.random.default_rng(1))
     assert err < 1e-14
-    S, NH, WA, WB, n_tab, nA, nB, nO, nD, imag = st
+    S, NH, WA, WB, n_tab, nA, nB, nO, nD, imag, nP, nG = st
     assert (S, NH) == (16, 16) and imag == 0b100          # H2 = i sum(a^+ - a) is purely imaginary
+    assert nP == H1.nnz - 0 and nG == 0                   # every control entry is a quadrature pair (|v1| = |v2|)
     assert 0 < nO < 0.2 * (nA + nB)                        # only the (1,2) hop straddles the split
     merged = nA + nB + nO + nD
     assert merged < H0.nnz + H1.nnz + H2.nnz              # H1 / H2 columns are shared
@@ -106,7 +107,7 @@ def test_unstructured_matrices(lib, n, B, S):
     A2 = (sp.csr_matrix(A0) != 0).astype(np.float64) * 0.5 + sp.eye(n)   # same columns as A0 + a diagonal
     err, st = run(lib, [sp.csr_matrix(A0), A1, sp.csr_matrix(A2)], B, rng, S)
     assert err is not None and err < 1e-13
-    assert st[9] == 0b010
+    assert st[9] == 0b010 and st[11] > 0                   # A0 / A2 share columns with unequal values: generic kind
 
 
 def test_refusals(lib):
