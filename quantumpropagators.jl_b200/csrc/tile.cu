@@ -54,6 +54,14 @@ struct TileView {
   unsigned long long epoch;      // 1-based launch number of this view
 };
 
+// Small 16-byte tables travel as a kernel parameter (constant bank): a warp-uniform look-up is then
+// a constant-cache access instead of a 2-wavefront shared-memory broadcast (the shared-memory pipe is
+// what bounds this kernel).
+constexpr int TILE_CTAB = 448;  // 7 KB of the 32 KB parameter space
+struct ConstTab {
+  Entry16 e[TILE_CTAB];
+};
+
 struct qp_tile_s {
   bool ok = false;
   std::string why;
@@ -68,6 +76,7 @@ struct qp_tile_s {
   int64_t chunks_cur = 0;  // chunk count the counters have been counting with since their last reset
   unsigned long long epoch = 0;
   int n16 = 0, n32 = 0;
+  ConstTab* h_ctab = nullptr;  // host copy of the 16-byte table when it fits the kernel-parameter form
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -129,8 +138,8 @@ __device__ __forceinline__ Tab16 lds_tab16(uint32_t addr) {
 // per-entry decisions.  MODE 0: kind S_L (one operator, 2 FMA); MODE 1: kind P (operators NOPS-2 and
 // NOPS-1, second value = +-v, 4 FMA); MODE 2: kind G (32-byte entries, every operator); MODE 3:
 // kind O (as G, X from global memory at row + off).
-template <int NOPS, int MODE, int L>
-__device__ __forceinline__ void tile_list(uint32_t cw, const int nw, const uint32_t tab_base, const uint32_t xs_row,
+template <int NOPS, int MODE, int L, int CT>
+__device__ __forceinline__ void tile_list(const ConstTab& ctab, uint32_t cw, const int nw, const uint32_t tab_base, const uint32_t xs_row,
                                           const double2* __restrict__ xg_row, const int64_t batch,
                                           double (&pr)[NOPS], double (&pi)[NOPS]) {
   constexpr uint32_t ESZ = MODE >= 2 ? 32u : 16u;
@@ -147,7 +156,14 @@ __device__ __forceinline__ void tile_list(uint32_t cw, const int nw, const uint3
       for (int q = 0; q < 4; ++q) {
         const uint32_t code = (q & 1) ? (ww[2 * h + (q >> 1)] >> 16) : (ww[2 * h + (q >> 1)] & 0xffffu);
         ta[q] = tab_base + code * ESZ;
-        lo[q] = lds_tab16(ta[q]);
+        if (CT && MODE < 2) {
+          const Entry16 ce = ctab.e[code];
+          lo[q].v = ce.v;
+          lo[q].off = ce.off;
+          lo[q].flag = ce.neg2;
+        } else {
+          lo[q] = lds_tab16(ta[q]);
+        }
       }
       if (MODE >= 2 && NOPS > 1) {
 #pragma unroll
@@ -187,6 +203,31 @@ __device__ __forceinline__ void tile_list(uint32_t cw, const int nw, const uint3
   }
 }
 
+// class-O list after its first two codes (rows with more than two straddling couplings: rare)
+template <int NOPS, int CT>
+__device__ __forceinline__ void tile_list_rest(const ConstTab& ctab, uint4 first, uint32_t cw, const int nw, const uint32_t tab_base,
+                                               const uint32_t xs_row, const double2* __restrict__ xg_row, const int64_t batch,
+                                               double (&pr)[NOPS], double (&pi)[NOPS]) {
+  const uint32_t rest[7] = {first.y & 0xffffu, first.y >> 16, first.z & 0xffffu, first.z >> 16, first.w & 0xffffu, first.w >> 16, 0u};
+  for (int q = 0; q < 6 && rest[q] != 0u; ++q) {
+    const uint32_t ta = tab_base + rest[q] * 32u;
+    const Tab16 lo = lds_tab16(ta);
+    const double2 hi = lds_f64x2(ta + 16u);
+    const double2 xv = __ldg(xg_row + (int64_t)lo.off * batch);
+    pr[0] = fma(lo.v, xv.x, pr[0]);
+    pi[0] = fma(lo.v, xv.y, pi[0]);
+    if (NOPS > 1) {
+      pr[1] = fma(hi.x, xv.x, pr[1]);
+      pi[1] = fma(hi.x, xv.y, pi[1]);
+    }
+    if (NOPS > 2) {
+      pr[2] = fma(hi.y, xv.x, pr[2]);
+      pi[2] = fma(hi.y, xv.y, pi[2]);
+    }
+  }
+  if (nw > 1 && first.w != 0u) tile_list<NOPS, 3, 0, CT>(ctab, cw + 16u, nw - 1, tab_base, xs_row, xg_row, batch, pr, pi);
+}
+
 struct TileRowArgs {
   int rows, warp, lane;
   int64_t row0, rstep, c0, batch;
@@ -199,8 +240,8 @@ struct TileRowArgs {
 // (global / L2 loads) are requested before the current row is decoded; everything else a row needs
 // -- X, its code words, the tables, the diagonal -- is in shared memory.  All row-dependent global
 // addresses advance by constant strides.
-template <int EPI, int NOPS, int PASS>
-__device__ __forceinline__ void tile_rows(const TileView& tv, const TileRowArgs& ra, const double2* __restrict__ x,
+template <int EPI, int NOPS, int PASS, int CT>
+__device__ __forceinline__ void tile_rows(const TileView& tv, const ConstTab& ctab, const TileRowArgs& ra, const double2* __restrict__ x,
                                           const EpiArgs& e, const double2 (&u)[NOPS], double& dr, double& di, double& nn) {
   const int rows = ra.rows, warp = ra.warp;
   const int64_t batch = ra.batch;
@@ -241,13 +282,46 @@ __device__ __forceinline__ void tile_rows(const TileView& tv, const TileRowArgs&
     double pr[NOPS], pi[NOPS];
 #pragma unroll
     for (int l = 0; l < NOPS; ++l) pr[l] = pi[l] = 0.0;
-    tile_list<NOPS, 0, 0>(cw + w0[0], nw[0], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
-    if (NOPS > 1) tile_list<NOPS, 0, (NOPS > 1 ? 1 : 0)>(cw + w0[1], nw[1], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
-    if (NOPS > 2) tile_list<NOPS, 0, (NOPS > 2 ? 2 : 0)>(cw + w0[2], nw[2], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
-    if (NOPS > 1) tile_list<NOPS, 1, 0>(cw + w0[3], nw[3], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
-    tile_list<NOPS, 2, 0>(cw + w0[4], nw[4], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+    // class O (pass B): the first two entries' global gathers are issued NOW and consumed after the
+    // shared-memory lists, so their L2 latency hides behind the rest of the row
+    uint4 ow = make_uint4(0u, 0u, 0u, 0u);
+    Tab16 o_lo[2];
+    double2 o_hi[2], o_x[2];
+    if (PASS == 1 && nw[5] > 0) {
+      ow = lds_u32x4(cw + w0[5]);
+      if (ow.x != 0u) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t ta = ra.tab32_base + ((q ? (ow.x >> 16) : (ow.x & 0xffffu)) * 32u);
+          o_lo[q] = lds_tab16(ta);
+          if (NOPS > 1) o_hi[q] = lds_f64x2(ta + 16u);
+          o_x[q] = __ldg(xg_row + (int64_t)o_lo[q].off * batch);
+        }
+      }
+    }
+    tile_list<NOPS, 0, 0, CT>(ctab, cw + w0[0], nw[0], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 1) tile_list<NOPS, 0, (NOPS > 1 ? 1 : 0), CT>(ctab, cw + w0[1], nw[1], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 2) tile_list<NOPS, 0, (NOPS > 2 ? 2 : 0), CT>(ctab, cw + w0[2], nw[2], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    if (NOPS > 1) tile_list<NOPS, 1, 0, CT>(ctab, cw + w0[3], nw[3], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
+    tile_list<NOPS, 2, 0, CT>(ctab, cw + w0[4], nw[4], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
     if (PASS == 1) {  // class O: the few couplings that straddle the split, from global memory
-      tile_list<NOPS, 3, 0>(cw + w0[5], nw[5], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+      if (ow.x != 0u) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          pr[0] = fma(o_lo[q].v, o_x[q].x, pr[0]);
+          pi[0] = fma(o_lo[q].v, o_x[q].y, pi[0]);
+          if (NOPS > 1) {
+            pr[1] = fma(o_hi[q].x, o_x[q].x, pr[1]);
+            pi[1] = fma(o_hi[q].x, o_x[q].y, pi[1]);
+          }
+          if (NOPS > 2) {
+            pr[2] = fma(o_hi[q].y, o_x[q].x, pr[2]);
+            pi[2] = fma(o_hi[q].y, o_x[q].y, pi[2]);
+          }
+        }
+        if ((ow.y | ow.z | ow.w) != 0u || nw[5] > 1)  // more than two: the rest of the list (first word without its first two codes)
+          tile_list_rest<NOPS, CT>(ctab, ow, cw + w0[5], nw[5], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+      }
     } else {          // explicit diagonals
       const double2 d01 = lds_f64x2(ra.diag_base + (uint32_t)s * 32u);
       pr[0] = fma(d01.x, xown.x, pr[0]);
@@ -276,9 +350,9 @@ __device__ __forceinline__ void tile_rows(const TileView& tv, const TileRowArgs&
   }
 }
 
-template <int EPI, int NOPS>
+template <int EPI, int NOPS, int CT>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
-k_spmm_tile(const __grid_constant__ TileView tv, const double2* __restrict__ coef, int coef_stride, int64_t batch,
+k_spmm_tile(const __grid_constant__ TileView tv, const __grid_constant__ ConstTab ctab, const double2* __restrict__ coef, int coef_stride, int64_t batch,
             const double2* __restrict__ x, EpiArgs e) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // shared memory: X tile | 16-byte table | 32-byte table | the tile's code words | diagonals (pass A)
@@ -343,6 +417,30 @@ k_spmm_tile(const __grid_constant__ TileView tv, const double2* __restrict__ coe
         for (int idx = threadIdx.x; idx < rows * 2; idx += TILE_THREADS)  // 32 bytes per row: d0 d1 | d2 pad
           cp_async16(s_diag + idx * 2, tv.diag + row0 * 4 + idx * 2);
     }
+    // ... and ask L2 for the tile of the item after this one (first touch of a pass-A tile comes from
+    // HBM: the request is in flight while this item is computed)
+    {
+      const int64_t nxt = item + gridDim.x;
+      if (nxt < total) {
+        int npass, ntile;
+        int64_t ng;
+        if (nxt < tilesA) { npass = 0; ng = 0; ntile = (int)nxt; }
+        else {
+          const int64_t j = nxt - tilesA;
+          const int64_t p = 1 + j / per_phase;
+          const int k = (int)(j % per_phase);
+          if (p < chunks && k < tilesA) { npass = 0; ng = p; ntile = k; }
+          else { npass = 1; ng = p - 1; ntile = p < chunks ? k - tilesA : k; }
+        }
+        const int nrows = npass == 0 ? tv.S : tv.NH;
+        const int64_t nrow0 = npass == 0 ? (int64_t)ntile * tv.S : ntile;
+        const int64_t nstep = npass == 0 ? 1 : tv.S;
+        for (int idx = threadIdx.x; idx < nrows * 4; idx += TILE_THREADS) {  // 4 lines of 128 B per row
+          const int s = idx >> 2, j = idx & 3;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (nrow0 + s * nstep) * batch + ng * 32 + j * 8));
+        }
+      }
+    }
     // 2. this lane's coefficients (times i for a purely imaginary operator)
     double2 u[NOPS];
 #pragma unroll
@@ -377,8 +475,8 @@ k_spmm_tile(const __grid_constant__ TileView tv, const double2* __restrict__ coe
     ra.xs_base = xs_base;
     ra.codes_base = codes_base;
     ra.diag_base = diag_base;
-    if (pass == 0) tile_rows<EPI, NOPS, 0>(tv, ra, x, e, u, dr, di, nn);
-    else tile_rows<EPI, NOPS, 1>(tv, ra, x, e, u, dr, di, nn);
+    if (pass == 0) tile_rows<EPI, NOPS, 0, CT>(tv, ctab, ra, x, e, u, dr, di, nn);
+    else tile_rows<EPI, NOPS, 1, CT>(tv, ctab, ra, x, e, u, dr, di, nn);
     if (pass == 1 && epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, c0 + lane, dr, di, nn);
 
     // every warp is done with the tile (the next item overwrites it) and has issued its stores
@@ -410,6 +508,7 @@ void qp_tile_free(qp_tile_s* t) {
   cudaFree(t->d_diag);
   cudaFree(t->d_ring);
   cudaFree(t->d_done);
+  delete t->h_ctab;
   delete t;
 }
 
@@ -459,6 +558,12 @@ static int32_t tile_ensure(qp_gen_t gen) {
   QP_CUDA(ctx, cudaMalloc(&t->d_ring, sizeof(double2) * (size_t)TILE_RING * (size_t)n * 32));
   t->n16 = (int)f.tab16.size();
   t->n32 = (int)f.tab32.size();
+  static const int no_ctab = getenv("QPROP_TILE_CTAB") ? atoi(getenv("QPROP_TILE_CTAB")) == 0 : 0;
+  if (t->n16 <= TILE_CTAB && !no_ctab) {
+    t->h_ctab = new ConstTab();
+    memset(t->h_ctab, 0, sizeof(ConstTab));
+    memcpy(t->h_ctab->e, f.tab16.data(), sizeof(Entry16) * f.tab16.size());
+  }
   // the big host arrays are not needed any more
   std::vector<uint16_t>().swap(f.codes[0]);
   std::vector<uint16_t>().swap(f.codes[1]);
@@ -467,7 +572,7 @@ static int32_t tile_ensure(qp_gen_t gen) {
   return QP_OK;
 }
 
-template <int EPI, int NOPS>
+template <int EPI, int NOPS, int CT>
 static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
   qp_tile_s* t = gen->tile;
@@ -510,7 +615,9 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   tv.doneA = t->d_done;
   tv.doneB = t->d_done + t->chunk_cap;
   tv.epoch = ++t->epoch;
-  auto kern = k_spmm_tile<EPI, NOPS>;
+  auto kern = k_spmm_tile<EPI, NOPS, CT>;
+  static const ConstTab empty_tab = {};
+  const ConstTab& ctab = CT ? *t->h_ctab : empty_tab;
   const size_t smem = tile_smem_bytes(f, (size_t)t->n16, (size_t)t->n32);
   if (!ctx->smem_configured.count((const void*)kern)) {
     QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -533,17 +640,18 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const double2* coef = gen->d_coef;
-  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tv, coef, coef_stride, batch, x, e));
+  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tv, ctab, coef, coef_stride, batch, x, e));
   QP_LAUNCHED(ctx);
   return QP_OK;
 }
 
 template <int EPI>
 static int32_t tile_launch_nops(qp_gen_t gen, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e) {
+  const bool ct = gen->tile->h_ctab != nullptr;
   switch (gen->n_ops) {
-    case 1: return tile_launch<EPI, 1>(gen, coef_stride, x, batch, e);
-    case 2: return tile_launch<EPI, 2>(gen, coef_stride, x, batch, e);
-    default: return tile_launch<EPI, 3>(gen, coef_stride, x, batch, e);
+    case 1: return ct ? tile_launch<EPI, 1, 1>(gen, coef_stride, x, batch, e) : tile_launch<EPI, 1, 0>(gen, coef_stride, x, batch, e);
+    case 2: return ct ? tile_launch<EPI, 2, 1>(gen, coef_stride, x, batch, e) : tile_launch<EPI, 2, 0>(gen, coef_stride, x, batch, e);
+    default: return ct ? tile_launch<EPI, 3, 1>(gen, coef_stride, x, batch, e) : tile_launch<EPI, 3, 0>(gen, coef_stride, x, batch, e);
   }
 }
 
