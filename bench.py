@@ -70,6 +70,7 @@ def parse_args():
     ap.add_argument("--no-ensemble", action="store_true")
     ap.add_argument("--ensemble-B", type=int, default=1024)
     ap.add_argument("--ensemble-steps", type=int, default=5)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="host-resident trajectories interleaved per GPU in the e2e arm")
     return ap.parse_args()
 
 
@@ -464,12 +465,20 @@ def main():
     ctx.sync()
     seq_s = (time.perf_counter() - t0) / n_seq
     barrier()
-    # (b) two host-resident trajectories per GPU on two contexts (= two streams): the copies of one
-    # overlap the step of the other; every step still moves its state in and out
-    ctx2 = qp.Context(local_rank)
-    p2 = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx2, matrix_format=args.format, **kw)
+    # (b) several host-resident trajectories per GPU, one context (= one stream) each: the copies of
+    # one overlap the steps of the others; every step still moves its state in and out
     qp.reinit_prop(p, p.state)
-    lanes = [(p, ctx, host_a), (p2, ctx2, host_b)]
+    lanes = [(p, ctx, host_a)]
+    for i in range(1, max(2, args.e2e_lanes)):
+        ctx_i = qp.Context(local_rank)
+        p_i = qp.init_prop(w["psi0"], gen, w["tlist"], "cheby", ctx=ctx_i, matrix_format=args.format, **kw)
+        if i == 1:
+            host_i = host_b
+        else:
+            host_i = torch.empty(N, dtype=torch.complex128, pin_memory=True)
+            host_i.copy_(host_a)
+        lanes.append((p_i, ctx_i, host_i))
+    n_lanes = len(lanes)
 
     def enqueue(lane):
         prop, c, host = lane
@@ -481,10 +490,10 @@ def main():
     def pipelined(n_steps):
         for lane in lanes:
             enqueue(lane)
-        done = 2
+        done = n_lanes
         i = 0
         while done < n_steps:
-            lane = lanes[i % 2]
+            lane = lanes[i % n_lanes]
             lane[1].sync()  # the host owns this trajectory's buffer again (result of its last step)
             enqueue(lane)
             done += 1
@@ -493,7 +502,7 @@ def main():
             lane[1].sync()
         return done
 
-    pipelined(6)
+    pipelined(2 * n_lanes + 2)
     barrier()
     t0 = time.perf_counter()
     n_e2e = 0
@@ -501,7 +510,7 @@ def main():
         n_e2e += pipelined(max(K, 4))
     e2e_s = (time.perf_counter() - t0) / n_e2e
     barrier()
-    del p2, ctx2, lanes
+    del lanes
 
     # ---------------- ensemble (BASELINE configs[2]) -----------------------------------------
     ens_out = None
@@ -574,7 +583,7 @@ def main():
                 "value": world * 1e3 / e2e_ms, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * N + 16 * p.wrk.gen.n_coeffs, "d2h_bytes_per_step": 16 * N,
                 "note": "host-resident states: every step copies its state pinned host -> device, runs prop_step!, copies device -> pinned host; "
-                        "two trajectories per GPU interleaved on two contexts so the copies of one overlap the step of the other",
+                        f"{max(2, args.e2e_lanes)} trajectories per GPU interleaved on their own contexts (streams) so the copies of one overlap the steps of the others",
                 "sequential_value": world * 1e3 / seq_ms,
                 "sequential_note": "one trajectory, upload -> prop_step! -> download strictly in sequence",
             },

@@ -229,8 +229,14 @@ int32_t qp_cheby_step_bytes(qp_cheby_t wrk, int64_t* bytes);
  * Replaces: arnoldi! (src/arnoldi.jl:60-100), extend_arnoldi! (:115-129) and the vector
  * work of newton! (src/newton.jl:346-367).  The small dense step (Ritz values, Leja
  * points, divided differences, polynomial in the Hessenberg matrix; src/newton.jl:297-343)
- * stays on the host, where `func` is an arbitrary closure.  Krylov workspaces hold
- * m_max+1 vectors of a single state (batch == 1). */
+ * stays on the host, where `func` is an arbitrary closure.  A Krylov workspace holds m_max+1
+ * vectors of the shape of `like`.  batch == 1: classical Gram-Schmidt with a fused multi-dot and
+ * selective re-orthogonalisation, enqueued without host round trips.  batch > 1 (a bundle of
+ * states sharing the generator, e.g. the forward / backward states of GRAPE and Krotov, reference
+ * src/cheby_propagator.jl:147-152, docs/src/overview.md:193-195): the B Arnoldi processes run in
+ * lock step with the reference's own modified Gram-Schmidt, every state with its own Hessenberg
+ * matrix:  hess = [batch][ld * ld] column-major matrices, m_out = [batch] dimensions, weights of
+ * qp_krylov_combine = [n_w][batch]. */
 int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max, qp_krylov_t* K);
 int32_t qp_krylov_destroy(qp_krylov_t K);
 /* q_1 <- v; for j = 1..m: q_{j+1} = H q_j, orthogonalised against q_1..q_j; fills the

@@ -224,6 +224,142 @@ static int kgrid(qp_ctx_t ctx, int64_t n) {
 
 // ---------------------------------------------------------------------------------------
 
+// ---------------------------------------------------------------------------------------
+// State bundles (batch > 1): B states sharing one generator run the Arnoldi process in lock step,
+// each with its own Hessenberg matrix (the forward / backward sweeps of GRAPE and
+// Krotov propagate many states under one generator).  Orthogonalisation here is the reference's own
+// modified Gram-Schmidt -- j dot + axpy pairs per column (src/arnoldi.jl:84-87) -- with every dot
+// product, norm and update a batched kernel over the [N][B] layout.
+// ---------------------------------------------------------------------------------------
+
+// y[r, b] += alpha[b] * x[r, b]
+__global__ void k_axpy_pb(const double2* __restrict__ alpha, const double2* __restrict__ x, double2* __restrict__ y,
+                          int64_t n, int64_t batch) {
+  const int64_t total = n * batch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 a = alpha[i % batch];
+    const double2 xv = x[i];
+    double2 yv = y[i];
+    yv.x += a.x * xv.x - a.y * xv.y;
+    yv.y += a.x * xv.y + a.y * xv.x;
+    y[i] = yv;
+  }
+}
+
+// x[r, b] *= alpha[b]
+__global__ void k_scal_pb(const double2* __restrict__ alpha, double2* __restrict__ x, int64_t n, int64_t batch) {
+  const int64_t total = n * batch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 a = alpha[i % batch];
+    const double2 xv = x[i];
+    x[i] = make_double2(a.x * xv.x - a.y * xv.y, a.x * xv.y + a.y * xv.x);
+  }
+}
+
+// y[r, b] (+)= sum_i w[i * batch + b] * q_i[r, b]
+__global__ void k_combine_pb(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ w, int n_w,
+                             double2* __restrict__ y, int64_t n, int64_t batch, int accumulate) {
+  const int64_t total = n * batch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i % batch;
+    double2 acc = accumulate ? y[i] : make_double2(0.0, 0.0);
+    for (int k = 0; k < n_w; ++k) {
+      const double2 a = w[(int64_t)k * batch + b];
+      const double2 qv = q0[(int64_t)k * stride + i];
+      acc.x += a.x * qv.x - a.y * qv.y;
+      acc.y += a.x * qv.y + a.y * qv.x;
+    }
+    y[i] = acc;
+  }
+}
+
+// per-trajectory numbers -> device (through the context's pinned staging area)
+static int32_t upload_pb(qp_krylov_t K, const double2* host, size_t count) {
+  qp_ctx_t ctx = K->ctx;
+  if (K->pb_elems < count) {
+    QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(K->d_pb);
+    K->d_pb = nullptr;
+    K->pb_elems = 0;
+    QP_CUDA(ctx, cudaMalloc(&K->d_pb, sizeof(double2) * count));
+    K->pb_elems = count;
+  }
+  QP_CHECK(qp_ctx_reserve_stage(ctx, count));
+  QP_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage));
+  memcpy(ctx->h_stage, host, sizeof(double2) * count);
+  QP_CUDA(ctx, cudaMemcpyAsync(K->d_pb, ctx->h_stage, sizeof(double2) * count, cudaMemcpyHostToDevice, ctx->stream));
+  QP_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
+  return QP_OK;
+}
+
+// st[:, b] *= alpha[b]  (used by the batched newton! in newton.cu)
+int32_t qp_krylov_scale_pb(qp_krylov_t K, qp_state_t st, const qp_c128* alpha) {
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(upload_pb(K, reinterpret_cast<const double2*>(alpha), (size_t)K->batch));
+  k_scal_pb<<<kgrid(ctx, K->n * K->batch), KBLOCK, 0, ctx->stream>>>(K->d_pb, st->d, K->n, K->batch);
+  QP_LAUNCHED(ctx);
+  return QP_OK;
+}
+
+static int32_t scal_pb(qp_krylov_t K, double2* x, const std::vector<double2>& alpha) {
+  qp_ctx_t ctx = K->ctx;
+  QP_CHECK(upload_pb(K, alpha.data(), alpha.size()));
+  k_scal_pb<<<kgrid(ctx, K->n * K->batch), KBLOCK, 0, ctx->stream>>>(K->d_pb, x, K->n, K->batch);
+  QP_LAUNCHED(ctx);
+  return QP_OK;
+}
+
+// One Arnoldi column for every state of the bundle: q[j+1] = H q[j], MGS against q[0..j].
+// hess: [batch][ld * ld] column-major matrices; alive[b] = 0 once trajectory b's Krylov space is exhausted.
+static int32_t arnoldi_column_batched(qp_krylov_t K, int stride, int j, double dt, bool normalise, double norm_min,
+                                      qp_c128* hess, int ld, std::vector<int>& m_eff, int m) {
+  qp_ctx_t ctx = K->ctx;
+  const int64_t n = K->n, B = K->batch, vec = n * B;
+  double2* w = K->q + (size_t)(j + 1) * vec;
+  QP_CHECK(qp_gen_apply(K->gen, stride, make_double2(1.0, 0.0), make_double2(0.0, 0.0), K->q + (size_t)j * vec, w, B));
+  std::vector<qp_c128> h((size_t)B);
+  std::vector<double2> alpha((size_t)B);
+  for (int i = 0; i <= j; ++i) {  // Hess[i, j] = dt <q_i|w>;  w -= (Hess[i, j] / dt) q_i   (:84-87)
+    QP_CHECK(qp_reduce_dot(ctx, K->q + (size_t)i * vec, w, n, B, h.data()));
+    for (int64_t b = 0; b < B; ++b) {
+      hess[(size_t)b * ld * ld + (size_t)j * ld + i] = qp_c128{dt * h[b].re, dt * h[b].im};
+      alpha[b] = make_double2(-h[b].re, -h[b].im);
+    }
+    QP_CHECK(upload_pb(K, alpha.data(), alpha.size()));
+    k_axpy_pb<<<kgrid(ctx, vec), KBLOCK, 0, ctx->stream>>>(K->d_pb, K->q + (size_t)i * vec, w, n, B);
+    QP_LAUNCHED(ctx);
+  }
+  if (normalise) {  // :88-97
+    std::vector<double> nrm2((size_t)B);
+    QP_CHECK(qp_reduce_norm2(ctx, w, n, B, nrm2.data()));
+    for (int64_t b = 0; b < B; ++b) {
+      const double hn = sqrt(nrm2[b]);
+      hess[(size_t)b * ld * ld + (size_t)j * ld + (j + 1)] = qp_c128{dt * hn, 0.0};
+      const bool ok = hn >= norm_min && hn > 0.0;
+      if (!ok && m_eff[b] == m) m_eff[b] = j + 1;  // dimensionality exhausted for this state
+      alpha[b] = make_double2(ok ? 1.0 / hn : 0.0, 0.0);  // an exhausted state keeps a zero vector (no inf / NaN)
+    }
+    QP_CHECK(scal_pb(K, w, alpha));
+  }
+  return QP_OK;
+}
+
+static int32_t arnoldi_batched(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_t v, int32_t m, double dt,
+                               int32_t extended, double norm_min, qp_c128* hess, int32_t ld, int32_t* m_out) {
+  qp_ctx_t ctx = K->ctx;
+  const int64_t B = K->batch, vec = K->n * B;
+  QpScopedTimer timer(ctx, "arnoldi!");
+  int stride = 0;
+  QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
+  memset(hess, 0, sizeof(qp_c128) * (size_t)ld * (size_t)ld * (size_t)B);
+  QP_CUDA(ctx, cudaMemcpyAsync(K->q, v->d, sizeof(double2) * vec, cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<int> m_eff((size_t)B, m);
+  for (int j = 0; j < m; ++j)
+    QP_CHECK(arnoldi_column_batched(K, stride, j, dt, j + 1 < m || extended, norm_min, hess, ld, m_eff, m));
+  for (int64_t b = 0; b < B; ++b) m_out[b] = m_eff[b];
+  return QP_OK;
+}
+
 extern "C" int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max, qp_krylov_t* out) {
   if (!gen) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_create: null generator");
   qp_ctx_t ctx = gen->ctx;
@@ -231,16 +367,15 @@ extern "C" int32_t qp_krylov_create(qp_gen_t gen, qp_state_t like, int32_t m_max
   QP_REQUIRE(ctx, out != nullptr && like != nullptr, "qp_krylov_create: null argument");
   *out = nullptr;
   QP_REQUIRE(ctx, like->ctx == ctx && like->n == gen->n, "qp_krylov_create: state does not match the generator");
-  if (like->batch != 1)
-    return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_krylov_create: Krylov workspaces hold a single state (batch == 1)");
   QP_REQUIRE(ctx, m_max >= 1, "qp_krylov_create: m_max must be >= 1");
   qp_krylov_t K = new qp_krylov_s();
   K->ctx = ctx;
   K->gen = gen;
   K->n = like->n;
+  K->batch = like->batch;
   K->m_max = m_max;
   cudaError_t e;
-  if ((e = cudaMalloc(&K->q, sizeof(double2) * (size_t)K->n * (size_t)(m_max + 1))) != cudaSuccess ||
+  if ((e = cudaMalloc(&K->q, sizeof(double2) * (size_t)K->n * (size_t)K->batch * (size_t)(m_max + 1))) != cudaSuccess ||
       (e = cudaMalloc(&K->d_h, sizeof(double2) * (size_t)(m_max + 8))) != cudaSuccess ||
       (e = cudaMalloc(&K->d_hall, sizeof(double2) * (size_t)(m_max + 1) * (size_t)(m_max + 2))) != cudaSuccess ||
       (e = cudaMalloc(&K->d_ctl, sizeof(ColCtl) * (size_t)(m_max + 1))) != cudaSuccess) {
@@ -264,6 +399,7 @@ extern "C" int32_t qp_krylov_destroy(qp_krylov_t K) {
   cudaFree(K->d_h);
   cudaFree(K->d_hall);
   cudaFree(K->d_ctl);
+  cudaFree(K->d_pb);
   delete K;
   return QP_OK;
 }
@@ -333,13 +469,14 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
   if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_arnoldi: null workspace");
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
-  QP_REQUIRE(ctx, v && v->ctx == ctx && v->n == K->n && v->batch == 1, "qp_arnoldi: bad start vector");
+  QP_REQUIRE(ctx, v && v->ctx == ctx && v->n == K->n && v->batch == K->batch, "qp_arnoldi: bad start vector");
   QP_REQUIRE(ctx, hess != nullptr && m_out != nullptr, "qp_arnoldi: null output");
   QP_REQUIRE(ctx, m >= 1, "qp_arnoldi: m must be >= 1");
   // @assert length(q) >= m + 1 ; size(Hess) >= dim_hess   src/arnoldi.jl:76-77
   QP_REQUIRE(ctx, m <= K->m_max, "qp_arnoldi: m=%d exceeds the workspace (m_max=%d)", m, K->m_max);
   const int dim_hess = extended ? m + 1 : m;
   QP_REQUIRE(ctx, ld >= dim_hess, "qp_arnoldi: Hessenberg storage %d x %d too small for dimension %d", ld, ld, dim_hess);
+  if (K->batch > 1) return arnoldi_batched(K, op_coeffs, v, m, dt, extended, norm_min, hess, ld, m_out);
   QpScopedTimer timer(ctx, "arnoldi!");
   int stride = 0;
   QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
@@ -387,6 +524,7 @@ extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, in
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
   QP_REQUIRE(ctx, hess != nullptr, "qp_arnoldi_extend: null Hessenberg matrix");
+  if (K->batch != 1) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_arnoldi_extend: single states only (batch == 1)");
   QP_REQUIRE(ctx, m >= 2 && m <= K->m_max && ld >= m, "qp_arnoldi_extend: bad dimension m=%d (m_max=%d, ld=%d)", m,
              K->m_max, ld);
   const int64_t n = K->n;
@@ -419,10 +557,18 @@ extern "C" int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* wts, int32_t 
   if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_combine: null workspace");
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
-  QP_REQUIRE(ctx, st && st->ctx == ctx && st->n == K->n && st->batch == 1, "qp_krylov_combine: bad state");
+  QP_REQUIRE(ctx, st && st->ctx == ctx && st->n == K->n && st->batch == K->batch, "qp_krylov_combine: bad state");
   QP_REQUIRE(ctx, wts != nullptr && n_w >= 1 && first >= 0 && first + n_w <= K->m_max + 1,
              "qp_krylov_combine: vectors [%d, %d) outside the workspace", first, first + n_w);
   const int64_t n = K->n;
+  if (K->batch > 1) {  // weights [n_w][batch]
+    const int64_t vec = n * K->batch;
+    QP_CHECK(upload_pb(K, reinterpret_cast<const double2*>(wts), (size_t)n_w * (size_t)K->batch));
+    k_combine_pb<<<kgrid(ctx, vec), KBLOCK, 0, ctx->stream>>>(K->q + (size_t)first * vec, vec, K->d_pb, n_w, st->d, n, K->batch,
+                                                               accumulate ? 1 : 0);
+    QP_LAUNCHED(ctx);
+    return QP_OK;
+  }
   for (int i0 = 0; i0 < n_w; i0 += KV) {
     const int nv = std::min(KV, n_w - i0);
     Weights wt;
@@ -440,9 +586,10 @@ extern "C" int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst) {
   if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_get: null workspace");
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
-  QP_REQUIRE(ctx, dst && dst->ctx == ctx && dst->n == K->n && dst->batch == 1, "qp_krylov_get: bad state");
+  QP_REQUIRE(ctx, dst && dst->ctx == ctx && dst->n == K->n && dst->batch == K->batch, "qp_krylov_get: bad state");
   QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_get: index %d out of range", index);
-  QP_CUDA(ctx, cudaMemcpyAsync(dst->d, K->q + (size_t)index * K->n, sizeof(double2) * K->n, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t vec = (size_t)K->n * (size_t)K->batch;
+  QP_CUDA(ctx, cudaMemcpyAsync(dst->d, K->q + (size_t)index * vec, sizeof(double2) * vec, cudaMemcpyDeviceToDevice, ctx->stream));
   return QP_OK;
 }
 
@@ -450,8 +597,9 @@ extern "C" int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src) {
   if (!K) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_krylov_set: null workspace");
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
-  QP_REQUIRE(ctx, src && src->ctx == ctx && src->n == K->n && src->batch == 1, "qp_krylov_set: bad state");
+  QP_REQUIRE(ctx, src && src->ctx == ctx && src->n == K->n && src->batch == K->batch, "qp_krylov_set: bad state");
   QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_set: index %d out of range", index);
-  QP_CUDA(ctx, cudaMemcpyAsync(K->q + (size_t)index * K->n, src->d, sizeof(double2) * K->n, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t vec = (size_t)K->n * (size_t)K->batch;
+  QP_CUDA(ctx, cudaMemcpyAsync(K->q + (size_t)index * vec, src->d, sizeof(double2) * vec, cudaMemcpyDeviceToDevice, ctx->stream));
   return QP_OK;
 }

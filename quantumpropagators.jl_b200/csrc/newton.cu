@@ -213,6 +213,155 @@ struct HostTimer {
   }
 };
 
+// k_scal_pb / per-trajectory scaling lives in krylov.cu
+int32_t qp_krylov_scale_pb(qp_krylov_t K, qp_state_t st, const qp_c128* alpha);
+
+// newton! for a bundle of B states sharing one generator: the Arnoldi process and
+// the vector updates are batched kernels, every state keeps its own Hessenberg matrix, Leja points
+// and Newton coefficients, and the restart loop runs in lock step until the LAST state has converged
+// (a converged state contributes zero weights from then on and keeps its restart vector).
+static int32_t newton_step_batched(qp_krylov_t K, qp_state_t psi, qp_state_t v, const qp_c128* op_coeffs, double dt,
+                                   const NewtonFunc& func, double norm_min, double relerr, int32_t max_restarts,
+                                   int32_t* restarts_out) {
+  qp_ctx_t ctx = K->ctx;
+  const int64_t B = K->batch;
+  const int ld = K->m_max + 1;
+  struct Traj {
+    std::vector<cplx> a, leja, ritz, R, R2, P;
+    int n_a = 0, n_leja = 0, m = 0, restarts = 0;
+    double radius = 0.0, beta = 0.0;
+    bool done = false;
+  };
+  std::vector<Traj> T((size_t)B);
+  std::vector<qp_c128> hess((size_t)ld * ld * B), wP((size_t)(K->m_max + 1) * B), wR((size_t)(K->m_max + 1) * B), sc((size_t)B);
+  std::vector<int32_t> m_out((size_t)B);
+  std::vector<double> nrm((size_t)B);
+
+  QP_CHECK(qp_copy(v, psi));  // v <- Psi (:268), normalised per state
+  QP_CHECK(qp_norm(v, nrm.data()));
+  for (int64_t b = 0; b < B; ++b) {
+    QP_REQUIRE(ctx, nrm[b] > 0.0, "qp_newton_step: state %lld of the bundle has zero norm", (long long)b);
+    T[b].beta = nrm[b];
+    T[b].R.resize(ld);
+    T[b].R2.resize(ld);
+    T[b].P.resize(ld);
+    sc[b] = qp_c128{1.0 / nrm[b], 0.0};
+  }
+  QP_CHECK(qp_krylov_scale_pb(K, v, sc.data()));
+
+  int m = K->m_max, s = 0;
+  for (;;) {
+    QP_CHECK(qp_arnoldi(K, op_coeffs, v, m, dt, 1, norm_min, hess.data(), ld, m_out.data()));
+    bool need_scale = false;
+    for (int64_t b = 0; b < B; ++b) sc[b] = qp_c128{1.0, 0.0};
+    std::fill(wP.begin(), wP.end(), qp_c128{0.0, 0.0});
+    std::fill(wR.begin(), wR.end(), qp_c128{0.0, 0.0});
+    for (int64_t b = 0; b < B; ++b) {
+      Traj& t = T[b];
+      wR[(size_t)0 * B + b] = qp_c128{1.0, 0.0};  // default: the restart vector stays q_0 = v
+      if (t.done) continue;
+      const cplx* Hb = reinterpret_cast<const cplx*>(hess.data()) + (size_t)b * ld * ld;
+      const int mb = m_out[b];
+      t.m = mb;
+      if (mb == 1 && s == 0) {  // v is an eigenvector: f(H dt) Psi = f(lambda) Psi   (:289-295)
+        const cplx f = func(t.beta * Hb[0]);
+        sc[b] = qp_c128{f.real(), f.imag()};
+        need_scale = true;
+        t.done = true;
+        continue;
+      }
+      std::vector<cplx> hb(Hb, Hb + (size_t)ld * ld);
+      {
+        HostTimer tm(ctx, "diagonalize_hessenberg_matrix");
+        if (!ritz_accumulated(hb, ld, mb, t.ritz))
+          return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: QR iteration for the Ritz values did not converge (state %lld)", (long long)b);
+      }
+      if (t.n_leja == 0) {
+        double mx = 0.0;
+        for (const cplx& z : t.ritz) mx = std::max(mx, std::abs(z));
+        t.radius = 1.2 * mx;
+      }
+      QP_REQUIRE(ctx, t.radius > 0.0, "qp_newton_step: Leja radius must be positive");
+      const int n_s = t.n_leja;
+      {
+        HostTimer tm(ctx, "get Leja points");
+        extend_leja(t.leja, t.n_leja, t.ritz, mb);
+      }
+      {
+        HostTimer tm(ctx, "get Newton coeffs");
+        if (!extend_newton_coeffs(t.a, t.n_a, t.leja, func, t.n_leja, t.radius))
+          return qp_fail(ctx, QP_ERR_INTERNAL, "qp_newton_step: Divided differences too small");
+      }
+      auto Hm = [&](int i, int j) { return hb[(size_t)j * ld + i]; };
+      auto step_R = [&](cplx shift) {
+        for (int i = 0; i <= mb; ++i) {
+          cplx acc(0.0, 0.0);
+          for (int j = 0; j <= mb; ++j) acc += Hm(i, j) * t.R[j];
+          t.R2[i] = (acc - shift * t.R[i]) / t.radius;
+        }
+        std::swap(t.R, t.R2);
+      };
+      {
+        HostTimer tm(ctx, "evaluate polynomial");
+        std::fill(t.R.begin(), t.R.end(), cplx(0.0, 0.0));
+        t.R[0] = t.beta;
+        for (int i = 0; i <= mb; ++i) t.P[i] = t.a[n_s] * t.R[i];
+        for (int k = 1; k < mb; ++k) {
+          step_R(t.leja[n_s + k - 1]);
+          for (int i = 0; i <= mb; ++i) t.P[i] += t.a[n_s + k] * t.R[i];
+        }
+      }
+      for (int i = 0; i < mb; ++i) wP[(size_t)i * B + b] = qp_c128{t.P[i].real(), t.P[i].imag()};
+      step_R(t.leja[n_s + mb - 1]);
+      double b2 = 0.0;
+      for (int i = 0; i <= mb; ++i) b2 += std::norm(t.R[i]);
+      t.beta = std::sqrt(b2);
+      if (t.beta > 0.0)
+        for (int i = 0; i <= mb; ++i) wR[(size_t)i * B + b] = qp_c128{t.R[i].real() / t.beta, t.R[i].imag() / t.beta};
+    }
+    if (need_scale) QP_CHECK(qp_krylov_scale_pb(K, psi, sc.data()));
+    // Psi (+)= sum_i P_i q_i: the first restart overwrites Psi (fill!(Psi, 0), :346) -- except for states
+    // that took the eigenvector shortcut, whose weights are zero and which must keep their (scaled) Psi
+    if (s == 0) {
+      bool any_shortcut = false;
+      for (int64_t b = 0; b < B; ++b) any_shortcut |= T[b].done;
+      if (any_shortcut) {  // zero the other states only
+        for (int64_t b = 0; b < B; ++b) sc[b] = T[b].done ? qp_c128{1.0, 0.0} : qp_c128{0.0, 0.0};
+        QP_CHECK(qp_krylov_scale_pb(K, psi, sc.data()));
+        QP_CHECK(qp_krylov_combine(K, wP.data(), 0, m, psi, 1));
+      } else {
+        QP_CHECK(qp_krylov_combine(K, wP.data(), 0, m, psi, 0));
+      }
+    } else {
+      QP_CHECK(qp_krylov_combine(K, wP.data(), 0, m, psi, 1));
+    }
+    QP_CHECK(qp_krylov_combine(K, wR.data(), 0, m + 1, v, 0));
+    QP_CHECK(qp_norm(psi, nrm.data()));
+    bool all_done = true;
+    for (int64_t b = 0; b < B; ++b) {
+      Traj& t = T[b];
+      if (t.done) continue;
+      if (t.beta * std::abs(t.a[t.n_a - 1]) / (1.0 + nrm[b]) < relerr) {
+        t.done = true;
+        t.restarts = s;
+      } else {
+        all_done = false;
+      }
+    }
+    if (all_done) break;
+    ++s;
+    if (s > max_restarts)
+      return qp_fail(ctx, QP_ERR_NOT_CONVERGED, "newton!: no convergence within max_restarts=%d", max_restarts);
+  }
+  if (restarts_out) *restarts_out = s;
+  K->last_n_a = T[0].n_a;
+  K->last_n_leja = T[0].n_leja;
+  K->last_radius = T[0].radius;
+  K->last_a.assign(reinterpret_cast<const qp_c128*>(T[0].a.data()), reinterpret_cast<const qp_c128*>(T[0].a.data()) + T[0].n_a);
+  K->last_leja.assign(reinterpret_cast<const qp_c128*>(T[0].leja.data()), reinterpret_cast<const qp_c128*>(T[0].leja.data()) + T[0].n_leja);
+  return QP_OK;
+}
+
 extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, const qp_c128* op_coeffs, double dt,
                                   int32_t func_id, qp_newton_func_t func_cb, void* user, double norm_min,
                                   double relerr, int32_t max_restarts, int32_t* restarts_out) {
@@ -220,8 +369,8 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
   qp_ctx_t ctx = K->ctx;
   QP_CHECK(qp_ctx_bind(ctx));
   QP_REQUIRE(ctx, psi && v && psi->ctx == ctx && v->ctx == ctx, "qp_newton_step: bad state");
-  QP_REQUIRE(ctx, psi->n == K->n && v->n == K->n && psi->batch == 1 && v->batch == 1,
-             "qp_newton_step: states must be single vectors of the workspace's dimension");
+  QP_REQUIRE(ctx, psi->n == K->n && v->n == K->n && psi->batch == K->batch && v->batch == K->batch,
+             "qp_newton_step: states must have the shape of the workspace (%lld x %lld)", (long long)K->n, (long long)K->batch);
   QP_REQUIRE(ctx, psi->d != v->d, "qp_newton_step: psi and the work vector must not alias");
   QP_REQUIRE(ctx, dt != 0.0, "qp_newton_step: dt must be non-zero");
   QP_REQUIRE(ctx, func_id == QP_FUNC_EXPMI || func_id == QP_FUNC_EXP || (func_id == QP_FUNC_CALLBACK && func_cb != nullptr),
@@ -229,6 +378,7 @@ extern "C" int32_t qp_newton_step(qp_krylov_t K, qp_state_t psi, qp_state_t v, c
   // NewtonWrk: m_max > 2 (src/newton.jl:40-46)
   QP_REQUIRE(ctx, K->m_max > 2, "qp_newton_step: Newton propagation requires m_max > 2 (got %d)", K->m_max);
   const NewtonFunc func{func_id, func_cb, user};
+  if (K->batch > 1) return newton_step_batched(K, psi, v, op_coeffs, dt, func, norm_min, relerr, max_restarts, restarts_out);
   const int ld = K->m_max + 1;
   int m = K->m_max;
   std::vector<cplx> hess((size_t)ld * ld), a, leja, ritz, R(ld), R2(ld), P(ld);

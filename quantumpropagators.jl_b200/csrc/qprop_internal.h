@@ -223,9 +223,11 @@ struct qp_cheby_s {
 struct qp_krylov_s {
   CtxHandle ctx;
   qp_gen_t gen = nullptr;
-  int64_t n = 0;
+  int64_t n = 0, batch = 1;
   int m_max = 0;
-  double2* q = nullptr;    // (m_max + 1) vectors of length n, contiguous
+  double2* d_pb = nullptr;  // per-trajectory numbers of a state bundle (batch > 1)
+  size_t pb_elems = 0;
+  double2* q = nullptr;    // (m_max + 1) vectors of length n * batch, contiguous
   double2* d_h = nullptr;  // device Hessenberg column (m_max + 2 complex): correction of a second GS round
   double2* d_hall = nullptr;      // all columns, [m_max + 1][m_max + 2]
   struct ColCtl* d_ctl = nullptr; // per-column norms / DGKS flag, [m_max + 1] (krylov.cu)

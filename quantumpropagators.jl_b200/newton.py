@@ -51,6 +51,7 @@ class KrylovWrk:
         self.gen = _device_generator(H, like.ctx)
         self.m_max = int(m_max)
         self.n = like.n
+        self.batch = like.batch
         lib = self.ctx._lib
         h = C.c_void_p()
         L.check(lib.qp_krylov_create(self.gen.handle, like.handle, self.m_max, C.byref(h)), self.ctx.handle)
@@ -58,10 +59,14 @@ class KrylovWrk:
         self._finalizer = weakref.finalize(self, lib.qp_krylov_destroy, h)
 
     def combine(self, weights, first: int, st: DeviceState, accumulate: bool) -> DeviceState:
-        """st ← (accumulate ? st : 0) + Σ_i weights[i] q_{first+i}."""
+        """st ← (accumulate ? st : 0) + Σ_i weights[i] q_{first+i}; for a bundle of B states ``weights``
+        is (n_w, B): state b uses ``weights[:, b]``."""
         w = L.as_c128_array(weights)
+        n_w = w.shape[0] if self.batch > 1 else w.size
+        if self.batch > 1 and w.shape != (n_w, self.batch):
+            raise ValueError(f"weights must have shape (n_w, {self.batch}) for a bundle")
         L.check(
-            self.ctx._lib.qp_krylov_combine(self.handle, L.ptr(w), int(first), int(w.size), st.handle, 1 if accumulate else 0),
+            self.ctx._lib.qp_krylov_combine(self.handle, L.ptr(w), int(first), int(n_w), st.handle, 1 if accumulate else 0),
             self.ctx.handle,
         )
         return st
@@ -76,12 +81,28 @@ def arnoldi_(Hess: np.ndarray, K: KrylovWrk, m: int, Psi: DeviceState, H, dt=1.0
     """``m = arnoldi!(Hess, q, m, Ψ, H, dt; extended, norm_min)`` (reference
     ``src/arnoldi.jl:60-100``).  ``Hess`` is a square complex128 host array (any order); it is
     overwritten (zero outside the computed block).  Returns the possibly reduced ``m``."""
+    c = _op_coeffs(H, K.gen, coeffs)
+    if K.batch > 1:
+        # bundle of states: Hess is (B, ld, ld), one Hessenberg matrix per state; returns the B dimensions
+        if Hess.ndim != 3 or Hess.shape[0] != K.batch or Hess.shape[1] != Hess.shape[2]:
+            raise ValueError(f"Hess must have shape ({K.batch}, ld, ld) for a bundle of {K.batch} states")
+        ld = Hess.shape[1]
+        buf = np.zeros((K.batch, ld, ld), dtype=np.complex128)  # [b][column-major ld x ld]
+        m_out = np.zeros(K.batch, dtype=np.int32)
+        L.check(
+            K.ctx._lib.qp_arnoldi(
+                K.handle, L.ptr(c), Psi.handle, int(m), float(dt), 1 if extended else 0, float(norm_min),
+                buf.ctypes.data_as(C.c_void_p), ld, m_out.ctypes.data_as(C.POINTER(C.c_int32)),
+            ),
+            K.ctx.handle,
+        )
+        Hess[...] = buf.transpose(0, 2, 1)  # column-major matrices -> Hess[b, i, j]
+        return m_out
     ld = Hess.shape[0]
     if Hess.shape[0] != Hess.shape[1]:
         raise ValueError("Hess must be square")
     buf = np.zeros((ld, ld), dtype=np.complex128, order="F")
     m_out = C.c_int32()
-    c = _op_coeffs(H, K.gen, coeffs)
     L.check(
         K.ctx._lib.qp_arnoldi(
             K.handle, L.ptr(c), Psi.handle, int(m), float(dt), 1 if extended else 0, float(norm_min),
@@ -215,8 +236,7 @@ class NewtonWrk:
             m_max = v0.n - 1
             if m_max <= 2:
                 raise ValueError("Newton propagation requires state dimension > 2")
-        if v0.batch != 1:
-            raise ValueError("Newton propagation handles a single state (batch == 1)")
+        self.batch = v0.batch  # > 1: a bundle of states sharing the generator (library host step only)
         self.m_max = m_max
         self.krylov = KrylovWrk(v0, H, m_max)
         self.v = v0.similar()
@@ -285,6 +305,8 @@ def newton_(Psi: DeviceState, H, dt, wrk: NewtonWrk, func=None, norm_min=1e-14, 
         raise AssertionError("dt must be non-zero")
     if host_step == "library":
         return _newton_library(Psi, H, dt, wrk, func, norm_min, relerr, max_restarts, coeffs)
+    if Psi.batch != 1:
+        raise ValueError('host_step="python" handles a single state; bundles run with host_step="library"')
     func = _default_func if func is None else func
     K = wrk.krylov
     m = wrk.m_max

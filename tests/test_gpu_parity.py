@@ -729,6 +729,104 @@ def test_newton_exact_krylov_breakdown(qp, ctx, hermitian):
     assert np.all(np.isfinite(q3)) and np.linalg.norm(q3) < 1e-14
 
 
+@pytest.mark.parametrize("hermitian", [True, False])
+def test_state_bundle_arnoldi_and_newton(qp, ctx, hermitian):
+    """a bundle of B states sharing one generator through the batched Krylov workspace:
+    per-state Hessenberg matrices equal the single-state ones, Arnoldi vectors are orthonormal per
+    state, and the batched newton! equals B single-state propagations and the dense exponential
+    (different states converge after different numbers of restarts; one is an exact eigenvector and
+    takes the shortcut of src/newton.jl:289-295)."""
+    rng = np.random.default_rng(21 + hermitian)
+    N, B, m = 60, 5, 6
+    A = rand_sparse(rng, N, 0.15, hermitian=hermitian)
+    A = (A * (4.0 / np.max(np.abs(np.linalg.eigvals(A.toarray()))))).tocsr()
+    psi = rand_state(rng, N, B)
+    psi[:, 1] *= 0.1                                     # different norms (the convergence test of newton! is absolute)
+    if hermitian:
+        ev, U = np.linalg.eigh(A.toarray())
+        psi[:, 3] = U[:, 7]                              # an exact eigenvector
+    st = qp.DeviceState.from_host(ctx, psi)
+    wrk = qp.NewtonWrk(st, A, m_max=m)
+    # Arnoldi, bundle vs one state at a time
+    v = st.copy()
+    nrm = v.norm()
+    vh = psi / nrm
+    v.upload(vh)
+    Hess = np.zeros((B, m + 1, m + 1), dtype=np.complex128)
+    m_out = qp.arnoldi_(Hess, wrk.krylov, m, v, A, 0.7, norm_min=1e-12, coeffs=[])
+    if hermitian:
+        assert m_out[3] == 1                             # the eigenvector exhausts its Krylov space at once
+    for b in range(B):
+        s1 = qp.DeviceState.from_host(ctx, vh[:, b].copy())
+        w1 = qp.NewtonWrk(s1, A, m_max=m)
+        H1 = np.zeros((m + 1, m + 1), dtype=np.complex128)
+        m1 = qp.arnoldi_(H1, w1.krylov, m, s1, A, 0.7, norm_min=1e-12, coeffs=[])
+        assert m1 == m_out[b]
+        if m1 == m:
+            assert np.max(np.abs(Hess[b] - H1)) < 1e-12
+    Q = np.stack([wrk.krylov.get(j, st.similar()).to_host() for j in range(m + 1)])   # (m+1, N, B)
+    for b in range(B):
+        k = m_out[b] + (1 if m_out[b] == m else 0)
+        G = Q[:k, :, b].conj() @ Q[:k, :, b].T
+        assert np.max(np.abs(G - np.eye(k))) < 1e-12
+    # newton! on the bundle
+    dt = 0.9
+    out = qp.newton_(st, A, dt, wrk, coeffs=[], max_restarts=200)
+    got = out.to_host()
+    want = sla.expm(-1j * dt * A.toarray()) @ psi
+    for b in range(B):
+        assert rel(got[:, b], want[:, b]) < RTOL
+        s1 = qp.DeviceState.from_host(ctx, psi[:, b].copy())
+        w1 = qp.NewtonWrk(s1, A, m_max=m)
+        qp.newton_(s1, A, dt, w1, coeffs=[], max_restarts=200)
+        assert rel(got[:, b], s1.to_host()) < 1e-11
+
+
+def test_state_bundle_forward_store_backward_consume(qp, ctx):
+    """The sweep pattern of GRAPE / Krotov (reference src/cheby_propagator.jl:147-152, 353-356;
+    consumer pattern test/test_exputils.jl:148-172): a bundle of states is propagated forward with
+    every time slot stored (device-resident copies), a bundle of co-states is propagated BACKWARD from
+    the final time, and at every slot the stored forward states are consumed: the overlaps
+    <chi_k(t_n)|psi_k(t_n)> must not depend on n (unitary evolution), for Chebyshev and for Newton."""
+    rng = np.random.default_rng(77)
+    w = qp.workloads.config2_tfim(6, nt=9, dt=0.1)
+    N, B = w["psi0"].shape[0], 4
+    H0, H1, H2 = w["ops"]
+    tl = w["tlist"]
+    mids = O.get_tlist_midpoints(tl)
+    coeffs = [[w["controls"][0](t), w["controls"][1](t)] for t in mids]
+    psi0, chiT = rand_state(rng, N, B), rand_state(rng, N, B)
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    dt = tl[1] - tl[0]
+    for method in ("cheby", "newton"):
+        psi = qp.DeviceState.from_host(ctx, psi0)
+        chi = qp.DeviceState.from_host(ctx, chiT)
+        if method == "cheby":
+            wrk_f = qp.ChebyWrk(psi, gen, 2.02 * w["E_max"], -1.01 * w["E_max"], dt)
+            step = lambda s, c, sign: qp.cheby_(s, None, sign * dt, wrk_f, coeffs=c)                         # noqa: E731
+        else:
+            wrk_n = qp.NewtonWrk(psi, gen, m_max=8)
+            step = lambda s, c, sign: qp.newton_(s, gen, sign * dt, wrk_n, coeffs=c)                         # noqa: E731
+        storage = qp.init_storage(psi, tl)                 # list of nt slots (device-resident bundle copies)
+        qp.write_to_storage(storage, 1, psi)
+        for n in range(1, len(tl)):
+            step(psi, coeffs[n - 1], +1)
+            qp.write_to_storage(storage, n + 1, psi)
+        fwd = qp.DeviceState(ctx, N, B)
+        tau = [chi.dot(qp.get_from_storage_(fwd, storage, len(tl)))]
+        for n in range(len(tl) - 1, 0, -1):               # backward sweep consuming the stored forward states
+            step(chi, coeffs[n - 1], -1)
+            tau.append(chi.dot(qp.get_from_storage_(fwd, storage, n)))
+        tau = np.array(tau)                               # (nt, B)
+        assert np.max(np.abs(tau - tau[0])) < 1e-10
+        assert np.max(np.abs(tau[0] - np.einsum("nb,nb->b", chiT.conj(), psi.to_host()))) < 1e-12
+        # and the backward-propagated co-states returned to chi(0) = U^+ chi(T): compare with the oracle per state
+        U = np.eye(N, dtype=complex)
+        for c in coeffs:
+            U = sla.expm(-1j * dt * (H0 + c[0] * H1 + c[1] * H2).toarray()) @ U
+        assert rel(chi.to_host(), U.conj().T @ chiT) < RTOL
+
+
 def test_specrange_arnoldi_brackets_spectrum(qp, ctx):
     """test/test_specrad.jl:80-144: :arnoldi within 5% of Δ outside the true spectrum;
     :diag exact; :manual / :auto dispatch."""
