@@ -100,6 +100,7 @@ extern "C" int32_t qp_ctx_destroy(qp_ctx_t ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_red) cudaFree(ctx->d_red);
+  if (ctx->d_part) cudaFree(ctx->d_part);
   if (ctx->h_red) cudaFreeHost(ctx->h_red);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -152,6 +153,41 @@ int32_t qp_ctx_reserve_stage(qp_ctx_t ctx, size_t elems) {
   ctx->stage_elems = 0;
   QP_CUDA(ctx, cudaMallocHost(&ctx->h_stage, elems * sizeof(qp_c128)));
   ctx->stage_elems = elems;
+  return QP_OK;
+}
+
+int32_t qp_ctx_reserve_part(qp_ctx_t ctx, size_t doubles) {
+  if (ctx->part_doubles >= doubles) return QP_OK;
+  QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_part);
+  ctx->d_part = nullptr;
+  ctx->part_doubles = 0;
+  QP_CUDA(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * doubles));
+  ctx->part_doubles = doubles;
+  return QP_OK;
+}
+
+// one block per trajectory: every thread adds its slots (fixed stride), then a fixed-order tree
+__global__ void __launch_bounds__(256)
+k_part_reduce(const double* __restrict__ part, int64_t n_slots, int64_t batch, double* __restrict__ chk) {
+  const int64_t b = blockIdx.x;
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < n_slots; i += 256)
+    for (int k = 0; k < 3; ++k) s[k] += part[(i * batch + b) * 3 + k];
+  __shared__ double sh[256][3];
+  for (int k = 0; k < 3; ++k) sh[threadIdx.x][k] = s[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int k = 0; k < 3; ++k) sh[threadIdx.x][k] += sh[threadIdx.x + o][k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) chk[3 * b + threadIdx.x] = sh[0][threadIdx.x];
+}
+
+int32_t qp_part_reduce(qp_ctx_t ctx, const double* part, int64_t n_slots, int64_t batch, double* chk) {
+  k_part_reduce<<<(unsigned)batch, 256, 0, ctx->stream>>>(part, n_slots, batch, chk);
+  QP_LAUNCHED(ctx);
   return QP_OK;
 }
 

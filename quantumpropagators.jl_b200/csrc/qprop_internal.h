@@ -47,6 +47,9 @@ struct qp_ctx_s {
   double* d_red = nullptr;
   double* h_red = nullptr;
   size_t red_doubles = 0;
+  // per-warp / per-tile partial sums of the fused expectation value and the normalization check
+  double* d_part = nullptr;
+  size_t part_doubles = 0;
   // small pinned staging area for per-step coefficient uploads
   qp_c128* h_stage = nullptr;
   size_t stage_elems = 0;
@@ -274,6 +277,9 @@ int32_t qp_fail(qp_ctx_t ctx, int32_t code, const char* fmt, ...);
 int32_t qp_ctx_bind(qp_ctx_t ctx);  // cudaSetDevice
 int32_t qp_ctx_reserve_red(qp_ctx_t ctx, size_t doubles);
 int32_t qp_ctx_reserve_stage(qp_ctx_t ctx, size_t elems);
+int32_t qp_ctx_reserve_part(qp_ctx_t ctx, size_t doubles);
+// chk[b][k] = sum over the n_slots slots of part[slot][b][k] in a fixed order (deterministic)
+int32_t qp_part_reduce(qp_ctx_t ctx, const double* part, int64_t n_slots, int64_t batch, double* chk);
 
 // timers ("matrix-vector product", "prop_step!", ...): CUDA events on the ctx stream
 struct QpScopedTimer {

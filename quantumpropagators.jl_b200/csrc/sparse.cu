@@ -1169,6 +1169,27 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
 // kernel dispatch
 // ---------------------------------------------------------------------------------------
 
+// Deterministic sums of the single-state kernels (normalization check, fused expectation value): the
+// launch gets a zeroed buffer of one slot per warp, every warp stores its partial sums there, and
+// part_end adds the slots up in a fixed order into e.chk.  QPROP_ATOMIC_SUMS=1 keeps the atomics.
+template <int EPI>
+static int32_t part_begin(qp_gen_t gen, EpiArgs& e, int64_t n_warps) {
+  e.part = nullptr;
+  if (!epi_has_sums(EPI) || e.chk == nullptr) return QP_OK;
+  static const int atomic = getenv("QPROP_ATOMIC_SUMS") ? atoi(getenv("QPROP_ATOMIC_SUMS")) : 0;
+  if (atomic) return QP_OK;
+  qp_ctx_t ctx = gen->ctx;
+  QP_CHECK(qp_ctx_reserve_part(ctx, (size_t)3 * (size_t)n_warps));
+  QP_CUDA(ctx, cudaMemsetAsync(ctx->d_part, 0, sizeof(double) * 3 * (size_t)n_warps, ctx->stream));
+  e.part = ctx->d_part;
+  return QP_OK;
+}
+template <int EPI>
+static int32_t part_end(qp_gen_t gen, const EpiArgs& e, int64_t n_warps) {
+  if (e.part == nullptr) return QP_OK;
+  return qp_part_reduce(gen->ctx, e.part, n_warps, 1, e.chk);
+}
+
 // TMA-staged SELL kernel: one CTA per SM (or a small multiple when a CTA's slice range would
 // exceed the staged offset table), dynamic shared memory = stages + barriers + slice offsets.
 template <int EPI, int WARPS, int STAGES, int CH>
@@ -1186,9 +1207,11 @@ static int32_t launch_sell_tma(qp_gen_t gen, const MatView& m, const double2* x,
     ctx->smem_configured.insert((const void*)kern);
   }
   if (smem > 226 * 1024) return qp_fail(ctx, QP_ERR_INTERNAL, "TMA kernel needs %zu bytes of shared memory", smem);
-  kern<<<(unsigned)ctas, WARPS * 32, smem, ctx->stream>>>(m, gen->d_coef, gen->n_ops, x, e, spc);
+  EpiArgs e2 = e;
+  QP_CHECK(part_begin<EPI>(gen, e2, ctas * WARPS));
+  kern<<<(unsigned)ctas, WARPS * 32, smem, ctx->stream>>>(m, gen->d_coef, gen->n_ops, x, e2, spc);
   QP_LAUNCHED(ctx);
-  return QP_OK;
+  return part_end<EPI>(gen, e2, ctas * WARPS);
 }
 
 static DictView make_dict_view(qp_gen_t gen) {
@@ -1240,9 +1263,11 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   cfg.numAttrs = pdl ? 1 : 0;
   const double2* coef = gen->d_coef;
   const int spc_i = (int)spc;
-  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, m, coef, x, e, spc_i));
+  EpiArgs e2 = e;
+  QP_CHECK(part_begin<EPI>(gen, e2, ctas * wpc));
+  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, m, coef, x, e2, spc_i));
   QP_LAUNCHED(ctx);
-  return QP_OK;
+  return part_end<EPI>(gen, e2, ctas * wpc);
 }
 
 template <int EPI, int CB, int REALV, int T, int G, int LATE>
@@ -1331,16 +1356,21 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     col_ranges = (nh + cols - 1) / cols;
     if (col_ranges > 65535) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "left/right generator too large for one launch");
     dim3 grid((unsigned)row_blocks, (unsigned)col_ranges);
+    EpiArgs e2 = e;
+    QP_CHECK(part_begin<EPI>(gen, e2, row_blocks * col_ranges * 8));
     k_spmv_lr<EPI, JB><<<grid, 256, sizeof(LRTerm) * gen->n_lr_terms, st>>>(gen->d_lr_terms, gen->n_lr_terms, gen->n_ops, nh,
-                                                                               gen->d_coef, x, e, (int)cols);
+                                                                               gen->d_coef, x, e2, (int)cols);
     QP_LAUNCHED(ctx);
-    return QP_OK;
+    return part_end<EPI>(gen, e2, row_blocks * col_ranges * 8);
   }
   if (gen->format == QP_FORMAT_DENSE) {
     if (batch != 1) return launch_dense_batched<EPI>(gen, coef_stride, x, batch, e);  // FP64 tensor cores
-    k_gemv_dense<EPI><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e);
+    EpiArgs e2 = e;
+    const int64_t gblocks = (n * 32 + 255) / 256;
+    QP_CHECK(part_begin<EPI>(gen, e2, gblocks * 8));
+    k_gemv_dense<EPI><<<(unsigned)gblocks, 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e2);
     QP_LAUNCHED(ctx);
-    return QP_OK;
+    return part_end<EPI>(gen, e2, gblocks * 8);
   }
   if (batch >= 32) {  // two-pass tiled path (tile.cu): structured generators, batch a multiple of 32
     bool handled = false;
@@ -1418,9 +1448,11 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     int64_t blocks = (gen->n_slices + 7) / 8;
     int64_t cap = (int64_t)ctx->sm_count * occ;
     if (blocks > cap) blocks = cap;
-    k_spmv_sell<EPI><<<(unsigned)blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e);
+    EpiArgs e2 = e;
+    QP_CHECK(part_begin<EPI>(gen, e2, blocks * 8));
+    k_spmv_sell<EPI><<<(unsigned)blocks, 256, 0, st>>>(m, gen->d_coef, gen->n_ops, x, e2);
     QP_LAUNCHED(ctx);
-    return QP_OK;
+    return part_end<EPI>(gen, e2, blocks * 8);
   }
   MatView m{gen->d_mptr, gen->d_mcolop, gen->d_mval, n};
   const int lanes = gen->lanes;
@@ -1440,17 +1472,19 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   const double2* coef = gen->d_coef;
   const int n_ops = gen->n_ops;
   cudaError_t le = cudaSuccess;
+  EpiArgs e2 = e;
+  QP_CHECK(part_begin<EPI>(gen, e2, (int64_t)blocks * 8));
   switch (lanes) {
-    case 1: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<1, EPI>, m, coef, n_ops, x, e); break;
-    case 2: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<2, EPI>, m, coef, n_ops, x, e); break;
-    case 4: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<4, EPI>, m, coef, n_ops, x, e); break;
-    case 8: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<8, EPI>, m, coef, n_ops, x, e); break;
-    case 16: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<16, EPI>, m, coef, n_ops, x, e); break;
-    default: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<32, EPI>, m, coef, n_ops, x, e); break;
+    case 1: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<1, EPI>, m, coef, n_ops, x, e2); break;
+    case 2: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<2, EPI>, m, coef, n_ops, x, e2); break;
+    case 4: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<4, EPI>, m, coef, n_ops, x, e2); break;
+    case 8: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<8, EPI>, m, coef, n_ops, x, e2); break;
+    case 16: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<16, EPI>, m, coef, n_ops, x, e2); break;
+    default: le = cudaLaunchKernelEx(&cfg, k_spmv_csr<32, EPI>, m, coef, n_ops, x, e2); break;
   }
   QP_CUDA(ctx, le);
   QP_LAUNCHED(ctx);
-  return QP_OK;
+  return part_end<EPI>(gen, e2, (int64_t)blocks * 8);
 }
 
 int32_t qp_launch_fused(qp_gen_t gen, int epi, int coef_stride, const double2* x, int64_t batch,

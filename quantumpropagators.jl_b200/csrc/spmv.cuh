@@ -45,6 +45,8 @@ struct EpiArgs {
   double2* y;            // MUL: y;  FIRST: v1 out;  MID/LAST: v_{k-1} in, v_{k+1} out
   double2* acc;          // psi accumulator
   double* chk;           // normalization-check accumulators [batch][3] or nullptr
+  double* part;          // deterministic mode: per-warp (single states) / per-tile (tiled batched kernel)
+                         // partial sums, added up in a fixed order by k_part_reduce (nullptr: atomics)
   int vec_hint;          // 1: access the Chebyshev vectors with an L2 evict_last policy (TMA kernel)
 };
 
@@ -181,6 +183,21 @@ __device__ __forceinline__ void chk_flush(const EpiArgs& e, int64_t b, double dr
   atomicAdd(e.chk + 3 * b + 2, nn);
 }
 
+// single-state kernels: one partial per warp.  With e.part set the warp stores its sums in its own slot
+// (global warp index) and a second kernel adds the slots up in a fixed order -- run-to-run reproducible
+// expectation values -- otherwise atomics.
+__device__ __forceinline__ void chk_flush_warp(const EpiArgs& e, double dr, double di, double nn) {
+  if (e.chk == nullptr) return;
+  if (e.part != nullptr) {
+    const int64_t gw = (((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    e.part[3 * gw + 0] = dr;
+    e.part[3 * gw + 1] = di;
+    e.part[3 * gw + 2] = nn;
+    return;
+  }
+  chk_flush(e, 0, dr, di, nn);
+}
+
 // ---------------------------------------------------------------------------------------
 // merged CSR, batch == 1: LANES lanes per row
 // ---------------------------------------------------------------------------------------
@@ -263,7 +280,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if ((threadIdx.x & 31) == 0) chk_flush(e, 0, dr, di, nn);
+    if ((threadIdx.x & 31) == 0) chk_flush_warp(e, dr, di, nn);
   }
 }
 
@@ -308,7 +325,7 @@ k_spmv_sell(MatView m, const double2* __restrict__ coef, int n_ops, const double
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
   }
 }
 
@@ -500,7 +517,7 @@ k_spmv_sell_tma(MatView m, const double2* __restrict__ coef, int n_ops, const do
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
   }
 }
 
@@ -716,7 +733,7 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
   }
 }
 
@@ -991,7 +1008,7 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
   }
 }
 

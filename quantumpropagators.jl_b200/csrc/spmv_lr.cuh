@@ -164,6 +164,6 @@ k_spmv_lr(const LRTerm* __restrict__ terms, int n_terms, int n_ops, int64_t nh, 
       di += __shfl_xor_sync(0xffffffffu, di, o);
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
     }
-    if (lane == 0) chk_flush(e, 0, dr, di, nn);
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
   }
 }

@@ -363,6 +363,7 @@ k_spmm_tile(const __grid_constant__ TileView tv, const __grid_constant__ ConstTa
   uint4* s_codes = reinterpret_cast<uint4*>(s_tab32 + tv.n32);
   const int code_words = tv.S * tv.WT[0] > tv.NH * tv.WT[1] ? tv.S * tv.WT[0] : tv.NH * tv.WT[1];
   double* s_diag = reinterpret_cast<double*>(s_codes + code_words);  // [S][4] (3 used)
+  double* s_red = s_diag + (size_t)tv.S * 4;                          // [TILE_WARPS][32][3], deterministic sums only
   for (int j = threadIdx.x; j < tv.n16; j += TILE_THREADS) s_tab16[j] = tv.tab16[j];
   for (int j = threadIdx.x; j < tv.n32; j += TILE_THREADS) s_tab32[j] = tv.tab32[j];
   __syncthreads();
@@ -477,10 +478,31 @@ k_spmm_tile(const __grid_constant__ TileView tv, const __grid_constant__ ConstTa
     ra.diag_base = diag_base;
     if (pass == 0) tile_rows<EPI, NOPS, 0, CT>(tv, ctab, ra, x, e, u, dr, di, nn);
     else tile_rows<EPI, NOPS, 1, CT>(tv, ctab, ra, x, e, u, dr, di, nn);
-    if (pass == 1 && epi_has_sums(EPI) && e.chk != nullptr) chk_flush(e, c0 + lane, dr, di, nn);
+    const bool det_sums = pass == 1 && epi_has_sums(EPI) && e.chk != nullptr && e.part != nullptr;
+    if (pass == 1 && epi_has_sums(EPI) && e.chk != nullptr) {
+      if (det_sums) {  // per-warp sums -> shared memory; warp 0 adds them in a fixed order below
+        s_red[(warp * 32 + lane) * 3 + 0] = dr;
+        s_red[(warp * 32 + lane) * 3 + 1] = di;
+        s_red[(warp * 32 + lane) * 3 + 2] = nn;
+      } else {
+        chk_flush(e, c0 + lane, dr, di, nn);
+      }
+    }
 
     // every warp is done with the tile (the next item overwrites it) and has issued its stores
     __syncthreads();
+    if (det_sums && warp == 0) {  // slot = B-tile index: e.part[tile][trajectory][3]
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int w2 = 0; w2 < TILE_WARPS; ++w2) {
+        s0 += s_red[(w2 * 32 + lane) * 3 + 0];
+        s1 += s_red[(w2 * 32 + lane) * 3 + 1];
+        s2 += s_red[(w2 * 32 + lane) * 3 + 2];
+      }
+      double* dst = e.part + ((int64_t)tile * batch + c0 + lane) * 3;
+      dst[0] = s0;
+      dst[1] = s1;
+      dst[2] = s2;
+    }
     if (threadIdx.x == 0) {
       __threadfence();
       atomicAdd((pass == 0 ? tv.doneA : tv.doneB) + g, 1ull);
@@ -496,7 +518,8 @@ k_spmm_tile(const __grid_constant__ TileView tv, const __grid_constant__ ConstTa
 static size_t tile_smem_bytes(const qptile::TileFormat& f, size_t n16, size_t n32) {
   const size_t rows = (size_t)std::max(f.S, f.NH);
   const size_t code_words = std::max((size_t)f.S * f.WT[0], (size_t)f.NH * f.WT[1]);
-  return rows * 512 + n16 * sizeof(Entry16) + n32 * sizeof(Entry32) + code_words * 16 + (size_t)f.S * 32;
+  return rows * 512 + n16 * sizeof(Entry16) + n32 * sizeof(Entry32) + code_words * 16 + (size_t)f.S * 32 +
+         (size_t)TILE_WARPS * 32 * 3 * sizeof(double);  // + the per-warp sums of the deterministic reductions
 }
 
 void qp_tile_free(qp_tile_s* t) {
@@ -640,8 +663,20 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const double2* coef = gen->d_coef;
-  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tv, ctab, coef, coef_stride, batch, x, e));
+  // deterministic sums (fused expectation value, normalization check): one slot per B tile and
+  // trajectory, added up in a fixed order afterwards
+  EpiArgs e2 = e;
+  e2.part = nullptr;
+  static const int atomic = getenv("QPROP_ATOMIC_SUMS") ? atoi(getenv("QPROP_ATOMIC_SUMS")) : 0;
+  const bool det = epi_has_sums(EPI) && e.chk != nullptr && !atomic;
+  if (det) {
+    const size_t doubles = (size_t)f.S * (size_t)batch * 3;
+    QP_CHECK(qp_ctx_reserve_part(ctx, doubles));
+    e2.part = ctx->d_part;  // every (tile, trajectory) slot is written by exactly one item: no memset needed
+  }
+  QP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tv, ctab, coef, coef_stride, batch, x, e2));
   QP_LAUNCHED(ctx);
+  if (det) QP_CHECK(qp_part_reduce(ctx, e2.part, f.S, batch, e2.chk));
   return QP_OK;
 }
 

@@ -1007,6 +1007,23 @@ def test_expval_fused(qp, ctx, fmt, n, B):
     np.testing.assert_array_equal(dx.to_host(), X)  # the state is untouched
 
 
+@pytest.mark.parametrize("fmt,n_spins,B", [("selld", 14, 1), ("sell", 14, 1), ("csr", 12, 1), ("auto", 8, 64)])
+def test_expval_bitwise_reproducible(qp, ctx, fmt, n_spins, B):
+    """The fused expectation value adds per-warp (single states) / per-tile (tiled batched kernel)
+    partial sums in a fixed order: repeated calls agree to the last bit (no atomics)."""
+    rng = np.random.default_rng(n_spins)
+    H0, H1, H2 = qp.workloads.tfim_chain(n_spins)
+    N = H0.shape[0]
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2, fmt)
+    x = qp.DeviceState.from_host(ctx, rand_state(rng, N, None if B == 1 else B))
+    vals = [np.atleast_1d(gen.expval(x, [0.3, -0.7])) for _ in range(6)]
+    for v in vals[1:]:
+        assert np.array_equal(v.view(np.float64), vals[0].view(np.float64))
+    X = x.to_host().reshape(N, -1)
+    want = np.einsum("nb,nb->b", X.conj(), (H0 + 0.3 * H1 - 0.7 * H2) @ X)
+    assert np.max(np.abs(vals[0] - want)) < 1e-11
+
+
 def test_expval_dense(qp, ctx):
     rng = np.random.default_rng(21)
     n = 130
