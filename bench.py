@@ -93,7 +93,7 @@ def profiled_traffic(fmt):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             d = json.load(f)
-        return d.get(fmt), d.get("_source", "profiles/traffic.json (ncu --set full capture, not measured in this run)")
+        return d.get(fmt), d.get("_source_" + fmt, "profiles/traffic.json") + " -- an ncu capture, not measured in this run"
     except Exception:
         return None, None
 

@@ -52,6 +52,7 @@ struct TileView {
   unsigned long long* doneA;     // [chunks] items of pass A finished (monotonic over launches)
   unsigned long long* doneB;     // [chunks]
   unsigned long long epoch;      // 1-based launch number of this view
+  long long spin_limit;          // cycles a dependency wait may spin before the kernel traps (0: no limit)
 };
 
 // Small 16-byte tables travel as a kernel parameter (constant bank): a warp-uniform look-up is then
@@ -100,11 +101,11 @@ __device__ __forceinline__ void st_cg(double2* p, double2 v) {
 }
 
 // spin until *ctr >= target; a dependency that never arrives is a bug -- trap instead of hanging the GPU
-__device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsigned long long target) {
+__device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsigned long long target, long long limit) {
   const long long t0 = clock64();
   while (ld_acquire(ctr) < target) {
     __nanosleep(64);
-    if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s
+    if (limit > 0 && clock64() - t0 > limit) __trap();  // default 2^33 cycles ~ 4 s; QPROP_TILE_SPIN_LIMIT=0 under sanitizers
   }
 }
 
@@ -452,9 +453,9 @@ k_spmm_tile(const __grid_constant__ TileView tv, const __grid_constant__ ConstTa
     // 3. dependencies: pass A overwrites the ring slot pass B of chunk g - 3 reads; pass B needs all of A(g)
     if (threadIdx.x == 0) {
       if (pass == 0) {
-        if (g >= TILE_RING) wait_counter(tv.doneB + (g - TILE_RING), tgtB);
+        if (g >= TILE_RING) wait_counter(tv.doneB + (g - TILE_RING), tgtB, tv.spin_limit);
       } else {
-        wait_counter(tv.doneA + g, tgtA);
+        wait_counter(tv.doneA + g, tgtA, tv.spin_limit);
       }
     }
     cp_async_wait_all();
@@ -638,6 +639,8 @@ static int32_t tile_launch(qp_gen_t gen, int coef_stride, const double2* x, int6
   tv.doneA = t->d_done;
   tv.doneB = t->d_done + t->chunk_cap;
   tv.epoch = ++t->epoch;
+  static const long long spin_limit = getenv("QPROP_TILE_SPIN_LIMIT") ? atoll(getenv("QPROP_TILE_SPIN_LIMIT")) : (1ll << 33);
+  tv.spin_limit = spin_limit;
   auto kern = k_spmm_tile<EPI, NOPS, CT>;
   static const ConstTab empty_tab = {};
   const ConstTab& ctab = CT ? *t->h_ctab : empty_tab;
