@@ -93,6 +93,10 @@ struct qp_ens_s {
       return qp_fail((ctx), QP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, (api)->GetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 
+// NCCL sets up its channels and peer connections lazily at the first collective (~1 s at 8 ranks):
+// do that here, at creation, so that the first gather costs what every gather costs.
+static int32_t ens_warm_up(qp_ens_t E);
+
 extern "C" int32_t qp_ens_shard(int64_t n_total, int32_t rank, int32_t n_ranks, int64_t* b0, int64_t* b1) {
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks || n_total < 0 || !b0 || !b1)
     return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_ens_shard: rank %d outside a world of %d", rank, n_ranks);
@@ -143,6 +147,11 @@ extern "C" int32_t qp_ens_create(const int32_t* devices, int32_t n_ranks, qp_ens
       return rc;
     }
     E->use_nccl = true;
+    int32_t wrc = ens_warm_up(E);
+    if (wrc != QP_OK) {
+      qp_ens_destroy(E);
+      return wrc;
+    }
   } else if (n_ranks > 1 && !distinct) {
     for (int i = 1; i < n_ranks; ++i)
       if (devices[i] != devices[0]) {
@@ -196,6 +205,11 @@ extern "C" int32_t qp_ens_create_rank(qp_ctx_t ctx, int32_t rank, int32_t n_rank
       return qp_fail(ctx, QP_ERR_CUDA, "ncclCommInitRank failed: %s", api->GetErrorString(r));
     }
     E->use_nccl = true;
+    int32_t wrc = ens_warm_up(E);
+    if (wrc != QP_OK) {
+      qp_ens_destroy(E);
+      return wrc;
+    }
   }
   *out = E;
   return QP_OK;
@@ -295,6 +309,29 @@ static int32_t ens_exchange(qp_ens_t E, const std::vector<const double2*>& src, 
     }
   }
   return QP_OK;
+}
+
+static int32_t ens_warm_up(qp_ens_t E) {
+  // one trajectory per rank, one number each: the same grouped broadcasts a gather issues
+  const int nl = (int)E->ctx.size();
+  std::vector<int64_t> off((size_t)E->n_ranks + 1);
+  for (int r = 0; r <= E->n_ranks; ++r) off[r] = r;
+  std::vector<double2*> d_src(nl, nullptr);
+  std::vector<const double2*> src(nl);
+  int32_t rc = QP_OK;
+  for (int i = 0; i < nl && rc == QP_OK; ++i) {
+    rc = qp_ctx_bind(E->ctx[i]);
+    if (rc == QP_OK && cudaMalloc(&d_src[i], sizeof(double2)) != cudaSuccess) rc = qp_fail(E->ctx[i], QP_ERR_OOM, "qp_ens: cudaMalloc failed");
+    if (rc == QP_OK) cudaMemsetAsync(d_src[i], 0, sizeof(double2), E->ctx[i]->stream);
+    src[i] = d_src[i];
+  }
+  if (rc == QP_OK) rc = ens_exchange(E, src, 1, off);
+  for (int i = 0; i < nl; ++i) {
+    cudaSetDevice(E->ctx[i]->device);
+    cudaStreamSynchronize(E->ctx[i]->stream);
+    cudaFree(d_src[i]);
+  }
+  return rc;
 }
 
 static int32_t ens_offsets(qp_ens_t E, int64_t n_total, std::vector<int64_t>& off) {
