@@ -455,6 +455,52 @@ def test_tiled_cheby_per_trajectory(qp, ctx, B, backward):
     assert np.max(np.abs(st.norm() - 1)) < 1e-12
 
 
+@pytest.mark.parametrize("n_ops", [1, 2])
+def test_tiled_one_and_two_operators(qp, ctx, n_ops):
+    """The NOPS = 1 / 2 instantiations of the tiled kernel: a drift-only generator and drift + one
+    control (kind P = the pair (drift, control) when their entries share columns with |v| equal), all
+    epilogues through a two-coefficient (CHEB_ONLY) and a many-coefficient Chebyshev step."""
+    rng = np.random.default_rng(40 + n_ops)
+    H0, H1, _ = qp.workloads.transmon_chain(4, 4)
+    ops = [H0 + H1] if n_ops == 1 else [H0 + 0.5 * H1, H1]     # shared columns, equal and unequal magnitudes
+    N, B = 256, 64
+    gen = qp.DeviceGenerator(ctx, ops, n_ops - 1)
+    assert gen.tile_info()["available"]
+    X = rand_state(rng, N, B)
+    x = qp.DeviceState.from_host(ctx, X)
+    y = x.similar()
+    c = [] if n_ops == 1 else [0.4 - 0.3j]
+    gen.mul(y, x, c, 1.0, 0.0)
+    Hd = (ops[0] if n_ops == 1 else ops[0] + c[0] * ops[1]).toarray()
+    assert np.max(np.abs(y.to_host() - Hd @ X)) < 1e-12
+    assert np.max(np.abs(gen.expval(x, c) - np.einsum("nb,nb->b", X.conj(), Hd @ X))) < 1e-12
+    # Chebyshev with a real coefficient (Hermitian): tiny dt -> 2 coefficients (CHEB_ONLY), larger dt -> FIRST/MID/LAST
+    cr = [] if n_ops == 1 else [0.4]
+    Hh = (ops[0] if n_ops == 1 else ops[0] + cr[0] * ops[1]).toarray()
+    bound = float(np.abs(Hh).sum(axis=1).max())
+    for dt, n_min in ((1e-14, 2), (0.7, 4)):
+        st = qp.DeviceState.from_host(ctx, X)
+        wrk = qp.ChebyWrk(st, gen, 2 * bound, -bound, dt)
+        assert (wrk.n_coeffs == 2) if n_min == 2 else (wrk.n_coeffs >= n_min)
+        qp.cheby_(st, None, dt, wrk, coeffs=cr, check_normalization=True)
+        want = sla.expm(-1j * dt * Hh) @ X
+        assert np.max(np.linalg.norm(st.to_host() - want, axis=0)) < 1e-10
+
+
+def test_tiled_normalization_check_fails_loudly(qp, ctx):
+    """A spectral range that is too small makes the Chebyshev recursion blow up: with
+    check_normalization the batched tiled path reports it (src/cheby.jl:194-200) instead of returning
+    garbage."""
+    rng = np.random.default_rng(3)
+    H0, H1, H2 = qp.workloads.transmon_chain(4, 4)
+    gen = qp.DeviceGenerator(ctx, [H0, H1, H2], 2)
+    st = qp.DeviceState.from_host(ctx, rand_state(rng, 256, 32))
+    wrk = qp.ChebyWrk(st, gen, 0.05, -0.025, 5.0)                # true spectral width is ~ 4
+    with pytest.raises(qp.QPropError) as exc:
+        qp.cheby_(st, None, 5.0, wrk, coeffs=[1.0, 1.0], check_normalization=True)
+    assert exc.value.status == -5 and "normalization" in str(exc.value).lower()
+
+
 def test_tiled_real_operators_and_unqualified_generators(qp, ctx):
     """TFIM (real operators, two diagonals, XOR couplings) on the tiled path; an unstructured random
     generator does not qualify and silently uses the one-pass kernels -- same results."""
