@@ -33,7 +33,8 @@ QP_FORMAT_SELL = 2
 QP_FORMAT_DENSE = 3
 QP_FORMAT_SELLD = 4
 QP_FORMAT_LR = 5
-FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense", 4: "selld", 5: "leftright"}
+QP_FORMAT_BITFLIP = 6
+FORMAT_NAMES = {0: "auto", 1: "csr", 2: "sell", 3: "dense", 4: "selld", 5: "leftright", 6: "bitflip"}
 
 
 class QPropLibraryError(RuntimeError):

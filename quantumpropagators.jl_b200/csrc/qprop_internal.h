@@ -144,6 +144,9 @@ struct DictView {
 // two-pass tiled format of the trajectory-batched path (tile.cu / tile_format.h), built lazily
 struct qp_tile_s;
 void qp_tile_free(qp_tile_s* t);
+// bit-flip (XOR-stencil) form of a generator for single states (bitflip.cu), detected at qp_gen_create
+struct qp_bitflip_s;
+void qp_bitflip_free(qp_bitflip_s* b);
 
 constexpr int QP_DICT_MAX = 4096;       // table entries incl. the padding entry
 constexpr int QP_DICT_HASH_CAP = 16384; // open-addressing capacity used while building
@@ -199,6 +202,7 @@ struct qp_gen_s {
   int64_t lr_n = 0;
   // dense: pointers to the row-major operators
   const double2** d_dense_ops = nullptr;
+  qp_bitflip_s* bitflip = nullptr;  // bit-flip (XOR-stencil) form for single states (bitflip.cu), QP_FORMAT_BITFLIP
   qp_tile_s* tile = nullptr;   // two-pass tiled format for batched states (nullptr: not tried yet)
   // device copy of the effective per-operator coefficients (drift ops = 1), [n_ops][B]
   double2* d_coef = nullptr;

@@ -617,6 +617,7 @@ static void gen_free(qp_gen_t g) {
   cudaFree(g->d_lr_terms);
   cudaFree(g->d_coef);
   qp_tile_free(g->tile);
+  qp_bitflip_free(g->bitflip);
   delete g;
 }
 
@@ -854,7 +855,7 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   // "The number of coefficients cannot exceed the number of operators" src/generators.jl:116-121
   QP_REQUIRE(ctx, n_coeffs >= 0 && n_coeffs <= n_ops,
              "qp_gen_create: the number of coefficients (%d) cannot exceed the number of operators (%d)", n_coeffs, n_ops);
-  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_LR, "qp_gen_create: bad format %d", format);
+  QP_REQUIRE(ctx, format >= QP_FORMAT_AUTO && format <= QP_FORMAT_BITFLIP, "qp_gen_create: bad format %d", format);
   bool any_dense = false, all_dense = true, any_lr = false, all_lr = true;
   for (int l = 0; l < n_ops; ++l) {
     QP_REQUIRE(ctx, ops[l] != nullptr, "qp_gen_create: operator %d is null", l);
@@ -1027,7 +1028,7 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   bool dict_ok = false;
   // attempted for every AUTO generator: besides the B = 1 SELL-D kernel (large N only) the
   // dictionary also serves the trajectory-batched kernel at any N
-  if ((format == QP_FORMAT_AUTO && !getenv("QPROP_NO_DICT")) || format == QP_FORMAT_SELLD) {
+  if ((format == QP_FORMAT_AUTO && !getenv("QPROP_NO_DICT")) || format == QP_FORMAT_SELLD || format == QP_FORMAT_BITFLIP) {
     int32_t rc = build_dict(ctx, g, &dict_ok, false);
     // typical second chance: a diagonal drift term with thousands of distinct energies on top of
     // couplings with a handful of values -- keep the diagonals as explicit vectors
@@ -1045,6 +1046,21 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
                           QP_DICT_MAX));
     }
   }
+  // bit-flip form (bitflip.cu): diagonal operators + uniform XOR stencils, no matrix stream at all
+  bool bitflip_ok = false;
+  if ((format == QP_FORMAT_AUTO && rows_ok && !getenv("QPROP_NO_BITFLIP")) || format == QP_FORMAT_BITFLIP) {
+    int32_t rc = qp_bitflip_build(g, &bitflip_ok);
+    if (rc == QP_OK && format == QP_FORMAT_BITFLIP && !bitflip_ok)
+      rc = qp_fail(ctx, QP_ERR_UNSUPPORTED,
+                   "qp_gen_create: QP_FORMAT_BITFLIP needs operators that are diagonal or the same set of (row XOR mask, value) "
+                   "entries in every row, N a multiple of 32");
+    if (rc != QP_OK) {
+      cudaFree(d_len);
+      cudaFree(d_slice_entries);
+      return bail(rc);
+    }
+  }
+  if (chosen == QP_FORMAT_AUTO && bitflip_ok) chosen = QP_FORMAT_BITFLIP;
   if (chosen == QP_FORMAT_AUTO) {
     const bool sell_ok = rows_ok && pad <= 1.25 && sell_entries < (uint64_t(1) << 32);
     // padded code slots per true nonzero (the code stream is 1-2 B/entry, so padding is cheap in
@@ -1084,7 +1100,10 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     g->d_sptr = nullptr;
     g->stored_entries = nnz_total;
   }
-  if (chosen == QP_FORMAT_SELLD) {
+  if (chosen == QP_FORMAT_BITFLIP) {
+    g->stored_entries = nnz_total;
+    g->stored_bytes = qp_bitflip_stored_bytes(g->bitflip);
+  } else if (chosen == QP_FORMAT_SELLD) {
     g->stored_entries = g->dict_words * (16 / g->code_bytes);
     g->stored_bytes = g->dict_words * 16 + (g->uniform_words ? 0 : 4 * (n_slices + 1)) + 16 * (int64_t)g->n_diag * n;
   } else {
@@ -1387,6 +1406,7 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     QP_LAUNCHED(ctx);
     return QP_OK;
   }
+  if (gen->format == QP_FORMAT_BITFLIP) return qp_launch_bitflip(gen, EPI, x, e);
   if (gen->format == QP_FORMAT_SELLD) {
     const DictView m = make_dict_view(gen);
     // compiled for 16 resident warps per SM (<= 128 registers): measured best on B200 against

@@ -1013,6 +1013,10 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
 }
 
 // two-pass tiled path for batched states (tile.cu); *handled = false: use the one-pass kernels
+// bit-flip (XOR-stencil) form (bitflip.cu): *ok = false if the generator does not have the structure
+int32_t qp_bitflip_build(qp_gen_t gen, bool* ok);
+int64_t qp_bitflip_stored_bytes(const qp_bitflip_s* b);
+int32_t qp_launch_bitflip(qp_gen_t gen, int epi, const double2* x, const EpiArgs& e);
 int32_t qp_launch_tile(qp_gen_t gen, int epi, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e,
                        bool* handled);
 int32_t qp_tile_info(qp_gen_t gen, int32_t* available, int32_t* S, int32_t* NH, int32_t* n_table, int64_t* entries);

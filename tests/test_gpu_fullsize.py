@@ -37,7 +37,7 @@ def test_config2_full_size_properties(qp, ctx, tfim20):
     psi2 /= np.linalg.norm(psi2)
     # forward then backward over the whole grid is the identity
     p = qp.init_prop(psi1, G, w["tlist"], "cheby", **kw)
-    assert p.wrk.gen.format == "selld"
+    assert p.wrk.gen.format == "bitflip"   # diagonal + uniform bit-flip operators, detected at N >= 148 * 1024
     norms = []
     while qp.prop_step(p) is not None:
         norms.append(p.state.norm())
@@ -168,7 +168,7 @@ def tfim20_oracle(tfim20_full):
     return dict(final=psi, n_coeffs=wrk.n_coeffs)
 
 
-@pytest.mark.parametrize("fmt", ["selld", "sell", "csr"])
+@pytest.mark.parametrize("fmt", ["bitflip", "selld", "sell", "csr"])
 def test_config2_full_tlist_vs_oracle(qp, ctx, tfim20_full, tfim20_oracle, fmt):
     """Config 2 (TFIM N = 2^20, H0 + 2 PWC controls) over the FULL 100-step tlist for every
     sparse storage format / kernel against the C oracle: ≤ 1e-10 on the final state, norm
