@@ -29,6 +29,9 @@ constexpr int BF_MAX_TERMS = 32;
 constexpr int BF_MAX_DIAG = 4;
 
 constexpr int BF_MAX_LOW = 8;
+constexpr int BF_MAX_JOINT = 2048;     // entries of the folded diagonal table (shared memory)
+constexpr int BF_DIAG_DISTINCT = 256;  // distinct values per coded diagonal
+constexpr int BF_HASH_CAP = 1024;
 
 struct BitflipView {
   int64_t n;
@@ -44,6 +47,13 @@ struct BitflipView {
   const double* diag_r[BF_MAX_DIAG];   // real diagonal (or nullptr)
   const double2* diag_c[BF_MAX_DIAG];  // complex diagonal (or nullptr)
   int diag_op[BF_MAX_DIAG];
+  // coded diagonals (all diagonals real with few distinct values each): one 16-bit code per row whose mixed-radix
+  // digits index the sorted tables of distinct values; the kernel prologue folds this launch's coefficients into
+  // one shared-memory table, so the diagonals cost 2 B and one look-up per row
+  const uint16_t* dcode;   // [n] or nullptr
+  const double* dtab;      // the tables, one after the other
+  int n_joint;
+  int dcount[BF_MAX_DIAG], dstride[BF_MAX_DIAG], doff[BF_MAX_DIAG];
   // REALC launches only: the products coefficient x value (and the diagonals' coefficients), computed on the
   // host from the host copy of the coefficients -- they reach the DFMAs straight from the constant bank
   double cre[BF_MAX_TERMS];
@@ -90,6 +100,51 @@ __global__ void k_bf_extract_diag(const uint32_t* __restrict__ ptr, const double
     dc[r] = v;
     dr[r] = v.x;
     if (v.y != 0.0) flags[1] = 1;
+  }
+}
+
+// distinct values of a real diagonal: open addressing on the bit patterns (-0.0 counts as 0.0)
+__global__ void k_bf_distinct(const double* __restrict__ d, int64_t n, unsigned long long* keys, int* flags) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const double val = d[r] + 0.0;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(val);
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 54) % BF_HASH_CAP;
+    int probes = 0;
+    for (; probes < BF_HASH_CAP; ++probes) {
+      unsigned long long cur = keys[h];
+      if (cur == key) break;
+      if (cur == ~0ull) {
+        cur = atomicCAS(&keys[h], ~0ull, key);
+        if (cur == ~0ull || cur == key) break;
+      }
+      h = (h + 1) % BF_HASH_CAP;
+    }
+    if (probes == BF_HASH_CAP) flags[0] = 1;
+  }
+}
+
+struct DiagTabs {
+  int n_diag;
+  const double* d[BF_MAX_DIAG];
+  int count[BF_MAX_DIAG], stride[BF_MAX_DIAG], off[BF_MAX_DIAG];
+};
+
+// code[r] = sum_i digit_i(r) * stride_i, digit_i = position of d_i[r] in the sorted table i
+__global__ void k_bf_encode(DiagTabs t, const double* __restrict__ tab, int64_t n, uint16_t* __restrict__ code, int* flags) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    for (int i = 0; i < t.n_diag; ++i) {
+      const double val = t.d[i][r] + 0.0;
+      int lo = 0, hi = t.count[i] - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[t.off[i] + mid] < val) lo = mid + 1;
+        else hi = mid;
+      }
+      if (tab[t.off[i] + lo] != val) flags[0] = 1;
+      c += lo * t.stride[i];
+    }
+    code[r] = (uint16_t)c;
   }
 }
 
@@ -244,6 +299,89 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
     v.op[v.n_high++] = 0;
   }
   if (v.n_high % 4 != 0) return fail(QP_OK);
+  // coded diagonals
+  bool diags_real = v.n_diag > 0;
+  for (int i = 0; i < v.n_diag; ++i) diags_real = diags_real && v.diag_r[i] != nullptr;
+  if (diags_real && !getenv("QPROP_BITFLIP_NO_CODES")) {
+    unsigned long long* d_keys = nullptr;
+    if (cudaMalloc(&d_keys, sizeof(unsigned long long) * BF_HASH_CAP) != cudaSuccess)
+      return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
+    std::vector<double> h_tab;
+    DiagTabs T;
+    memset(&T, 0, sizeof(T));
+    T.n_diag = v.n_diag;
+    bool codes_ok = true;
+    int64_t joint = 1;
+    for (int i = 0; i < v.n_diag && codes_ok; ++i) {
+      int h_flags[2] = {0, 0};
+      cudaMemsetAsync(d_keys, 0xFF, sizeof(unsigned long long) * BF_HASH_CAP, ctx->stream);
+      cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
+      k_bf_distinct<<<blocks, 256, 0, ctx->stream>>>(v.diag_r[i], n, d_keys, d_flags);
+      ctx->launches++;
+      std::vector<unsigned long long> h_keys(BF_HASH_CAP);
+      cudaMemcpyAsync(h_keys.data(), d_keys, sizeof(unsigned long long) * BF_HASH_CAP, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaFree(d_keys);
+        return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: distinct-value scan failed"));
+      }
+      std::vector<double> vals;
+      for (unsigned long long k : h_keys)
+        if (k != ~0ull) {
+          double x;
+          memcpy(&x, &k, 8);
+          vals.push_back(x);
+        }
+      bool has_nan = false;
+      for (double x : vals) has_nan = has_nan || x != x;
+      if (h_flags[0] != 0 || vals.empty() || (int)vals.size() > BF_DIAG_DISTINCT || has_nan) {
+        codes_ok = false;
+        break;
+      }
+      std::sort(vals.begin(), vals.end());
+      T.d[i] = v.diag_r[i];
+      T.count[i] = (int)vals.size();
+      T.stride[i] = (int)joint;
+      T.off[i] = (int)h_tab.size();
+      joint *= (int64_t)vals.size();
+      if (joint > BF_MAX_JOINT) codes_ok = false;
+      h_tab.insert(h_tab.end(), vals.begin(), vals.end());
+    }
+    cudaFree(d_keys);
+    if (codes_ok) {
+      double* d_tab = nullptr;
+      uint16_t* d_code = nullptr;
+      if (cudaMalloc(&d_tab, sizeof(double) * h_tab.size()) != cudaSuccess || cudaMalloc(&d_code, sizeof(uint16_t) * n) != cudaSuccess) {
+        cudaFree(d_tab);
+        return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of the diagonal codes failed"));
+      }
+      B->owned.push_back(d_tab);
+      B->owned.push_back(d_code);
+      int h_flags[2] = {0, 0};
+      cudaMemcpyAsync(d_tab, h_tab.data(), sizeof(double) * h_tab.size(), cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
+      k_bf_encode<<<blocks, 256, 0, ctx->stream>>>(T, d_tab, n, d_code, d_flags);
+      ctx->launches++;
+      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || h_flags[0] != 0)
+        return fail(qp_fail(ctx, QP_ERR_INTERNAL, "bit-flip form: encoding the diagonals failed"));
+      v.dcode = d_code;
+      v.dtab = d_tab;
+      v.n_joint = (int)joint;
+      for (int i = 0; i < v.n_diag; ++i) {
+        v.dcount[i] = T.count[i];
+        v.dstride[i] = T.stride[i];
+        v.doff[i] = T.off[i];
+        // the vectors are not needed any more
+        for (void*& p : B->owned)
+          if (p == (void*)v.diag_r[i]) {
+            cudaFree(p);
+            p = nullptr;
+          }
+        v.diag_r[i] = nullptr;
+      }
+    }
+  }
   B->all_real = all_real;
   cudaFree(d_flags);
   g->bitflip = B;
@@ -253,6 +391,7 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
 
 int64_t qp_bitflip_stored_bytes(const qp_bitflip_s* b) {
   int64_t bytes = 0;
+  if (b->view.dcode != nullptr) return 2 * b->view.n;
   for (int i = 0; i < b->view.n_diag; ++i) bytes += (b->view.diag_r[i] ? 8 : 16) * b->view.n;
   return bytes;
 }
@@ -266,21 +405,40 @@ __device__ __forceinline__ double2 shfl_xor_c(double2 v, int m) {
 }
 
 // REALC: every (coefficient x value) product and every (coefficient x diagonal) of this launch is real.
-template <int EPI, int REALC, int THREADS>
+template <int EPI, int REALC, int THREADS, int BATCH>
 __global__ void __launch_bounds__(THREADS, 1)
 k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict__ coef, const double2* __restrict__ x,
                EpiArgs e, int rounds) {
   __shared__ double2 s_c[BF_MAX_TERMS];   // coefficient x value per load term
   __shared__ double2 s_cl[BF_MAX_LOW];    // ... per shuffle term
   __shared__ double2 s_cd[BF_MAX_DIAG];   // coefficient per diagonal
+  extern __shared__ double2 s_dt[];       // coded diagonals: sum_i coefficient_i x value_i per joint code [n_joint]
   // programmatic dependent launch: the next term's launch and this set-up overlap the tail of the previous term
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!REALC) {
     if (threadIdx.x < v.n_high) s_c[threadIdx.x] = cmul2(coef[v.op[threadIdx.x]], v.val[threadIdx.x]);
     if (threadIdx.x < v.n_low) s_cl[threadIdx.x] = cmul2(coef[v.lop[threadIdx.x]], v.lval[threadIdx.x]);
     if (threadIdx.x < v.n_diag) s_cd[threadIdx.x] = coef[v.diag_op[threadIdx.x]];
-    __syncthreads();
   }
+  if (v.dcode != nullptr) {
+    for (int c = threadIdx.x; c < v.n_joint; c += THREADS) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int i = 0; i < BF_MAX_DIAG; ++i)
+        if (i < v.n_diag) {
+          const double d = v.dtab[v.doff[i] + (c / v.dstride[i]) % v.dcount[i]];
+          if (REALC) {
+            re = fma(v.cdr[i], d, re);
+          } else {
+            const double2 u = coef[v.diag_op[i]];
+            re = fma(u.x, d, re);
+            im = fma(u.y, d, im);
+          }
+        }
+      s_dt[c] = make_double2(re, im);
+    }
+  }
+  if (!REALC || v.dcode != nullptr) __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = THREADS >> 5;
@@ -293,12 +451,17 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   // requested right after the current slice's gathers, before any of them is consumed.
   double2 n_x = make_double2(0.0, 0.0), n_y = n_x, n_a = n_x;
   double n_d[BF_MAX_DIAG] = {0.0, 0.0, 0.0, 0.0};
+  unsigned short n_code = 0;
   auto prefetch = [&](int64_t sl) {
     const int64_t row = (sl < n_slices ? sl : 0) * 32 + lane;
-    n_x = __ldg(x + row);
+    n_x = ld_x(x + row);
+    if (v.dcode != nullptr) {
+      n_code = __ldg(v.dcode + row);
+    } else {
 #pragma unroll
-    for (int i = 0; i < BF_MAX_DIAG; ++i)
-      if (i < v.n_diag && v.diag_r[i] != nullptr) n_d[i] = ld_stream_f64(v.diag_r[i] + row);
+      for (int i = 0; i < BF_MAX_DIAG; ++i)
+        if (i < v.n_diag && v.diag_r[i] != nullptr) n_d[i] = ld_stream_f64(v.diag_r[i] + row);
+    }
     if (EPI == EPI_MUL) {
       if (e.betac.x != 0.0 || e.betac.y != 0.0) n_y = ld_noalloc(e.y + row);
     } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
@@ -315,6 +478,15 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
     const double2 xown = n_x, yv = n_y, av = n_a;
     // diagonals of this slice (requested one round ago)
     double dre = 0.0, dim = 0.0;
+    if (v.dcode != nullptr) {
+      if (REALC) {
+        dre = s_dt[n_code].x;
+      } else {
+        const double2 t = s_dt[n_code];
+        dre = t.x;
+        dim = t.y;
+      }
+    } else
 #pragma unroll
     for (int i = 0; i < BF_MAX_DIAG; ++i)
       if (i < v.n_diag) {
@@ -327,38 +499,51 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
         }
       }
     const int64_t s_next = s + nwarps;
-    double hr = 0.0, hi = 0.0, hr2 = 0.0, hi2 = 0.0;
-    // load terms in groups of four (the lists are padded with zero-valued terms on mask 0): sixteen gathers in
-    // flight, the first sixteen with compile-time positions in the constant bank
-    double2 xv[16];
+    double hr = 0.0, hi = 0.0, hr2 = 0.0, hi2 = 0.0, hr3 = 0.0, hi3 = 0.0, hr4 = 0.0, hi4 = 0.0;
+    // load terms in groups of four (the lists are padded with zero-valued terms on mask 0): BATCH gathers in
+    // flight, the first sixteen terms with compile-time positions in the constant bank
+    double2 xv[BATCH];
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (4 * g < v.n_high) {
+    for (int b0 = 0; b0 < 16; b0 += BATCH) {
 #pragma unroll
-        for (int q = 4 * g; q < 4 * g + 4; ++q) xv[q] = __ldg(x + (r32 ^ v.mask[q]));
-      }
-    if (it + 1 < rounds) prefetch(s_next);
+      for (int g = 0; g < BATCH / 4; ++g)
+        if (b0 + 4 * g < v.n_high) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (4 * g < v.n_high) {
+          for (int q = 4 * g; q < 4 * g + 4; ++q) xv[q] = ld_x(x + (r32 ^ v.mask[b0 + q]));
+        }
+      if (b0 == 0 && it + 1 < rounds) prefetch(s_next);
 #pragma unroll
-        for (int q = 4 * g; q < 4 * g + 4; ++q) {
-          if (REALC) {
-            const double c = v.cre[q];
-            if (q & 1) { hr2 = fma(c, xv[q].x, hr2); hi2 = fma(c, xv[q].y, hi2); }
-            else { hr = fma(c, xv[q].x, hr); hi = fma(c, xv[q].y, hi); }
-          } else {
-            const double2 c = s_c[q];
-            hr = fma(c.x, xv[q].x, hr);
-            hi = fma(c.x, xv[q].y, hi);
-            hr2 = fma(-c.y, xv[q].y, hr2);
-            hi2 = fma(c.y, xv[q].x, hi2);
+      for (int g = 0; g < BATCH / 4; ++g)
+        if (b0 + 4 * g < v.n_high) {
+#pragma unroll
+          for (int q = 4 * g; q < 4 * g + 4; ++q) {
+            if (REALC) {
+              const double c = v.cre[b0 + q];
+              constexpr int CH = BATCH >= 16 ? 1 : 3;  // two / four accumulation chains (registers)
+              if ((q & CH) == 0) { hr = fma(c, xv[q].x, hr); hi = fma(c, xv[q].y, hi); }
+              else if ((q & CH) == 1) { hr2 = fma(c, xv[q].x, hr2); hi2 = fma(c, xv[q].y, hi2); }
+              else if ((q & CH) == 2) { hr3 = fma(c, xv[q].x, hr3); hi3 = fma(c, xv[q].y, hi3); }
+              else { hr4 = fma(c, xv[q].x, hr4); hi4 = fma(c, xv[q].y, hi4); }
+            } else {
+              const double2 c = s_c[b0 + q];
+              if (q & 1) {
+                hr3 = fma(c.x, xv[q].x, hr3);
+                hi3 = fma(c.x, xv[q].y, hi3);
+                hr4 = fma(-c.y, xv[q].y, hr4);
+                hi4 = fma(c.y, xv[q].x, hi4);
+              } else {
+                hr = fma(c.x, xv[q].x, hr);
+                hi = fma(c.x, xv[q].y, hi);
+                hr2 = fma(-c.y, xv[q].y, hr2);
+                hi2 = fma(c.y, xv[q].x, hi2);
+              }
+            }
           }
         }
-      }
+    }
     for (int t = 16; t < v.n_high; t += 4) {  // more than sixteen load terms
 #pragma unroll
-      for (int q = 0; q < 4; ++q) xv[q] = __ldg(x + (r32 ^ v.mask[t + q]));
+      for (int q = 0; q < 4; ++q) xv[q] = ld_x(x + (r32 ^ v.mask[t + q]));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const double2 c = REALC ? make_double2(v.cre[t + q], 0.0) : s_c[t + q];
@@ -389,15 +574,15 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
       }
     if (!REALC) {  // complex diagonals (rare): not prefetched
       for (int i = 0; i < v.n_diag; ++i)
-        if (v.diag_r[i] == nullptr) {
+        if (v.diag_c[i] != nullptr) {
           const double2 u = s_cd[i];
           const double2 d = ld_stream(v.diag_c[i] + row);
           dre += u.x * d.x - u.y * d.y;
           dim += u.x * d.y + u.y * d.x;
         }
     }
-    hr += hr2 + dre * xown.x - dim * xown.y;
-    hi += hi2 + dre * xown.y + dim * xown.x;
+    hr = (hr + hr2) + (hr3 + hr4) + (dre * xown.x - dim * xown.y);
+    hi = (hi + hi2) + (hi3 + hi4) + (dre * xown.y + dim * xown.x);
     if (active) epi_apply<EPI>(e, row, make_double2(hr, hi), xown, yv, av, dr, di, nn);
     s = s_next;
   }
@@ -411,7 +596,7 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   }
 }
 
-template <int EPI, int REALC, int THREADS>
+template <int EPI, int REALC, int THREADS, int BATCH>
 static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
   BitflipView& v = gen->bitflip->view;
@@ -420,7 +605,13 @@ static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) 
     for (int t = 0; t < v.n_low; ++t) v.lcre[t] = gen->h_coef[v.lop[t]].x * v.lval[t].x;
     for (int i = 0; i < v.n_diag; ++i) v.cdr[i] = gen->h_coef[v.diag_op[i]].x;
   }
-  auto kern = k_spmv_bitflip<EPI, REALC, THREADS>;
+  auto kern = k_spmv_bitflip<EPI, REALC, THREADS, BATCH>;
+  // the table of the coded diagonals is the only shared memory of note: prefer L1 (the near partners live there)
+  static const int carve = getenv("QPROP_BITFLIP_CARVEOUT") ? atoi(getenv("QPROP_BITFLIP_CARVEOUT")) : -1;
+  if (carve >= 0 && !ctx->smem_configured.count((const void*)kern)) {
+    QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    ctx->smem_configured.insert((const void*)kern);
+  }
   const int wpc = THREADS / 32;
   const int64_t n_slices = v.n >> 5;
   int64_t ctas = ctx->sm_count;
@@ -432,6 +623,7 @@ static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) 
   cfg.gridDim = dim3((unsigned)ctas);
   cfg.blockDim = dim3(THREADS);
   cfg.stream = ctx->stream;
+  cfg.dynamicSmemBytes = v.dcode != nullptr ? sizeof(double2) * (size_t)v.n_joint : 0;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -461,9 +653,11 @@ static int32_t bitflip_launch_epi(qp_gen_t gen, const double2* x, const EpiArgs&
   bool realc = gen->bitflip->all_real && gen->h_coef_valid && (int)gen->h_coef.size() == gen->n_ops;
   for (int l = 0; realc && l < gen->n_ops; ++l) realc = gen->h_coef[l].y == 0.0;
   static const int threads_env = getenv("QPROP_BITFLIP_THREADS") ? atoi(getenv("QPROP_BITFLIP_THREADS")) : 512;
-  if (threads_env == 1024) return realc ? bitflip_launch<EPI, 1, 1024>(gen, x, e) : bitflip_launch<EPI, 0, 1024>(gen, x, e);
-  if (threads_env == 768) return realc ? bitflip_launch<EPI, 1, 768>(gen, x, e) : bitflip_launch<EPI, 0, 768>(gen, x, e);
-  return realc ? bitflip_launch<EPI, 1, 512>(gen, x, e) : bitflip_launch<EPI, 0, 512>(gen, x, e);
+  static const int batch_env = getenv("QPROP_BITFLIP_BATCH") ? atoi(getenv("QPROP_BITFLIP_BATCH")) : 16;
+  if (threads_env == 1024) return realc ? bitflip_launch<EPI, 1, 1024, 8>(gen, x, e) : bitflip_launch<EPI, 0, 1024, 8>(gen, x, e);
+  if (threads_env == 768) return realc ? bitflip_launch<EPI, 1, 768, 8>(gen, x, e) : bitflip_launch<EPI, 0, 768, 8>(gen, x, e);
+  if (batch_env == 8) return realc ? bitflip_launch<EPI, 1, 512, 8>(gen, x, e) : bitflip_launch<EPI, 0, 512, 8>(gen, x, e);
+  return realc ? bitflip_launch<EPI, 1, 512, 16>(gen, x, e) : bitflip_launch<EPI, 0, 512, 16>(gen, x, e);
 }
 
 int32_t qp_launch_bitflip(qp_gen_t gen, int epi, const double2* x, const EpiArgs& e) {

@@ -54,6 +54,18 @@ __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// Loads of vectors WRITTEN BY THE PREVIOUS KERNEL inside kernels that use programmatic dependent launch
+// (k_spmv_csr, k_spmv_selld, k_spmv_bitflip).  Non-coherent loads (__ldg, const __restrict__, ld.global.nc) are
+// invariant loads to the compiler AND to ptxas, and both are free to move them above griddepcontrol.wait -- seen
+// in the SASS of k_spmv_bitflip (LDG.E.128.CONSTANT of the first slice's own x above ACQBULK, with __ldg and with
+// a volatile ld.global.nc alike) as rare stale reads in back-to-back terms.  A plain ld.global (still allocating
+// in L1) is ordered after the wait.
+__device__ __forceinline__ double2 ld_x(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+}
+
 // streaming loads for the matrix arrays: read-only path, do not allocate in L1 (keep L1 for
 // the gathered x entries, which are the only data with reuse)
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
@@ -96,7 +108,7 @@ __device__ __forceinline__ double2 vld(const double2* p, int hint) {
   return hint ? ld_hint(p, policy_evict_last()) : *p;
 }
 __device__ __forceinline__ double2 vldg(const double2* p, int hint) {
-  return hint ? ld_nc_hint(p, policy_evict_last()) : __ldg(p);
+  return hint ? ld_nc_hint(p, policy_evict_last()) : ld_x(p);
 }
 __device__ __forceinline__ void vst(double2* p, double2 v, int hint) {
   if (hint) st_hint(p, v, policy_evict_last());
@@ -246,7 +258,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
   if (active) {
     double2 pxv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pxv[i] = __ldg(x + (pco[i] & QP_COL_MASK));  // padding: column 0, value 0
+    for (int i = 0; i < 4; ++i) pxv[i] = ld_x(x + (pco[i] & QP_COL_MASK));  // padding: column 0, value 0
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const double2 u = s_coef[pco[i] >> QP_COL_BITS];
@@ -259,7 +271,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
     for (uint32_t k = p0 + lane + 4 * LANES; k < p1; k += LANES) {
       const uint32_t co = ld_stream(m.colop + k);
       const double2 v = ld_stream(m.val + k);
-      const double2 xv = __ldg(x + (co & QP_COL_MASK));
+      const double2 xv = ld_x(x + (co & QP_COL_MASK));
       const double2 u = s_coef[co >> QP_COL_BITS];
       const double tr = v.x * xv.x - v.y * xv.y;
       const double ti = v.x * xv.y + v.y * xv.x;
@@ -557,7 +569,7 @@ __device__ __forceinline__ void selld_groups(const uint32_t* w, const double2* s
   for (int t = 0; t < NC; ++t)
     code[t] = CB == 1 ? (w[t >> 2] >> (8 * (t & 3))) & 0xffu : (w[t >> 1] >> (16 * (t & 1))) & 0xffffu;
 #pragma unroll
-  for (int t = 0; t < NC; ++t) xv[t] = __ldg(xbase + s_delta[code[t]]);
+  for (int t = 0; t < NC; ++t) xv[t] = ld_x(xbase + s_delta[code[t]]);
   if (REALT) {  // every (coefficient x value) of this step is real: 8-byte lookups, 2 DFMA per entry
 #pragma unroll
     for (int t = 0; t < NC; ++t) {
@@ -628,7 +640,7 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
     if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + row);
     return;
   }
-  xr = __ldg(x + row);  // allocates in L1: neighbouring rows gather it
+  xr = ld_x(x + row);  // allocates in L1: neighbouring rows gather it
   if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
     yv = ld_noalloc(e.y + row);
     av = ld_noalloc(e.acc + row);
@@ -714,7 +726,7 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
     sr += sr2;
     si += si2;
     if (m.n_diag > 0 && live) {  // explicit diagonals: hx += sum_i u_i d_i[row] x[row]
-      const double2 xs = EPI == EPI_MUL ? __ldg(x + row) : xr;
+      const double2 xs = EPI == EPI_MUL ? ld_x(x + row) : xr;
       double2 d = make_double2(0.0, 0.0);
       for (int i = 0; i < m.n_diag; ++i) {
         const double2 t = cmul2(coef[(m.diag_ops >> (4 * i)) & 15ull], ld_stream(m.diag + (int64_t)i * m.n + row));

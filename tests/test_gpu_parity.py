@@ -1286,11 +1286,13 @@ def test_selld_uniform_width_tails_and_real_table(qp, ctx, row_len, n_vals):
         assert abs(gen.expval(dx, [c]) - np.vdot(x, dense @ x)) < 1e-12 * n
 
 
-def _bitflip_ops(rng, n_bits, masks, complex_values, complex_diag):
+def _bitflip_ops(rng, n_bits, masks, complex_values, complex_diag, few_values=False):
     """Diagonal operators + one operator that couples every row r to r ^ m with the same value."""
     N = 1 << n_bits
     rows = np.arange(N)
     d0 = rng.standard_normal(N) + (1j * rng.standard_normal(N) if complex_diag else 0)
+    if few_values:   # both diagonals take a handful of values: stored as one 16-bit code per row
+        d0 = rng.choice(np.array([-2.5, -0.0, 0.0, 0.75, 3.0]), N)
     d1 = rng.integers(-3, 4, N).astype(float)
     vals = rng.standard_normal(len(masks)) + (1j * rng.standard_normal(len(masks)) if complex_values else 0)
     X = sum(sp.csr_matrix((np.full(N, v, dtype=complex), (rows, rows ^ m)), shape=(N, N)) for m, v in zip(masks, vals))
@@ -1304,16 +1306,22 @@ def _bitflip_ops(rng, n_bits, masks, complex_values, complex_diag):
     (10, [1 << i for i in range(10)], False, True, [0.7 - 0.2j, 0.4j]),       # complex diagonal, complex coefficients
     (12, [1 << i for i in range(12)] + [3 << i for i in range(11)], False, False, [1.1, 0.3]),  # 23 terms: tail batches
     (9, [64, 128, 256], False, False, [0.5, 2.0]),                            # no in-warp masks at all
+    (11, [1 << i for i in range(11)], False, "few", [0.7, -1.3]),             # coded diagonals, real coefficients
+    (10, [1, 2, 512, 77], True, "few", [0.7 - 0.2j, 0.4j]),                   # coded diagonals, complex coefficients
 ])
 def test_operator_mul_bitflip(qp, ctx, n_bits, masks, cv, cd, coeffs):
     """QP_FORMAT_BITFLIP (diagonal vectors + XOR stencil, no matrix stream): 5-argument mul! and the fused
     expectation value against scipy, real and complex coefficient products, masks below and above the warp
     width, term counts around the batch size of 8."""
     rng = np.random.default_rng(n_bits * 100 + len(masks))
-    ops = _bitflip_ops(rng, n_bits, masks, cv, cd)
+    ops = _bitflip_ops(rng, n_bits, masks, cv, cd is True, few_values=cd == "few")
     N = 1 << n_bits
     gen = qp.DeviceGenerator(ctx, ops, 2, "bitflip")
     assert gen.format == "bitflip"
+    # real diagonals with few distinct values (<= 256 each, <= 2048 jointly) are stored as one 16-bit code per row
+    n0, n2 = (len(np.unique(op.diagonal())) for op in (ops[0], ops[2]))
+    coded = cd is not True and max(n0, n2) <= 256 and n0 * n2 <= 2048
+    assert gen.stored_bytes == (2 * N if coded else 24 * N if cd is True else 16 * N)
     H = (ops[0] + coeffs[0] * ops[1] + coeffs[1] * ops[2]).tocsr()
     x = rand_state(rng, N)
     y0 = rand_state(rng, N)
