@@ -404,16 +404,23 @@ __device__ __forceinline__ double2 shfl_xor_c(double2 v, int m) {
   return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
+// One CTA per SM owns a contiguous slice range (near partners of neighbouring slices meet in L1); a warp takes a
+// slice per round, a lane a row.  Per round and lane: LB gathers in flight (two batches for the first sixteen load
+// terms, whose masks / products sit at compile-time positions of the constant bank), the shuffle terms, the
+// diagonal look-up, the fused epilogue.  Nothing is carried from round to round, so the kernel fits 72-80 registers
+// and 24-28 warps per SM hide the L1 / L2 latencies -- measured on config 2: 16 warps x 16 gathers with a
+// cross-round prefetch (128 registers) 2140 prop_step!/s, 24 x 8: 2410, 28 x 8: 2480-2500, 32 x 4: 2400;
+// with every far partner replaced by a near one (no L2 traffic at all) 2570: what is left is the L1 / shared-
+// memory data pipe (60 wavefronts of gathers, 20 of shuffles, 20 of vector streams per slice).
 // REALC: every (coefficient x value) product and every (coefficient x diagonal) of this launch is real.
-template <int EPI, int REALC, int THREADS, int BATCH>
+template <int EPI, int REALC, int THREADS, int LB>
 __global__ void __launch_bounds__(THREADS, 1)
 k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict__ coef, const double2* __restrict__ x,
-               EpiArgs e, int rounds) {
-  __shared__ double2 s_c[BF_MAX_TERMS];   // coefficient x value per load term
-  __shared__ double2 s_cl[BF_MAX_LOW];    // ... per shuffle term
-  __shared__ double2 s_cd[BF_MAX_DIAG];   // coefficient per diagonal
-  extern __shared__ double2 s_dt[];       // coded diagonals: sum_i coefficient_i x value_i per joint code [n_joint]
-  // programmatic dependent launch: the next term's launch and this set-up overlap the tail of the previous term
+                    EpiArgs e, int rounds) {
+  __shared__ double2 s_c[BF_MAX_TERMS];
+  __shared__ double2 s_cl[BF_MAX_LOW];
+  __shared__ double2 s_cd[BF_MAX_DIAG];
+  extern __shared__ double2 s_dt[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!REALC) {
     if (threadIdx.x < v.n_high) s_c[threadIdx.x] = cmul2(coef[v.op[threadIdx.x]], v.val[threadIdx.x]);
@@ -444,99 +451,51 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = THREADS >> 5;
   const int64_t n_slices = v.n >> 5;
   double dr = 0, di = 0, nn = 0;
-
-  // Every warp of the grid runs the same number of rounds (a uniform trip count keeps the shuffles free of
-  // re-convergence code); slices past the end (last CTA only) are computed on slice 0 and not stored.
-  // Software pipeline: the lane's own x, the diagonals and the epilogue operands of the NEXT slice are
-  // requested right after the current slice's gathers, before any of them is consumed.
-  double2 n_x = make_double2(0.0, 0.0), n_y = n_x, n_a = n_x;
-  double n_d[BF_MAX_DIAG] = {0.0, 0.0, 0.0, 0.0};
-  unsigned short n_code = 0;
-  auto prefetch = [&](int64_t sl) {
-    const int64_t row = (sl < n_slices ? sl : 0) * 32 + lane;
-    n_x = ld_x(x + row);
-    if (v.dcode != nullptr) {
-      n_code = __ldg(v.dcode + row);
-    } else {
-#pragma unroll
-      for (int i = 0; i < BF_MAX_DIAG; ++i)
-        if (i < v.n_diag && v.diag_r[i] != nullptr) n_d[i] = ld_stream_f64(v.diag_r[i] + row);
-    }
-    if (EPI == EPI_MUL) {
-      if (e.betac.x != 0.0 || e.betac.y != 0.0) n_y = ld_noalloc(e.y + row);
-    } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
-      n_y = ld_noalloc(e.y + row);
-      n_a = ld_noalloc(e.acc + row);
-    }
-  };
+  // every warp of the grid runs the same number of rounds (a uniform trip count keeps the shuffles free of
+  // re-convergence code); slices past the end (last CTA only) are computed on slice 0 and not stored -- predicating
+  // their loads instead costs 13 % (the batches of gathers are broken up by branches)
   int64_t s = (int64_t)blockIdx.x * rounds * nwarps + warp;
-  prefetch(s);
-  for (int it = 0; it < rounds; ++it) {
+  for (int it = 0; it < rounds; ++it, s += nwarps) {
     const bool active = s < n_slices;
     const int64_t row = (active ? s : 0) * 32 + lane;
     const uint32_t r32 = (uint32_t)row;
-    const double2 xown = n_x, yv = n_y, av = n_a;
-    // diagonals of this slice (requested one round ago)
-    double dre = 0.0, dim = 0.0;
-    if (v.dcode != nullptr) {
-      if (REALC) {
-        dre = s_dt[n_code].x;
-      } else {
-        const double2 t = s_dt[n_code];
-        dre = t.x;
-        dim = t.y;
-      }
-    } else
+    const double2 xown = ld_x(x + row);
+    unsigned short code = 0;
+    if (v.dcode != nullptr) code = __ldg(v.dcode + row);
+    double hr = 0.0, hi = 0.0, hr2 = 0.0, hi2 = 0.0;
+    double2 yv = make_double2(0.0, 0.0), av = yv;
+    double2 xv[LB];
 #pragma unroll
-    for (int i = 0; i < BF_MAX_DIAG; ++i)
-      if (i < v.n_diag) {
-        if (REALC) {  // all diagonals real, all coefficients real
-          dre = fma(v.cdr[i], n_d[i], dre);
-        } else if (v.diag_r[i] != nullptr) {
-          const double2 u = s_cd[i];
-          dre = fma(u.x, n_d[i], dre);
-          dim = fma(u.y, n_d[i], dim);
-        }
-      }
-    const int64_t s_next = s + nwarps;
-    double hr = 0.0, hi = 0.0, hr2 = 0.0, hi2 = 0.0, hr3 = 0.0, hi3 = 0.0, hr4 = 0.0, hi4 = 0.0;
-    // load terms in groups of four (the lists are padded with zero-valued terms on mask 0): BATCH gathers in
-    // flight, the first sixteen terms with compile-time positions in the constant bank
-    double2 xv[BATCH];
+    for (int b0 = 0; b0 < 16; b0 += LB) {
 #pragma unroll
-    for (int b0 = 0; b0 < 16; b0 += BATCH) {
-#pragma unroll
-      for (int g = 0; g < BATCH / 4; ++g)
+      for (int g = 0; g < LB / 4; ++g)
         if (b0 + 4 * g < v.n_high) {
 #pragma unroll
           for (int q = 4 * g; q < 4 * g + 4; ++q) xv[q] = ld_x(x + (r32 ^ v.mask[b0 + q]));
         }
-      if (b0 == 0 && it + 1 < rounds) prefetch(s_next);
+      if (b0 == 8 && THREADS < 1024) {  // the epilogue operands travel with the second batch
+        if (EPI == EPI_MUL) {
+          if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + row);
+        } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
+          yv = ld_noalloc(e.y + row);
+          av = ld_noalloc(e.acc + row);
+        }
+      }
 #pragma unroll
-      for (int g = 0; g < BATCH / 4; ++g)
+      for (int g = 0; g < LB / 4; ++g)
         if (b0 + 4 * g < v.n_high) {
 #pragma unroll
           for (int q = 4 * g; q < 4 * g + 4; ++q) {
             if (REALC) {
               const double c = v.cre[b0 + q];
-              constexpr int CH = BATCH >= 16 ? 1 : 3;  // two / four accumulation chains (registers)
-              if ((q & CH) == 0) { hr = fma(c, xv[q].x, hr); hi = fma(c, xv[q].y, hi); }
-              else if ((q & CH) == 1) { hr2 = fma(c, xv[q].x, hr2); hi2 = fma(c, xv[q].y, hi2); }
-              else if ((q & CH) == 2) { hr3 = fma(c, xv[q].x, hr3); hi3 = fma(c, xv[q].y, hi3); }
-              else { hr4 = fma(c, xv[q].x, hr4); hi4 = fma(c, xv[q].y, hi4); }
+              if (q & 1) { hr2 = fma(c, xv[q].x, hr2); hi2 = fma(c, xv[q].y, hi2); }
+              else { hr = fma(c, xv[q].x, hr); hi = fma(c, xv[q].y, hi); }
             } else {
               const double2 c = s_c[b0 + q];
-              if (q & 1) {
-                hr3 = fma(c.x, xv[q].x, hr3);
-                hi3 = fma(c.x, xv[q].y, hi3);
-                hr4 = fma(-c.y, xv[q].y, hr4);
-                hi4 = fma(c.y, xv[q].x, hi4);
-              } else {
-                hr = fma(c.x, xv[q].x, hr);
-                hi = fma(c.x, xv[q].y, hi);
-                hr2 = fma(-c.y, xv[q].y, hr2);
-                hi2 = fma(c.y, xv[q].x, hi2);
-              }
+              hr = fma(c.x, xv[q].x, hr);
+              hi = fma(c.x, xv[q].y, hi);
+              hr2 = fma(-c.y, xv[q].y, hr2);
+              hi2 = fma(c.y, xv[q].x, hi2);
             }
           }
         }
@@ -555,7 +514,6 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
         }
       }
     }
-    // shuffle terms: the partner row is a lane of this warp
 #pragma unroll
     for (int q = 0; q < BF_MAX_LOW; ++q)
       if (q < v.n_low) {
@@ -572,19 +530,36 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
           hi2 = fma(c.y, xs.x, hi2);
         }
       }
-    if (!REALC) {  // complex diagonals (rare): not prefetched
-      for (int i = 0; i < v.n_diag; ++i)
-        if (v.diag_c[i] != nullptr) {
-          const double2 u = s_cd[i];
+    if (THREADS >= 1024) {  // 64 registers: the epilogue operands are requested once the gathers are consumed
+      if (EPI == EPI_MUL) {
+        if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + row);
+      } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
+        yv = ld_noalloc(e.y + row);
+        av = ld_noalloc(e.acc + row);
+      }
+    }
+    double dre = 0.0, dim = 0.0;
+    if (v.dcode != nullptr) {
+      const double2 t = s_dt[code];
+      dre = t.x;
+      if (!REALC) dim = t.y;
+    } else {
+      for (int i = 0; i < v.n_diag; ++i) {
+        const double2 u = REALC ? make_double2(v.cdr[i], 0.0) : s_cd[i];
+        if (v.diag_r[i] != nullptr) {
+          const double d = ld_stream_f64(v.diag_r[i] + row);
+          dre = fma(u.x, d, dre);
+          if (!REALC) dim = fma(u.y, d, dim);
+        } else if (v.diag_c[i] != nullptr) {
           const double2 d = ld_stream(v.diag_c[i] + row);
           dre += u.x * d.x - u.y * d.y;
           dim += u.x * d.y + u.y * d.x;
         }
+      }
     }
-    hr = (hr + hr2) + (hr3 + hr4) + (dre * xown.x - dim * xown.y);
-    hi = (hi + hi2) + (hi3 + hi4) + (dre * xown.y + dim * xown.x);
+    hr = (hr + hr2) + (dre * xown.x - dim * xown.y);
+    hi = (hi + hi2) + (dre * xown.y + dim * xown.x);
     if (active) epi_apply<EPI>(e, row, make_double2(hr, hi), xown, yv, av, dr, di, nn);
-    s = s_next;
   }
   if (epi_has_sums(EPI) && e.chk != nullptr) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -596,7 +571,7 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   }
 }
 
-template <int EPI, int REALC, int THREADS, int BATCH>
+template <int EPI, int REALC, int THREADS, int LB>
 static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
   BitflipView& v = gen->bitflip->view;
@@ -605,13 +580,7 @@ static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) 
     for (int t = 0; t < v.n_low; ++t) v.lcre[t] = gen->h_coef[v.lop[t]].x * v.lval[t].x;
     for (int i = 0; i < v.n_diag; ++i) v.cdr[i] = gen->h_coef[v.diag_op[i]].x;
   }
-  auto kern = k_spmv_bitflip<EPI, REALC, THREADS, BATCH>;
-  // the table of the coded diagonals is the only shared memory of note: prefer L1 (the near partners live there)
-  static const int carve = getenv("QPROP_BITFLIP_CARVEOUT") ? atoi(getenv("QPROP_BITFLIP_CARVEOUT")) : -1;
-  if (carve >= 0 && !ctx->smem_configured.count((const void*)kern)) {
-    QP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    ctx->smem_configured.insert((const void*)kern);
-  }
+  auto kern = k_spmv_bitflip<EPI, REALC, THREADS, LB>;
   const int wpc = THREADS / 32;
   const int64_t n_slices = v.n >> 5;
   int64_t ctas = ctx->sm_count;
@@ -652,12 +621,26 @@ static int32_t bitflip_launch_epi(qp_gen_t gen, const double2* x, const EpiArgs&
   // real products: known on the host when the coefficients were set from the host and are not per-trajectory
   bool realc = gen->bitflip->all_real && gen->h_coef_valid && (int)gen->h_coef.size() == gen->n_ops;
   for (int l = 0; realc && l < gen->n_ops; ++l) realc = gen->h_coef[l].y == 0.0;
-  static const int threads_env = getenv("QPROP_BITFLIP_THREADS") ? atoi(getenv("QPROP_BITFLIP_THREADS")) : 512;
-  static const int batch_env = getenv("QPROP_BITFLIP_BATCH") ? atoi(getenv("QPROP_BITFLIP_BATCH")) : 16;
-  if (threads_env == 1024) return realc ? bitflip_launch<EPI, 1, 1024, 8>(gen, x, e) : bitflip_launch<EPI, 0, 1024, 8>(gen, x, e);
-  if (threads_env == 768) return realc ? bitflip_launch<EPI, 1, 768, 8>(gen, x, e) : bitflip_launch<EPI, 0, 768, 8>(gen, x, e);
-  if (batch_env == 8) return realc ? bitflip_launch<EPI, 1, 512, 8>(gen, x, e) : bitflip_launch<EPI, 0, 512, 8>(gen, x, e);
-  return realc ? bitflip_launch<EPI, 1, 512, 16>(gen, x, e) : bitflip_launch<EPI, 0, 512, 16>(gen, x, e);
+  // CTA shape: 24 / 28 warps x 8 gathers or 32 warps x 4 -- the one whose whole rounds waste the fewest SM slots
+  // (ties: 28 warps); QPROP_BITFLIP_THREADS = 768 / 896 / 1024 forces one
+  static const int threads_env = getenv("QPROP_BITFLIP_THREADS") ? atoi(getenv("QPROP_BITFLIP_THREADS")) : 0;
+  int threads = threads_env;
+  if (threads != 768 && threads != 896 && threads != 1024) {
+    const int64_t n_slices = gen->n >> 5, per_sm = (n_slices + gen->ctx->sm_count - 1) / gen->ctx->sm_count;
+    int64_t best = -1;
+    for (int t : {896, 768, 1024}) {
+      const int wpc = t / 32;
+      const int64_t spc = (per_sm + wpc - 1) / wpc * wpc, ctas = (n_slices + spc - 1) / spc;
+      const int64_t slots = spc * gen->ctx->sm_count * ((ctas + gen->ctx->sm_count - 1) / gen->ctx->sm_count);
+      if (best < 0 || slots < best) {
+        best = slots;
+        threads = t;
+      }
+    }
+  }
+  if (threads == 1024) return realc ? bitflip_launch<EPI, 1, 1024, 4>(gen, x, e) : bitflip_launch<EPI, 0, 1024, 4>(gen, x, e);
+  if (threads == 768) return realc ? bitflip_launch<EPI, 1, 768, 8>(gen, x, e) : bitflip_launch<EPI, 0, 768, 8>(gen, x, e);
+  return realc ? bitflip_launch<EPI, 1, 896, 8>(gen, x, e) : bitflip_launch<EPI, 0, 896, 8>(gen, x, e);
 }
 
 int32_t qp_launch_bitflip(qp_gen_t gen, int epi, const double2* x, const EpiArgs& e) {
