@@ -662,7 +662,7 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
   // nothing written by the previous term (x, y, acc) is touched before griddepcontrol.wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int j = threadIdx.x; j < m.n_dict; j += blockDim.x) {
-    s_val[j] = cmul2(coef[m.dop[j]], m.dval[j]);
+    s_val[j] = cmul2(coef[m.dop[j]], ld_stream(m.dval + j));  // static data: may sit above the wait
     s_delta[j] = m.ddelta[j];
   }
   __syncthreads();

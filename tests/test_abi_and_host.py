@@ -308,3 +308,47 @@ def test_library_leja_and_newton_coeffs_match_oracle():
             assert lib.qp_extend_newton_coeffs(arr.ctypes.data_as(C.c_void_p), cap, C.byref(na),
                                                leja_lib.ctypes.data_as(C.c_void_p), m, fid, fn, None, float(radius)) == 0
         assert np.max(np.abs(a_cb[:m] - a_exp[:m])) <= 1e-12 * np.max(np.abs(a_exp[:m]))
+
+
+def test_no_vector_load_is_scheduled_above_the_pdl_wait():
+    """Kernels launched with programmatic dependent launch may touch the vectors written by the
+    previous term only after griddepcontrol.wait (SASS: ACQBULK).  ptxas is free to move
+    NON-COHERENT loads (LDG...CONSTANT: __ldg, const __restrict__, ld.global.nc) above the wait --
+    it did so with the first own-x load of the bit-flip kernel, a rare stale read -- so the vectors are
+    read with plain ld.global (csrc/spmv.cuh: ld_x) and every load that legitimately sits in the
+    prologue (matrix, tables, coefficients) is non-coherent or narrower than 128 bits.  This scans
+    the built objects: no plain 128-bit global load (= a vector element) before the wait, and in the
+    Krylov kernels (no prologue at all) no load whatsoever."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    csrc = os.path.dirname(_lib.LIB_PATH)
+    objs = {name: os.path.join(csrc, name + ".o") for name in ("sparse", "bitflip", "krylov")}
+    if not os.path.exists(cuobjdump) or not all(os.path.exists(p) for p in objs.values()):
+        pytest.skip("cuobjdump or the built objects are not available")
+    total = 0
+    for name, path in objs.items():
+        sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
+        fn, before_wait, seen_wait = None, [], False
+        kernels = {}
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                if fn is not None and seen_wait:
+                    kernels[fn] = before_wait
+                fn, before_wait, seen_wait = m.group(1), [], False
+                continue
+            if "ACQBULK" in line:
+                seen_wait = True
+            elif not seen_wait and "LDG" in line:
+                before_wait.append(line.strip())
+        if fn is not None and seen_wait:
+            kernels[fn] = before_wait
+        total += len(kernels)
+        for fn, loads in kernels.items():
+            if name == "krylov":
+                assert not loads, f"{fn}: load above griddepcontrol.wait: {loads[0]}"
+            bad = [l for l in loads if re.search(r"LDG\.E(\.NA)?\.128 ", l)]
+            assert not bad, f"{fn}: plain 128-bit load above griddepcontrol.wait: {bad[0]}"
+    assert total >= 100   # the CSR, SELL-D, bit-flip and Krylov kernels all use the attribute
