@@ -282,8 +282,9 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
     }
   }
   if (terms.empty()) return fail(QP_OK);  // purely diagonal generators gain nothing here
+  const int max_low = getenv("QPROP_BITFLIP_SHUFFLES") ? std::min(BF_MAX_LOW, atoi(getenv("QPROP_BITFLIP_SHUFFLES"))) : BF_MAX_LOW;
   for (const Term& t : terms) {
-    if (t.mask < 32u && v.n_low < BF_MAX_LOW) {
+    if (t.mask < 32u && v.n_low < max_low) {
       v.lmask[v.n_low] = t.mask;
       v.lval[v.n_low] = t.val;
       v.lop[v.n_low++] = t.op;
@@ -292,6 +293,14 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
       v.val[v.n_high] = t.val;
       v.op[v.n_high++] = t.op;
     }
+  }
+  // the load list is processed four terms at a time: fill it up with shuffle terms (an in-warp partner costs
+  // the same as a load that hits L1) before padding it
+  while (v.n_high % 4 != 0 && v.n_low > 0 && v.n_high < BF_MAX_TERMS) {
+    --v.n_low;
+    v.mask[v.n_high] = v.lmask[v.n_low];
+    v.val[v.n_high] = v.lval[v.n_low];
+    v.op[v.n_high++] = v.lop[v.n_low];
   }
   while (v.n_high % 4 != 0 && v.n_high < BF_MAX_TERMS) {  // zero-valued padding terms on the row itself
     v.mask[v.n_high] = 0u;
