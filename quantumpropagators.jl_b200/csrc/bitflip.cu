@@ -1,23 +1,27 @@
 // Bit-flip (XOR-stencil) form of a generator, single states (QP_FORMAT_BITFLIP).
 //
-// Spin-1/2 Hamiltonians are very often "diagonal operators + sums of bit flips": the transverse-field
-// Ising chain of BASELINE config 2 is H0 = -J sum Z_i Z_{i+1} (diagonal), H1 = sum X_i (row r couples to
-// the 20 columns r XOR 2^i, every entry the SAME value), H2 = sum Z_i (diagonal); QAOA mixers and any
-// transverse-field term look the same.  For such an operator nothing about an off-diagonal entry depends
-// on the row: column = row XOR mask_t, value = v_t.  So there is no matrix stream at all -- the K <= 32
-// (mask, value, operator) triples travel as a kernel parameter (constant bank), the diagonals are explicit
-// vectors (8 B per row when real) -- and a fused term is
+// Spin-1/2 generators are very often "diagonal operators + sums of bit flips".  The transverse-field Ising
+// chain of BASELINE config 2 is H0 = -J sum Z_i Z_{i+1} (diagonal), H1 = sum X_i (row r couples to the 20
+// columns r XOR 2^i, every entry the SAME value), H2 = sum Z_i (diagonal); QAOA mixers look the same; the
+// Liouvillian of config 4 is a diagonal + the flips of the two commutator halves + one CONDITIONAL flip per
+// decay channel (sigma^-_k (x) sigma^-_k: mask 2^k | 2^(k+n), present on the rows whose two bits are 0).  For
+// such an operator nothing about an off-diagonal entry depends on the row beyond a sub-cube condition:
 //
-//     (H x)[r] = sum_l u_l ( d_l[r] x[r] + sum_{t in l} v_t x[r XOR mask_t] )
+//     column = row XOR mask_t,   value = v_t  if (row AND cmask_t) == cval_t,  absent otherwise.
+//
+// So there is no matrix stream at all -- the <= 64 (mask, value, condition, operator) tuples travel as a
+// kernel parameter (constant bank), the diagonals are explicit vectors or 16-bit codes -- and a fused term is
+//
+//     (H x)[r] = sum_l u_l ( d_l[r] x[r] + sum_{t in l, cond_t(r)} v_t x[r XOR mask_t] )
 //
 // with no code words, no table look-ups and no per-entry decode: masks below 32 are warp shuffles of the
 // lane's own x[r], every other term is one coalesced 512 B load per warp.  The structure is DETECTED at
-// qp_gen_create from the uploaded sparse matrices (every row of an operator must carry exactly the same
-// set of masks with the same values; k_xor_check), never assumed; anything else keeps the dictionary /
-// SELL / CSR formats.  Same fused epilogues as every other kernel (spmv.cuh).
+// qp_gen_create from the uploaded sparse matrices (k_bf_scan: per operator the set of distinct row XOR column
+// values, and per value the uniform entry and the exact sub-cube of rows that carry it), never assumed;
+// anything else keeps the dictionary / SELL / CSR formats.  Same fused epilogues as every other kernel.
 //
 // Replaces: mul!(C, A::Operator, B, alpha, beta), src/generators.jl:634-645, inside the Chebyshev term
-// of src/cheby.jl:186-209 (config 2 of BASELINE.json).
+// of src/cheby.jl:186-209 (config 2 of BASELINE.json) and the Arnoldi matvec of src/arnoldi.jl:72 (config 4).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -25,24 +29,25 @@
 
 #include "spmv.cuh"
 
-constexpr int BF_MAX_TERMS = 32;
+constexpr int BF_MAX_TERMS = 64;   // load terms (incl. padding)
+constexpr int BF_STATIC = 32;      // load terms at compile-time positions of the constant bank
+constexpr int BF_MAX_LOW = 8;      // shuffle terms
 constexpr int BF_MAX_DIAG = 4;
-
-constexpr int BF_MAX_LOW = 8;
 constexpr int BF_MAX_JOINT = 2048;     // entries of the folded diagonal table (shared memory)
 constexpr int BF_DIAG_DISTINCT = 256;  // distinct values per coded diagonal
 constexpr int BF_HASH_CAP = 1024;
+constexpr int BF_SET_CAP = 128;        // hash slots for the distinct masks of one operator
 
 struct BitflipView {
   int64_t n;
-  // terms served by loads (any mask; high[0, n_high)) and by warp shuffles (mask < 32; low[0, n_low))
+  // terms served by loads (any mask; [0, n_high)) and by warp shuffles (mask < 32; [0, n_low))
   int n_high, n_low;
-  uint32_t mask[BF_MAX_TERMS];
-  double2 val[BF_MAX_TERMS];
-  int op[BF_MAX_TERMS];
-  uint32_t lmask[BF_MAX_LOW];
-  double2 lval[BF_MAX_LOW];
-  int lop[BF_MAX_LOW];
+  uint32_t mask[BF_MAX_TERMS], cmask[BF_MAX_TERMS], cval[BF_MAX_TERMS];
+  uint32_t lmask[BF_MAX_LOW], lcmask[BF_MAX_LOW], lcval[BF_MAX_LOW];
+  // values and operator indices (device arrays; [0, BF_MAX_TERMS) load terms, then the shuffle terms): only the
+  // launches that take their coefficients from device memory read them
+  const double2* tval;
+  const int* top;
   int n_diag;
   const double* diag_r[BF_MAX_DIAG];   // real diagonal (or nullptr)
   const double2* diag_c[BF_MAX_DIAG];  // complex diagonal (or nullptr)
@@ -54,11 +59,11 @@ struct BitflipView {
   const double* dtab;      // the tables, one after the other
   int n_joint;
   int dcount[BF_MAX_DIAG], dstride[BF_MAX_DIAG], doff[BF_MAX_DIAG];
-  // REALC launches only: the products coefficient x value (and the diagonals' coefficients), computed on the
-  // host from the host copy of the coefficients -- they reach the DFMAs straight from the constant bank
-  double cre[BF_MAX_TERMS];
-  double lcre[BF_MAX_LOW];
-  double cdr[BF_MAX_DIAG];
+  // CK >= 1 launches: the products coefficient x value (and the diagonals' coefficients), computed on the host
+  // from the host copy of the coefficients -- they reach the DFMAs straight from the constant bank
+  double cre[BF_MAX_TERMS], cim[BF_MAX_TERMS];
+  double lcre[BF_MAX_LOW], lcim[BF_MAX_LOW];
+  double2 cd[BF_MAX_DIAG];
 };
 
 __device__ __forceinline__ double ld_stream_f64(const double* p) {
@@ -69,8 +74,12 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
 
 struct qp_bitflip_s {
   BitflipView view;
-  std::vector<void*> owned;  // device arrays of the diagonals
-  bool all_real = false;     // every term value and every diagonal is real
+  std::vector<void*> owned;  // device arrays
+  std::vector<double2> h_val;  // host copies of the term values / operators, same layout as tval / top
+  std::vector<int> h_op;
+  bool values_real = false;  // every term value is real
+  bool diags_real = false;   // every diagonal is real
+  bool cond = false;         // some term is conditional
 };
 
 void qp_bitflip_free(qp_bitflip_s* b) {
@@ -83,20 +92,104 @@ void qp_bitflip_free(qp_bitflip_s* b) {
 // detection
 // ---------------------------------------------------------------------------------------
 
-// flags[0] = 1 unless every row has at most one entry and that entry sits on the diagonal
-__global__ void k_bf_check_diag(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ col, int64_t n, int* flags) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+// Per distinct mask = row XOR column of one operator: how many rows carry it, which row bits are constant
+// among them (ones = AND of the rows, zeros = AND of their complements), the value of the first entry seen
+// and whether every other entry has the same one.
+struct MaskSet {
+  unsigned long long key[BF_SET_CAP];    // mask | 1 << 32; 0 = empty
+  unsigned int ones[BF_SET_CAP], zeros[BF_SET_CAP];
+  unsigned long long count[BF_SET_CAP];
+  unsigned long long vre[BF_SET_CAP], vim[BF_SET_CAP];  // bit patterns; BF_UNSET = none yet
+  int bad;       // != 0: a mask with two different values
+  int overflow;  // != 0: more distinct masks than slots
+};
+constexpr unsigned long long BF_UNSET = 0x7ff8dead0badbeefull;
+
+__device__ __forceinline__ int bf_set_find(MaskSet* s, unsigned long long key) {
+  unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 57) % BF_SET_CAP;
+  for (int probes = 0; probes < BF_SET_CAP; ++probes) {
+    unsigned long long cur = s->key[h];
+    if (cur == key) return (int)h;
+    if (cur == 0ull) {
+      cur = atomicCAS(&s->key[h], 0ull, key);
+      if (cur == 0ull || cur == key) return (int)h;
+    }
+    h = (h + 1) % BF_SET_CAP;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void bf_set_value(MaskSet* s, int h, unsigned long long bre, unsigned long long bim) {
+  const unsigned long long o1 = atomicCAS(&s->vre[h], BF_UNSET, bre);
+  const unsigned long long o2 = atomicCAS(&s->vim[h], BF_UNSET, bim);
+  if ((o1 != BF_UNSET && o1 != bre) || (o2 != BF_UNSET && o2 != bim)) s->bad = 1;
+}
+
+__device__ __forceinline__ void bf_set_clear(MaskSet* s) {
+  for (int t = threadIdx.x; t < BF_SET_CAP; t += blockDim.x) {
+    s->key[t] = 0ull;
+    s->ones[t] = s->zeros[t] = 0xffffffffu;
+    s->count[t] = 0ull;
+    s->vre[t] = s->vim[t] = BF_UNSET;
+  }
+  if (threadIdx.x == 0) s->bad = s->overflow = 0;
+}
+
+__global__ void k_bf_set_init(MaskSet* g) { bf_set_clear(g); }
+
+// one block per chunk of rows: statistics in shared memory first, merged into the global set at the end
+__global__ void __launch_bounds__(256)
+k_bf_scan(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ col, const double2* __restrict__ val, int64_t n,
+          int rows_per_block, MaskSet* g) {
+  __shared__ MaskSet s;
+  bf_set_clear(&s);
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int64_t r = r0 + threadIdx.x; r < r0 + rows_per_block && r < n; r += blockDim.x) {
     const uint32_t p0 = ptr[r], p1 = ptr[r + 1];
-    if (p1 - p0 > 1u || (p1 - p0 == 1u && col[p0] != (uint32_t)r)) flags[0] = 1;
+    for (uint32_t p = p0; p < p1; ++p) {
+      const uint32_t m = col[p] ^ (uint32_t)r;
+      const int h = bf_set_find(&s, (unsigned long long)m | (1ull << 32));
+      if (h < 0) {
+        s.overflow = 1;
+        continue;
+      }
+      atomicAnd(&s.ones[h], (unsigned int)r);
+      atomicAnd(&s.zeros[h], ~(unsigned int)r);
+      atomicAdd(&s.count[h], 1ull);
+      if (m != 0u) {  // the diagonal may take any values
+        const double2 v = val[p];
+        bf_set_value(&s, h, (unsigned long long)__double_as_longlong(v.x + 0.0), (unsigned long long)__double_as_longlong(v.y + 0.0));
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < BF_SET_CAP; t += blockDim.x) {
+    if (s.key[t] == 0ull) continue;
+    const int h = bf_set_find(g, s.key[t]);
+    if (h < 0) {
+      g->overflow = 1;
+      continue;
+    }
+    atomicAnd(&g->ones[h], s.ones[t]);
+    atomicAnd(&g->zeros[h], s.zeros[t]);
+    atomicAdd(&g->count[h], s.count[t]);
+    if (s.vre[t] != BF_UNSET) bf_set_value(g, h, s.vre[t], s.vim[t]);
+  }
+  if (threadIdx.x == 0) {
+    if (s.bad) g->bad = 1;
+    if (s.overflow) g->overflow = 1;
   }
 }
 
 // diag[r] = the diagonal entry of row r (0 if absent); flags[1] = 1 if any imaginary part is non-zero
-__global__ void k_bf_extract_diag(const uint32_t* __restrict__ ptr, const double2* __restrict__ val, int64_t n,
-                                  double2* __restrict__ dc, double* __restrict__ dr, int* flags) {
+__global__ void k_bf_extract_diag(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ col,
+                                  const double2* __restrict__ val, int64_t n, double2* __restrict__ dc,
+                                  double* __restrict__ dr, int* flags) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t p0 = ptr[r], p1 = ptr[r + 1];
-    const double2 v = p1 > p0 ? val[p0] : make_double2(0.0, 0.0);
+    double2 v = make_double2(0.0, 0.0);
+    for (uint32_t p = ptr[r]; p < ptr[r + 1]; ++p)
+      if (col[p] == (uint32_t)r) v = val[p];
     dc[r] = v;
     dr[r] = v.x;
     if (v.y != 0.0) flags[1] = 1;
@@ -148,170 +241,160 @@ __global__ void k_bf_encode(DiagTabs t, const double* __restrict__ tab, int64_t 
   }
 }
 
-struct XorProbe {
-  int k;
-  uint32_t mask[BF_MAX_TERMS];
-  unsigned long long vre[BF_MAX_TERMS], vim[BF_MAX_TERMS];  // value bits
-};
-
-// flags[0] = 1 unless every row carries exactly the masks of the probe (row 0), each once, with the same values
-__global__ void k_bf_check_xor(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ col,
-                               const double2* __restrict__ val, int64_t n, XorProbe pr, int* flags) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t p0 = ptr[r], p1 = ptr[r + 1];
-    if ((int)(p1 - p0) != pr.k) {
-      flags[0] = 1;
-      continue;
-    }
-    unsigned seen = 0u;
-    for (uint32_t p = p0; p < p1; ++p) {
-      const uint32_t m = col[p] ^ (uint32_t)r;
-      const double2 v = val[p];
-      int hit = -1;
-      for (int t = 0; t < pr.k; ++t)
-        if (pr.mask[t] == m) hit = t;
-      if (hit < 0 || (unsigned long long)__double_as_longlong(v.x) != pr.vre[hit] ||
-          (unsigned long long)__double_as_longlong(v.y) != pr.vim[hit] || ((seen >> hit) & 1u)) {
-        flags[0] = 1;
-        break;
-      }
-      seen |= 1u << hit;
-    }
-  }
-}
-
-// Tries to put the generator into bit-flip form.  *ok = false (nothing kept) if any operator is neither
-// purely diagonal nor a uniform XOR stencil.
+// Tries to put the generator into bit-flip form.  *ok = false (nothing kept) if some operator is not a
+// diagonal plus (conditional) uniform bit flips.
 int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
   *ok = false;
   qp_ctx_t ctx = g->ctx;
   const int64_t n = g->n;
   if (n % 32 != 0 || n < 64 || n >= (int64_t(1) << 32)) return QP_OK;
+  const bool pow2 = (n & (n - 1)) == 0;
   qp_bitflip_s* B = new qp_bitflip_s();
   BitflipView& v = B->view;
   memset(&v, 0, sizeof(v));
   v.n = n;
   int* d_flags = nullptr;
+  MaskSet* d_set = nullptr;
   auto fail = [&](int32_t rc) {
     cudaFree(d_flags);
+    cudaFree(d_set);
     qp_bitflip_free(B);
     return rc;
   };
-  if (cudaMalloc(&d_flags, 2 * sizeof(int)) != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
+  if (cudaMalloc(&d_flags, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&d_set, sizeof(MaskSet)) != cudaSuccess)
+    return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
   const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
-  bool all_real = true;
-  struct Term { uint32_t mask; double2 val; int op; };
+  bool values_real = true, diags_real = true;
+  struct Term { uint32_t mask, cmask, cval; double2 val; int op; };
   std::vector<Term> terms;
+  std::vector<MaskSet> h_set(1);
   for (int l = 0; l < g->n_ops; ++l) {
     qp_op_t op = g->ops[l];
-    if (op->dense || op->leftright || op->nnz == 0) {
-      if (op->nnz == 0 && !op->dense && !op->leftright) continue;  // an all-zero operator contributes nothing
-      return fail(QP_OK);
-    }
-    int h_flags[2] = {0, 0};
-    cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
-    if (op->nnz <= n) {  // candidate diagonal
-      k_bf_check_diag<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, n, d_flags);
-      ctx->launches++;
-      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
-      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal check failed"));
-      if (h_flags[0] == 0) {
-        if (v.n_diag >= BF_MAX_DIAG) return fail(QP_OK);
-        double2* dc = nullptr;
-        double* dr = nullptr;
-        if (cudaMalloc(&dc, sizeof(double2) * n) != cudaSuccess || cudaMalloc(&dr, sizeof(double) * n) != cudaSuccess) {
-          cudaFree(dc);
-          return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of a diagonal failed"));
-        }
-        cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
-        k_bf_extract_diag<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_val, n, dc, dr, d_flags);
-        ctx->launches++;
-        cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-          cudaFree(dc);
-          cudaFree(dr);
-          return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal extraction failed"));
-        }
-        const bool real = h_flags[1] == 0;
-        if (real) {
-          cudaFree(dc);
-          B->owned.push_back(dr);
-          v.diag_r[v.n_diag] = dr;
-        } else {
-          cudaFree(dr);
-          B->owned.push_back(dc);
-          v.diag_c[v.n_diag] = dc;
-          all_real = false;
-        }
-        v.diag_op[v.n_diag++] = l;
+    if (op->dense || op->leftright) return fail(QP_OK);
+    if (op->nnz == 0) continue;  // an all-zero operator contributes nothing
+    constexpr int ROWS_PER_BLOCK = 2048;
+    k_bf_set_init<<<1, 128, 0, ctx->stream>>>(d_set);
+    k_bf_scan<<<(unsigned)((n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n,
+                                                                                            ROWS_PER_BLOCK, d_set);
+    ctx->launches += 2;
+    cudaMemcpyAsync(h_set.data(), d_set, sizeof(MaskSet), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: operator scan failed"));
+    const MaskSet& S = h_set[0];
+    if (S.bad || S.overflow) return fail(QP_OK);
+    bool has_diag = false;
+    for (int t = 0; t < BF_SET_CAP; ++t) {
+      if (S.key[t] == 0ull) continue;
+      const uint32_t m = (uint32_t)(S.key[t] & 0xffffffffull);
+      if (m == 0u) {
+        has_diag = true;
         continue;
       }
+      // rows carrying the entry: all of them, or exactly the sub-cube (row AND cmask) == cval
+      uint32_t cmask = 0u, cval = 0u;
+      if ((int64_t)S.count[t] != n) {
+        if (!pow2) return fail(QP_OK);
+        cmask = (S.ones[t] | S.zeros[t]) & (uint32_t)(n - 1);
+        cval = S.ones[t] & (uint32_t)(n - 1);
+        if ((int64_t)S.count[t] != (n >> __builtin_popcount(cmask))) return fail(QP_OK);
+      }
+      Term T;
+      T.mask = m;
+      T.cmask = cmask;
+      T.cval = cval;
+      memcpy(&T.val.x, &S.vre[t], 8);
+      memcpy(&T.val.y, &S.vim[t], 8);
+      T.op = l;
+      if (T.val.y != 0.0) values_real = false;
+      if (cmask != 0u) B->cond = true;
+      terms.push_back(T);
+      if ((int)terms.size() > BF_MAX_TERMS + BF_MAX_LOW - 4) return fail(QP_OK);
     }
-    // candidate XOR stencil: k = nnz / n entries per row, the masks and values of row 0
-    if (op->nnz % n != 0) return fail(QP_OK);
-    const int64_t k = op->nnz / n;
-    if (k < 1 || k > BF_MAX_TERMS || (int)terms.size() + k > BF_MAX_TERMS) return fail(QP_OK);
-    std::vector<uint32_t> h_col((size_t)k);
-    std::vector<double2> h_val((size_t)k);
-    uint32_t h_ptr[2] = {0, 0};
-    cudaMemcpy(h_ptr, op->d_ptr, sizeof(h_ptr), cudaMemcpyDeviceToHost);
-    if ((int64_t)(h_ptr[1] - h_ptr[0]) != k) return fail(QP_OK);
-    cudaMemcpy(h_col.data(), op->d_col + h_ptr[0], sizeof(uint32_t) * k, cudaMemcpyDeviceToHost);
-    if (cudaMemcpy(h_val.data(), op->d_val + h_ptr[0], sizeof(double2) * k, cudaMemcpyDeviceToHost) != cudaSuccess)
-      return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: probe download failed"));
-    XorProbe pr;
-    memset(&pr, 0, sizeof(pr));
-    pr.k = (int)k;
-    for (int t = 0; t < (int)k; ++t) {
-      pr.mask[t] = h_col[t];  // row 0: column XOR 0
-      if (pr.mask[t] == 0u) return fail(QP_OK);  // a diagonal entry inside a stencil operator
-      memcpy(&pr.vre[t], &h_val[t].x, 8);
-      memcpy(&pr.vim[t], &h_val[t].y, 8);
-      for (int s = 0; s < t; ++s)
-        if (pr.mask[s] == pr.mask[t]) return fail(QP_OK);
-    }
-    cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
-    k_bf_check_xor<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n, pr, d_flags);
-    ctx->launches++;
-    cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: stencil check failed"));
-    if (h_flags[0] != 0) return fail(QP_OK);
-    for (int t = 0; t < (int)k; ++t) {
-      terms.push_back(Term{pr.mask[t], h_val[t], l});
-      if (h_val[t].y != 0.0) all_real = false;
+    if (has_diag) {
+      if (v.n_diag >= BF_MAX_DIAG) return fail(QP_OK);
+      double2* dc = nullptr;
+      double* dr = nullptr;
+      if (cudaMalloc(&dc, sizeof(double2) * n) != cudaSuccess || cudaMalloc(&dr, sizeof(double) * n) != cudaSuccess) {
+        cudaFree(dc);
+        return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of a diagonal failed"));
+      }
+      int h_flags[2] = {0, 0};
+      cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
+      k_bf_extract_diag<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n, dc, dr, d_flags);
+      ctx->launches++;
+      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaFree(dc);
+        cudaFree(dr);
+        return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal extraction failed"));
+      }
+      if (h_flags[1] == 0) {
+        cudaFree(dc);
+        B->owned.push_back(dr);
+        v.diag_r[v.n_diag] = dr;
+      } else {
+        cudaFree(dr);
+        B->owned.push_back(dc);
+        v.diag_c[v.n_diag] = dc;
+        diags_real = false;
+      }
+      v.diag_op[v.n_diag++] = l;
     }
   }
+  cudaFree(d_set);
+  d_set = nullptr;
   if (terms.empty()) return fail(QP_OK);  // purely diagonal generators gain nothing here
+  // deterministic order (the hash set's is not): by operator, then by mask
+  std::sort(terms.begin(), terms.end(), [](const Term& a, const Term& b) { return a.op != b.op ? a.op < b.op : a.mask < b.mask; });
+  B->h_val.assign(BF_MAX_TERMS + BF_MAX_LOW, make_double2(0.0, 0.0));
+  B->h_op.assign(BF_MAX_TERMS + BF_MAX_LOW, 0);
   const int max_low = getenv("QPROP_BITFLIP_SHUFFLES") ? std::min(BF_MAX_LOW, atoi(getenv("QPROP_BITFLIP_SHUFFLES"))) : BF_MAX_LOW;
+  auto put_high = [&](const Term& t) {
+    v.mask[v.n_high] = t.mask;
+    v.cmask[v.n_high] = t.cmask;
+    v.cval[v.n_high] = t.cval;
+    B->h_val[v.n_high] = t.val;
+    B->h_op[v.n_high++] = t.op;
+  };
+  std::vector<Term> low;
   for (const Term& t : terms) {
-    if (t.mask < 32u && v.n_low < max_low) {
-      v.lmask[v.n_low] = t.mask;
-      v.lval[v.n_low] = t.val;
-      v.lop[v.n_low++] = t.op;
-    } else {
-      v.mask[v.n_high] = t.mask;
-      v.val[v.n_high] = t.val;
-      v.op[v.n_high++] = t.op;
-    }
+    if (t.mask < 32u && (int)low.size() < max_low) low.push_back(t);
+    else if (v.n_high < BF_MAX_TERMS) put_high(t);
+    else return fail(QP_OK);
   }
   // the load list is processed four terms at a time: fill it up with shuffle terms (an in-warp partner costs
-  // the same as a load that hits L1) before padding it
-  while (v.n_high % 4 != 0 && v.n_low > 0 && v.n_high < BF_MAX_TERMS) {
-    --v.n_low;
-    v.mask[v.n_high] = v.lmask[v.n_low];
-    v.val[v.n_high] = v.lval[v.n_low];
-    v.op[v.n_high++] = v.lop[v.n_low];
+  // the same as a load that hits L1) before padding it with zero-valued terms on the row itself
+  while (v.n_high % 4 != 0 && !low.empty() && v.n_high < BF_MAX_TERMS) {
+    put_high(low.back());
+    low.pop_back();
   }
-  while (v.n_high % 4 != 0 && v.n_high < BF_MAX_TERMS) {  // zero-valued padding terms on the row itself
-    v.mask[v.n_high] = 0u;
-    v.val[v.n_high] = make_double2(0.0, 0.0);
-    v.op[v.n_high++] = 0;
-  }
+  while (v.n_high % 4 != 0 && v.n_high < BF_MAX_TERMS) put_high(Term{0u, 0u, 0u, make_double2(0.0, 0.0), 0});
   if (v.n_high % 4 != 0) return fail(QP_OK);
+  for (const Term& t : low) {
+    v.lmask[v.n_low] = t.mask;
+    v.lcmask[v.n_low] = t.cmask;
+    v.lcval[v.n_low] = t.cval;
+    B->h_val[BF_MAX_TERMS + v.n_low] = t.val;
+    B->h_op[BF_MAX_TERMS + v.n_low++] = t.op;
+  }
+  {
+    double2* d_val = nullptr;
+    int* d_op = nullptr;
+    if (cudaMalloc(&d_val, sizeof(double2) * B->h_val.size()) != cudaSuccess || cudaMalloc(&d_op, sizeof(int) * B->h_op.size()) != cudaSuccess) {
+      cudaFree(d_val);
+      return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
+    }
+    B->owned.push_back(d_val);
+    B->owned.push_back(d_op);
+    cudaMemcpy(d_val, B->h_val.data(), sizeof(double2) * B->h_val.size(), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(d_op, B->h_op.data(), sizeof(int) * B->h_op.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: upload of the terms failed"));
+    v.tval = d_val;
+    v.top = d_op;
+  }
   // coded diagonals
-  bool diags_real = v.n_diag > 0;
-  for (int i = 0; i < v.n_diag; ++i) diags_real = diags_real && v.diag_r[i] != nullptr;
-  if (diags_real && !getenv("QPROP_BITFLIP_NO_CODES")) {
+  bool all_diags_real = v.n_diag > 0;
+  for (int i = 0; i < v.n_diag; ++i) all_diags_real = all_diags_real && v.diag_r[i] != nullptr;
+  if (all_diags_real && !getenv("QPROP_BITFLIP_NO_CODES")) {
     unsigned long long* d_keys = nullptr;
     if (cudaMalloc(&d_keys, sizeof(unsigned long long) * BF_HASH_CAP) != cudaSuccess)
       return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
@@ -391,7 +474,8 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
       }
     }
   }
-  B->all_real = all_real;
+  B->values_real = values_real;
+  B->diags_real = diags_real;
   cudaFree(d_flags);
   g->bitflip = B;
   *ok = true;
@@ -414,26 +498,28 @@ __device__ __forceinline__ double2 shfl_xor_c(double2 v, int m) {
 }
 
 // One CTA per SM owns a contiguous slice range (near partners of neighbouring slices meet in L1); a warp takes a
-// slice per round, a lane a row.  Per round and lane: LB gathers in flight (two batches for the first sixteen load
+// slice per round, a lane a row.  Per round and lane: LB gathers in flight (batches over the first BF_STATIC load
 // terms, whose masks / products sit at compile-time positions of the constant bank), the shuffle terms, the
 // diagonal look-up, the fused epilogue.  Nothing is carried from round to round, so the kernel fits 72-80 registers
 // and 24-28 warps per SM hide the L1 / L2 latencies -- measured on config 2: 16 warps x 16 gathers with a
-// cross-round prefetch (128 registers) 2140 prop_step!/s, 24 x 8: 2410, 28 x 8: 2480-2500, 32 x 4: 2400;
+// cross-round prefetch (128 registers) 2140 prop_step!/s, 24 x 8: 2410, 28 x 8: 2480-2540, 32 x 4: 2400;
 // with every far partner replaced by a near one (no L2 traffic at all) 2570: what is left is the L1 / shared-
 // memory data pipe (60 wavefronts of gathers, 20 of shuffles, 20 of vector streams per slice).
-// REALC: every (coefficient x value) product and every (coefficient x diagonal) of this launch is real.
-template <int EPI, int REALC, int THREADS, int LB>
+// CK: where the products coefficient x value come from -- 0: shared memory, computed in the prologue from the
+// device copy of the coefficients; 1 / 2: the constant bank, computed on the host (all real / complex).
+// COND: some term is conditional (its product is dropped on the rows outside its sub-cube).
+// NS: load terms at compile-time positions (16 or BF_STATIC; the unrolled batches beyond the list cost ~10 %).
+template <int EPI, int CK, int COND, int THREADS, int LB, int NS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict__ coef, const double2* __restrict__ x,
-                    EpiArgs e, int rounds) {
-  __shared__ double2 s_c[BF_MAX_TERMS];
-  __shared__ double2 s_cl[BF_MAX_LOW];
+               EpiArgs e, int rounds) {
+  __shared__ double2 s_c[CK == 0 ? BF_MAX_TERMS + BF_MAX_LOW : 1];
   __shared__ double2 s_cd[BF_MAX_DIAG];
-  extern __shared__ double2 s_dt[];
+  extern __shared__ double2 s_dt[];  // coded diagonals: sum_i coefficient_i x value_i per joint code [n_joint]
+  // programmatic dependent launch: the next term's launch and this set-up overlap the tail of the previous term
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (!REALC) {
-    if (threadIdx.x < v.n_high) s_c[threadIdx.x] = cmul2(coef[v.op[threadIdx.x]], v.val[threadIdx.x]);
-    if (threadIdx.x < v.n_low) s_cl[threadIdx.x] = cmul2(coef[v.lop[threadIdx.x]], v.lval[threadIdx.x]);
+  if (CK == 0) {
+    for (int t = threadIdx.x; t < BF_MAX_TERMS + BF_MAX_LOW; t += THREADS) s_c[t] = cmul2(coef[v.top[t]], v.tval[t]);
     if (threadIdx.x < v.n_diag) s_cd[threadIdx.x] = coef[v.diag_op[threadIdx.x]];
   }
   if (v.dcode != nullptr) {
@@ -443,18 +529,14 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
       for (int i = 0; i < BF_MAX_DIAG; ++i)
         if (i < v.n_diag) {
           const double d = v.dtab[v.doff[i] + (c / v.dstride[i]) % v.dcount[i]];
-          if (REALC) {
-            re = fma(v.cdr[i], d, re);
-          } else {
-            const double2 u = coef[v.diag_op[i]];
-            re = fma(u.x, d, re);
-            im = fma(u.y, d, im);
-          }
+          const double2 u = CK == 0 ? coef[v.diag_op[i]] : v.cd[i];
+          re = fma(u.x, d, re);
+          if (CK != 1) im = fma(u.y, d, im);
         }
       s_dt[c] = make_double2(re, im);
     }
   }
-  if (!REALC || v.dcode != nullptr) __syncthreads();
+  if (CK == 0 || v.dcode != nullptr) __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = THREADS >> 5;
@@ -474,15 +556,32 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
     double hr = 0.0, hi = 0.0, hr2 = 0.0, hi2 = 0.0;
     double2 yv = make_double2(0.0, 0.0), av = yv;
     double2 xv[LB];
+    // one term: product (from the constant bank or shared memory), condition, multiply-add
+    auto accumulate = [&](double cr, double ci, uint32_t cm, uint32_t cv, const double2& xq, int chain) {
+      if (COND) {
+        const bool on = (r32 & cm) == cv;
+        cr = on ? cr : 0.0;
+        if (CK != 1) ci = on ? ci : 0.0;
+      }
+      if (CK == 1) {
+        if (chain & 1) { hr2 = fma(cr, xq.x, hr2); hi2 = fma(cr, xq.y, hi2); }
+        else { hr = fma(cr, xq.x, hr); hi = fma(cr, xq.y, hi); }
+      } else {
+        hr = fma(cr, xq.x, hr);
+        hi = fma(cr, xq.y, hi);
+        hr2 = fma(-ci, xq.y, hr2);
+        hi2 = fma(ci, xq.x, hi2);
+      }
+    };
 #pragma unroll
-    for (int b0 = 0; b0 < 16; b0 += LB) {
+    for (int b0 = 0; b0 < NS; b0 += LB) {
 #pragma unroll
       for (int g = 0; g < LB / 4; ++g)
         if (b0 + 4 * g < v.n_high) {
 #pragma unroll
           for (int q = 4 * g; q < 4 * g + 4; ++q) xv[q] = ld_x(x + (r32 ^ v.mask[b0 + q]));
         }
-      if (b0 == 8 && THREADS < 1024) {  // the epilogue operands travel with the second batch
+      if (b0 == LB && THREADS < 1024) {  // the epilogue operands travel with the second batch
         if (EPI == EPI_MUL) {
           if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = ld_noalloc(e.y + row);
         } else if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
@@ -495,48 +594,38 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
         if (b0 + 4 * g < v.n_high) {
 #pragma unroll
           for (int q = 4 * g; q < 4 * g + 4; ++q) {
-            if (REALC) {
-              const double c = v.cre[b0 + q];
-              if (q & 1) { hr2 = fma(c, xv[q].x, hr2); hi2 = fma(c, xv[q].y, hi2); }
-              else { hr = fma(c, xv[q].x, hr); hi = fma(c, xv[q].y, hi); }
-            } else {
+            if (CK == 0) {
               const double2 c = s_c[b0 + q];
-              hr = fma(c.x, xv[q].x, hr);
-              hi = fma(c.x, xv[q].y, hi);
-              hr2 = fma(-c.y, xv[q].y, hr2);
-              hi2 = fma(c.y, xv[q].x, hi2);
+              accumulate(c.x, c.y, v.cmask[b0 + q], v.cval[b0 + q], xv[q], q);
+            } else {
+              accumulate(v.cre[b0 + q], CK == 2 ? v.cim[b0 + q] : 0.0, v.cmask[b0 + q], v.cval[b0 + q], xv[q], q);
             }
           }
         }
     }
-    for (int t = 16; t < v.n_high; t += 4) {  // more than sixteen load terms
+    for (int t = NS; t < v.n_high; t += 4) {  // more load terms than static positions
 #pragma unroll
       for (int q = 0; q < 4; ++q) xv[q] = ld_x(x + (r32 ^ v.mask[t + q]));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const double2 c = REALC ? make_double2(v.cre[t + q], 0.0) : s_c[t + q];
-        hr = fma(c.x, xv[q].x, hr);
-        hi = fma(c.x, xv[q].y, hi);
-        if (!REALC) {
-          hr2 = fma(-c.y, xv[q].y, hr2);
-          hi2 = fma(c.y, xv[q].x, hi2);
+        if (CK == 0) {
+          const double2 c = s_c[t + q];
+          accumulate(c.x, c.y, v.cmask[t + q], v.cval[t + q], xv[q], q);
+        } else {
+          accumulate(v.cre[t + q], CK == 2 ? v.cim[t + q] : 0.0, v.cmask[t + q], v.cval[t + q], xv[q], q);
         }
       }
     }
+    // shuffle terms: the partner row is a lane of this warp
 #pragma unroll
     for (int q = 0; q < BF_MAX_LOW; ++q)
       if (q < v.n_low) {
         const double2 xs = shfl_xor_c(xown, (int)v.lmask[q]);
-        if (REALC) {
-          const double c = v.lcre[q];
-          hr = fma(c, xs.x, hr);
-          hi = fma(c, xs.y, hi);
+        if (CK == 0) {
+          const double2 c = s_c[BF_MAX_TERMS + q];
+          accumulate(c.x, c.y, v.lcmask[q], v.lcval[q], xs, 0);
         } else {
-          const double2 c = s_cl[q];
-          hr = fma(c.x, xs.x, hr);
-          hi = fma(c.x, xs.y, hi);
-          hr2 = fma(-c.y, xs.y, hr2);
-          hi2 = fma(c.y, xs.x, hi2);
+          accumulate(v.lcre[q], CK == 2 ? v.lcim[q] : 0.0, v.lcmask[q], v.lcval[q], xs, 0);
         }
       }
     if (THREADS >= 1024) {  // 64 registers: the epilogue operands are requested once the gathers are consumed
@@ -551,14 +640,14 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
     if (v.dcode != nullptr) {
       const double2 t = s_dt[code];
       dre = t.x;
-      if (!REALC) dim = t.y;
+      if (CK != 1) dim = t.y;
     } else {
       for (int i = 0; i < v.n_diag; ++i) {
-        const double2 u = REALC ? make_double2(v.cdr[i], 0.0) : s_cd[i];
+        const double2 u = CK == 0 ? s_cd[i] : v.cd[i];
         if (v.diag_r[i] != nullptr) {
           const double d = ld_stream_f64(v.diag_r[i] + row);
           dre = fma(u.x, d, dre);
-          if (!REALC) dim = fma(u.y, d, dim);
+          if (CK != 1) dim = fma(u.y, d, dim);
         } else if (v.diag_c[i] != nullptr) {
           const double2 d = ld_stream(v.diag_c[i] + row);
           dre += u.x * d.x - u.y * d.y;
@@ -580,16 +669,25 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   }
 }
 
-template <int EPI, int REALC, int THREADS, int LB>
+template <int EPI, int CK, int COND, int THREADS, int LB, int NS>
 static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) {
   qp_ctx_t ctx = gen->ctx;
-  BitflipView& v = gen->bitflip->view;
-  if (REALC) {
-    for (int t = 0; t < v.n_high; ++t) v.cre[t] = gen->h_coef[v.op[t]].x * v.val[t].x;
-    for (int t = 0; t < v.n_low; ++t) v.lcre[t] = gen->h_coef[v.lop[t]].x * v.lval[t].x;
-    for (int i = 0; i < v.n_diag; ++i) v.cdr[i] = gen->h_coef[v.diag_op[i]].x;
+  qp_bitflip_s* B = gen->bitflip;
+  BitflipView& v = B->view;
+  if (CK != 0) {
+    for (int t = 0; t < v.n_high; ++t) {
+      const double2 u = gen->h_coef[B->h_op[t]], a = B->h_val[t];
+      v.cre[t] = u.x * a.x - u.y * a.y;
+      v.cim[t] = u.x * a.y + u.y * a.x;
+    }
+    for (int t = 0; t < v.n_low; ++t) {
+      const double2 u = gen->h_coef[B->h_op[BF_MAX_TERMS + t]], a = B->h_val[BF_MAX_TERMS + t];
+      v.lcre[t] = u.x * a.x - u.y * a.y;
+      v.lcim[t] = u.x * a.y + u.y * a.x;
+    }
+    for (int i = 0; i < v.n_diag; ++i) v.cd[i] = gen->h_coef[v.diag_op[i]];
   }
-  auto kern = k_spmv_bitflip<EPI, REALC, THREADS, LB>;
+  auto kern = k_spmv_bitflip<EPI, CK, COND, THREADS, LB, NS>;
   const int wpc = THREADS / 32;
   const int64_t n_slices = v.n >> 5;
   int64_t ctas = ctx->sm_count;
@@ -625,19 +723,16 @@ static int32_t bitflip_launch(qp_gen_t gen, const double2* x, const EpiArgs& e) 
   return QP_OK;
 }
 
-template <int EPI>
-static int32_t bitflip_launch_epi(qp_gen_t gen, const double2* x, const EpiArgs& e) {
-  // real products: known on the host when the coefficients were set from the host and are not per-trajectory
-  bool realc = gen->bitflip->all_real && gen->h_coef_valid && (int)gen->h_coef.size() == gen->n_ops;
-  for (int l = 0; realc && l < gen->n_ops; ++l) realc = gen->h_coef[l].y == 0.0;
-  // CTA shape: 24 / 28 warps x 8 gathers or 32 warps x 4 -- the one whose whole rounds waste the fewest SM slots
-  // (ties: 28 warps); QPROP_BITFLIP_THREADS = 768 / 896 / 1024 forces one
+template <int EPI, int CK, int COND>
+static int32_t bitflip_launch_shape(qp_gen_t gen, const double2* x, const EpiArgs& e) {
+  // CTA shape: 28 warps x 8 gathers (72 registers) or 32 warps x 4 (64) -- the one whose whole rounds waste fewer
+  // SM slots (ties: 28 warps); QPROP_BITFLIP_THREADS = 896 / 1024 forces one
   static const int threads_env = getenv("QPROP_BITFLIP_THREADS") ? atoi(getenv("QPROP_BITFLIP_THREADS")) : 0;
   int threads = threads_env;
-  if (threads != 768 && threads != 896 && threads != 1024) {
+  if (threads != 896 && threads != 1024) {
     const int64_t n_slices = gen->n >> 5, per_sm = (n_slices + gen->ctx->sm_count - 1) / gen->ctx->sm_count;
     int64_t best = -1;
-    for (int t : {896, 768, 1024}) {
+    for (int t : {896, 1024}) {
       const int wpc = t / 32;
       const int64_t spc = (per_sm + wpc - 1) / wpc * wpc, ctas = (n_slices + spc - 1) / spc;
       const int64_t slots = spc * gen->ctx->sm_count * ((ctas + gen->ctx->sm_count - 1) / gen->ctx->sm_count);
@@ -647,9 +742,24 @@ static int32_t bitflip_launch_epi(qp_gen_t gen, const double2* x, const EpiArgs&
       }
     }
   }
-  if (threads == 1024) return realc ? bitflip_launch<EPI, 1, 1024, 4>(gen, x, e) : bitflip_launch<EPI, 0, 1024, 4>(gen, x, e);
-  if (threads == 768) return realc ? bitflip_launch<EPI, 1, 768, 8>(gen, x, e) : bitflip_launch<EPI, 0, 768, 8>(gen, x, e);
-  return realc ? bitflip_launch<EPI, 1, 896, 8>(gen, x, e) : bitflip_launch<EPI, 0, 896, 8>(gen, x, e);
+  const bool few = gen->bitflip->view.n_high <= 16;
+  if (threads == 1024) return few ? bitflip_launch<EPI, CK, COND, 1024, 4, 16>(gen, x, e) : bitflip_launch<EPI, CK, COND, 1024, 4, BF_STATIC>(gen, x, e);
+  return few ? bitflip_launch<EPI, CK, COND, 896, 8, 16>(gen, x, e) : bitflip_launch<EPI, CK, COND, 896, 8, BF_STATIC>(gen, x, e);
+}
+
+template <int EPI>
+static int32_t bitflip_launch_epi(qp_gen_t gen, const double2* x, const EpiArgs& e) {
+  const qp_bitflip_s* B = gen->bitflip;
+  // products on the host when the coefficients were set from the host and are not per-trajectory; real products
+  // and real diagonal contributions: half the multiply-adds.  Coefficients that only exist on the device: one
+  // general variant (products from shared memory)
+  static const int device_coefs = getenv("QPROP_BITFLIP_DEVICE_COEFS") ? atoi(getenv("QPROP_BITFLIP_DEVICE_COEFS")) : 0;
+  const bool host = gen->h_coef_valid && (int)gen->h_coef.size() == gen->n_ops && !device_coefs;
+  if (!host) return bitflip_launch<EPI, 0, 1, 896, 8, BF_STATIC>(gen, x, e);
+  bool real = B->values_real && B->diags_real;
+  for (int l = 0; real && l < gen->n_ops; ++l) real = gen->h_coef[l].y == 0.0;
+  if (B->cond) return real ? bitflip_launch_shape<EPI, 1, 1>(gen, x, e) : bitflip_launch_shape<EPI, 2, 1>(gen, x, e);
+  return real ? bitflip_launch_shape<EPI, 1, 0>(gen, x, e) : bitflip_launch_shape<EPI, 2, 0>(gen, x, e);
 }
 
 int32_t qp_launch_bitflip(qp_gen_t gen, int epi, const double2* x, const EpiArgs& e) {

@@ -1340,7 +1340,8 @@ def test_operator_mul_bitflip(qp, ctx, n_bits, masks, cv, cd, coeffs):
 
 
 def test_bitflip_refuses_other_structures(qp, ctx):
-    """Row-dependent values (a Y-type flip: the sign follows the bit) or ragged rows are not bit-flip operators."""
+    """Row-dependent values (a Y-type flip: the sign follows the bit), rows that carry an entry without forming a
+    sub-cube, or generic sparse matrices are not bit-flip operators."""
     N = 256
     rows = np.arange(N)
     sign = 1 - 2 * ((rows >> 3) & 1)
@@ -1351,6 +1352,10 @@ def test_bitflip_refuses_other_structures(qp, ctx):
     A = sp.random(N, N, 0.05, random_state=1, format="csr").astype(complex)
     with pytest.raises(qp.QPropError):
         qp.DeviceGenerator(ctx, [A], 0, "bitflip")
+    r3 = rows[rows % 3 == 0]                       # the rows carrying the flip are not a sub-cube
+    C3 = sp.csr_matrix((np.ones(len(r3), dtype=complex), (r3, r3 ^ 16)), shape=(N, N))
+    with pytest.raises(qp.QPropError):
+        qp.DeviceGenerator(ctx, [C3], 0, "bitflip")
     # AUTO falls back silently and stays correct
     gen = qp.DeviceGenerator(ctx, [Y], 0)
     assert gen.format != "bitflip"
@@ -1358,3 +1363,56 @@ def test_bitflip_refuses_other_structures(qp, ctx):
     dy = qp.DeviceState(ctx, N).zero()
     gen.mul(dy, qp.DeviceState.from_host(ctx, x), [], 1.0, 0.0)
     assert rel(dy.to_host(), Y @ x) < 1e-14
+
+
+@pytest.mark.parametrize("n_bits,coeffs", [(8, [0.7, -1.3]), (11, [0.4 - 0.3j, 1.1j])])
+def test_operator_mul_bitflip_conditional_terms(qp, ctx, n_bits, coeffs):
+    """Conditional flips (sigma^-/sigma^+ on a bit: present on the rows whose bit is 0 / 1), a two-bit conditional
+    flip (the jump term of a decay channel in a Liouvillian), diagonal and flips inside ONE operator."""
+    rng = np.random.default_rng(n_bits)
+    N = 1 << n_bits
+    rows = np.arange(N)
+
+    def lower(k, g):      # |..0..><..1..|: row has bit k = 0, column = row | 2^k
+        r = rows[(rows >> k) & 1 == 0]
+        return sp.csr_matrix((np.full(len(r), g, dtype=complex), (r, r | (1 << k))), shape=(N, N))
+
+    def flip(m, g):
+        return sp.csr_matrix((np.full(N, g, dtype=complex), (rows, rows ^ m)), shape=(N, N))
+
+    def jump(k1, k2, g):  # both bits 1 -> 0
+        r = rows[((rows >> k1) & 1 == 0) & ((rows >> k2) & 1 == 0)]
+        return sp.csr_matrix((np.full(len(r), g, dtype=complex), (r, r | (1 << k1) | (1 << k2))), shape=(N, N))
+
+    d = sp.diags((rng.standard_normal(N) + 1j * rng.standard_normal(N))).tocsr()
+    op0 = (d + jump(1, n_bits - 1, 0.05) + jump(6, 3, 0.07) + lower(2, 0.3 - 0.1j) + lower(n_bits - 2, 0.2).T).tocsr()
+    op1 = sum(flip(1 << k, -1j) for k in range(n_bits // 2)) + sum(flip(1 << k, 1j) for k in range(n_bits // 2, n_bits))
+    op2 = (sp.diags(rng.integers(-2, 3, N).astype(complex)) + lower(0, 1.5) + lower(0, 1.5).T.conj()).tocsr()
+    ops = [op0, op1.tocsr(), op2]
+    gen = qp.DeviceGenerator(ctx, ops, 2, "bitflip")
+    assert gen.format == "bitflip"
+    H = (ops[0] + coeffs[0] * ops[1] + coeffs[1] * ops[2]).tocsr()
+    x = rand_state(rng, N)
+    y0 = rand_state(rng, N)
+    dx = qp.DeviceState.from_host(ctx, x)
+    for alpha, beta in [(1.0, 0.0), (0.3 - 0.8j, 1.0)]:
+        dy = qp.DeviceState.from_host(ctx, y0)
+        gen.mul(dy, dx, coeffs, alpha, beta)
+        assert rel(dy.to_host(), alpha * (H @ x) + beta * y0) < 1e-13
+    assert abs(gen.expval(dx, coeffs) - np.vdot(x, H @ x)) < 1e-11
+
+
+@pytest.mark.parametrize("n_spins", [4, 6])
+def test_newton_liouvillian_bitflip_vs_csr(qp, ctx, n_spins):
+    """BASELINE config 4 shape at reduced size: the Liouvillian (commutator halves = flips, decay channels =
+    conditional two-bit flips, complex diagonal) on the bit-flip form against merged CSR and the oracle."""
+    w = qp.workloads.config4_liouvillian(n_spins, nt=6, dt=0.05)
+    terms = [w["ops"][0]] + list(zip(w["ops"][1:], w["controls"]))
+    ref = O.propagate(w["psi0"], O.hamiltonian(*terms), w["tlist"], "newton")
+    outs = {}
+    for fmt in ("csr", "bitflip"):
+        p = qp.init_prop(w["psi0"], qp.hamiltonian(*terms), w["tlist"], "newton", ctx=ctx, matrix_format=fmt)
+        assert p.wrk.krylov.gen.format == fmt
+        outs[fmt] = qp.propagate(p)
+        assert rel(outs[fmt], ref) < RTOL, fmt
+    assert rel(outs["bitflip"], outs["csr"]) < 1e-12
