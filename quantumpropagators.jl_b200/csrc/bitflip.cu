@@ -519,7 +519,7 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   // programmatic dependent launch: the next term's launch and this set-up overlap the tail of the previous term
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (CK == 0) {
-    for (int t = threadIdx.x; t < BF_MAX_TERMS + BF_MAX_LOW; t += THREADS) s_c[t] = cmul2(coef[v.top[t]], v.tval[t]);
+    for (int t = threadIdx.x; t < BF_MAX_TERMS + BF_MAX_LOW; t += THREADS) s_c[t] = cmul2(coef[v.top[t]], ld_stream(v.tval + t));  // static data: may sit above the wait
     if (threadIdx.x < v.n_diag) s_cd[threadIdx.x] = coef[v.diag_op[threadIdx.x]];
   }
   if (v.dcode != nullptr) {
