@@ -736,7 +736,8 @@ static int32_t bitflip_launch_shape(qp_gen_t gen, const double2* x, const EpiArg
       const int wpc = t / 32;
       const int64_t spc = (per_sm + wpc - 1) / wpc * wpc, ctas = (n_slices + spc - 1) / spc;
       const int64_t slots = spc * gen->ctx->sm_count * ((ctas + gen->ctx->sm_count - 1) / gen->ctx->sm_count);
-      if (best < 0 || slots < best) {
+      // long term lists are latency-bound with 4 gathers in flight: 32 warps x 4 only if it saves 3 % of the slots
+      if (best < 0 || (gen->bitflip->view.n_high > 16 ? slots * 100 < best * 97 : slots < best)) {
         best = slots;
         threads = t;
       }

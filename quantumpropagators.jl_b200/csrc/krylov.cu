@@ -13,7 +13,7 @@
 
 #include "spmv.cuh"
 
-constexpr int KV = 8;           // Krylov vectors handled per fused pass
+constexpr int KV = 12;          // Krylov vectors handled per fused pass (m_max <= 11: every column in one chunk)
 constexpr int KBLOCK = 256;
 
 struct Weights {
@@ -133,6 +133,68 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
   }
 }
 
+// Round 1 of Gram-Schmidt and the multi-dot of a possible round 2 in ONE pass over q_0..q_{NV-1} and w:
+// w' = w - sum_i h[i] q_i is written back, and <q_i|w'> (the coefficients a second round would need) and |w'|^2
+// are accumulated from the values still in registers.  Saves the (NV + 1)-vector read pass of the second round's
+// multi-dot whenever the DGKS criterion fires (on config 4: in most columns).  dots[block][2 KV + 2] as in
+// k_multidot, norms[block] as in k_project_out.
+template <int NV>
+__global__ void __launch_bounds__(KBLOCK)
+k_project_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h, double2* __restrict__ w,
+                   int64_t n, double* __restrict__ dots, double* __restrict__ norms) {
+  pdl_sync();
+  double2 hv[NV];
+  double sr[NV], si[NV], nn = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    hv[i] = h[i];
+    sr[i] = si[i] = 0.0;
+  }
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double2 wv = w[r];
+    double2 qv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) qv[i] = q0[i * stride + r];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      wv.x -= hv[i].x * qv[i].x - hv[i].y * qv[i].y;
+      wv.y -= hv[i].x * qv[i].y + hv[i].y * qv[i].x;
+    }
+    w[r] = wv;
+    nn += wv.x * wv.x + wv.y * wv.y;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sr[i] += qv[i].x * wv.x + qv[i].y * wv.y;  // conj(q) * w'
+      si[i] += qv[i].x * wv.y - qv[i].y * wv.x;
+    }
+  }
+  __shared__ double sh[KBLOCK / 32][2 * NV + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sr[i] += __shfl_xor_sync(0xffffffffu, sr[i], o);
+      si[i] += __shfl_xor_sync(0xffffffffu, si[i], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sh[warp][2 * i] = sr[i];
+      sh[warp][2 * i + 1] = si[i];
+    }
+    sh[warp][2 * NV] = nn;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NV + 1) {
+    double t = 0.0;
+    for (int k = 0; k < KBLOCK / 32; ++k) t += sh[k][threadIdx.x];
+    if (threadIdx.x == 2 * NV) norms[blockIdx.x] = t;
+    else dots[(size_t)blockIdx.x * (2 * KV + 2) + threadIdx.x] = t;
+  }
+}
+
 // one warp: |w|^2 after the projection; round 1 decides on the device whether a second
 // (DGKS) round is needed -- when the projection removed more than half of |w|^2 -- and the
 // second round adds its correction to the accumulated column
@@ -219,7 +281,11 @@ static int kgrid(qp_ctx_t ctx, int64_t n) {
     case 5: { constexpr int NV = 5; CALL; } break; \
     case 6: { constexpr int NV = 6; CALL; } break; \
     case 7: { constexpr int NV = 7; CALL; } break; \
-    default: { constexpr int NV = 8; CALL; } break; \
+    case 8: { constexpr int NV = 8; CALL; } break; \
+    case 9: { constexpr int NV = 9; CALL; } break; \
+    case 10: { constexpr int NV = 10; CALL; } break; \
+    case 11: { constexpr int NV = 11; CALL; } break; \
+    default: { constexpr int NV = 12; CALL; } break; \
   }
 
 // ---------------------------------------------------------------------------------------
@@ -415,13 +481,36 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
   double2* w = K->q + (size_t)(j + 1) * n;
   const int nblocks = kgrid(ctx, n);
   const size_t need = (size_t)nblocks * (2 * KV + 2);
-  QP_CHECK(qp_ctx_reserve_red(ctx, need));
+  QP_CHECK(qp_ctx_reserve_red(ctx, need + (size_t)nblocks));
   double* partial = ctx->d_red;
   double2* h_acc = K->d_hall + (size_t)j * (K->m_max + 2);
   double2* h_corr = K->d_h;  // this round's coefficients
   ColCtl* ctl = K->d_ctl + j;
   static const double eta = getenv("QPROP_DGKS_ETA") ? atof(getenv("QPROP_DGKS_ETA")) : 0.70710678118654752;
   const double eta2 = eta * eta;
+  static const int unfused = getenv("QPROP_GS_UNFUSED") ? atoi(getenv("QPROP_GS_UNFUSED")) : 0;
+  if (nvec <= KV && !unfused) {
+    // single chunk: multi-dot | projection fused with the second round's multi-dot | decision |
+    // (gated) coefficients of the second round | (gated) second projection | (gated) final norm
+    double* norms = partial + need;
+    const double* gate = &ctl->again;
+    DISPATCH_NV(nvec, (qp_launch_pdl(k_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, w, n, partial, (const double*)nullptr)));
+    QP_LAUNCHED(ctx);
+    qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nvec, h_acc, 0, ctl, 1,
+                  (const double*)nullptr);
+    QP_LAUNCHED(ctx);
+    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_acc, w, n, partial, norms)));
+    QP_LAUNCHED(ctx);
+    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, norms, nblocks, ctl, 1, h_acc, h_corr, nvec, norm_min, eta2);
+    QP_LAUNCHED(ctx);
+    qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nvec, h_corr, 0, ctl, 0, gate);
+    QP_LAUNCHED(ctx);
+    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_corr, w, n, norms, gate)));
+    QP_LAUNCHED(ctx);
+    qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, norms, nblocks, ctl, 2, h_acc, h_corr, nvec, norm_min, eta2);
+    QP_LAUNCHED(ctx);
+    return QP_OK;
+  }
   for (int round = 1; round <= 2; ++round) {
     const double* gate = round == 2 ? &ctl->again : nullptr;
     double2* h = round == 1 ? h_acc : h_corr;
