@@ -56,9 +56,10 @@ extern "C" {
                              triples; chosen when the table has < 4096 entries            */
 #define QP_FORMAT_LR 5    /* matrix-free left/right products on column-stacked matrices
                              (qp_op_create_leftright); chosen automatically for such operators */
-#define QP_FORMAT_BITFLIP 6 /* no matrix stream: every operator is diagonal (an explicit vector) or a
-                             uniform bit-flip stencil -- each row r couples to r XOR mask_t with the
-                             same value v_t (sums of Pauli-X strings: transverse fields, QAOA mixers).
+#define QP_FORMAT_BITFLIP 6 /* no matrix stream: every operator is a diagonal (a vector or 16-bit codes)
+                             plus uniform bit flips -- row r couples to r XOR mask_t with the same value
+                             v_t, on all rows or on the sub-cube (r AND cmask_t) == cval_t (sums of
+                             Pauli-X strings, sigma+/sigma- terms, Liouvillians of such systems).
                              Detected from the uploaded matrices; single states use it, state batches
                              of such a generator keep the tiled / dictionary kernels */
 

@@ -32,7 +32,13 @@ using qptile::Entry16;
 using qptile::Entry32;
 using qptile::N_KINDS;
 
-constexpr int TILE_THREADS = 512;
+#ifndef TILE_THREADS_N
+#define TILE_THREADS_N 512
+#endif
+#ifndef TILE_LEAN
+#define TILE_LEAN 1
+#endif
+constexpr int TILE_THREADS = TILE_THREADS_N;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 constexpr int TILE_RING = 3;
 
@@ -273,10 +279,11 @@ __device__ __forceinline__ void tile_rows(const TileView& tv, const ConstTab& ct
       }
     }
   };
-  if (warp < rows) prefetch(t_ptr, idx);
+  if (!TILE_LEAN && warp < rows) prefetch(t_ptr, idx);
   for (int s = warp; s < rows; s += TILE_WARPS) {
+    if (TILE_LEAN) prefetch(t_ptr, idx);  // nothing carried from row to row: fewer registers, more warps
     const double2 tv_in = n_t, yv = n_y, av = n_a;
-    if (s + TILE_WARPS < rows) prefetch(t_ptr + t_stride, idx + el_stride);
+    if (!TILE_LEAN && s + TILE_WARPS < rows) prefetch(t_ptr + t_stride, idx + el_stride);
     const uint32_t xs_row = ra.xs_base + (uint32_t)s * 512u;
     const uint32_t cw = ra.codes_base + (uint32_t)(s * WT) * 16u;
     const double2 xown = lds_f64x2(xs_row);
