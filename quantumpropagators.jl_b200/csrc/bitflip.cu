@@ -507,7 +507,9 @@ __device__ __forceinline__ double2 shfl_xor_c(double2 v, int m) {
 // memory data pipe (60 wavefronts of gathers, 20 of shuffles, 20 of vector streams per slice).
 // CK: where the products coefficient x value come from -- 0: shared memory, computed in the prologue from the
 // device copy of the coefficients; 1 / 2: the constant bank, computed on the host (all real / complex).
-// COND: some term is conditional (its product is dropped on the rows outside its sub-cube).
+// COND: some term is conditional (its product is dropped on the rows outside its sub-cube; the load is issued
+// regardless -- predicating it on "the sub-cube excludes the whole warp" made config 4 7 % SLOWER, like every
+// other attempt to put a predicate in front of these loads).
 // NS: load terms at compile-time positions (16 or BF_STATIC; the unrolled batches beyond the list cost ~10 %).
 template <int EPI, int CK, int COND, int THREADS, int LB, int NS>
 __global__ void __launch_bounds__(THREADS, 1)
