@@ -1253,8 +1253,8 @@ static int32_t launch_selld(qp_gen_t gen, const DictView& m, const double2* x, c
   }
   // one CTA of 512 threads per SM: all 16 resident warps sweep ONE contiguous slice range (measured
   // 32.0 us per term on config 2 against 32.8 us for 2 x 256 and 33.5 us for 4 x 128)
-  static const int threads_env = getenv("QPROP_SELLD_THREADS") ? atoi(getenv("QPROP_SELLD_THREADS")) : 512;
-  const int threads = (threads_env == 128 || threads_env == 256) ? threads_env : 512;
+  static const int threads_env = getenv("QPROP_SELLD_THREADS") ? atoi(getenv("QPROP_SELLD_THREADS")) : SELLD_THREADS;
+  const int threads = (threads_env == 128 || threads_env == 256) ? threads_env : SELLD_THREADS;
   static const int per_sm = getenv("QPROP_SELLD_CTAS") ? atoi(getenv("QPROP_SELLD_CTAS")) : 0;
   int occ = per_sm;
   if (occ <= 0) {

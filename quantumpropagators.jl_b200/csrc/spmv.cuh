@@ -647,8 +647,14 @@ __device__ __forceinline__ void selld_epi_load(const EpiArgs& e, const double2* 
   }
 }
 
+#ifndef SELLD_THREADS
+#define SELLD_THREADS 512
+#endif
+#ifndef SELLD_LEAN
+#define SELLD_LEAN 0
+#endif
 template <int EPI, int CB, int TAIL, int REALT>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(SELLD_THREADS, 1)
 k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e,
              int slices_per_cta) {
   // the table, pre-multiplied by this step's operator coefficients, lives in shared memory
@@ -694,8 +700,9 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
     if (row < m.n) selld_epi_load<EPI>(e, x, row, n_xr, n_yv, n_av);
   };
   int64_t s = s_begin + warp;
-  if (s < s_end) prefetch(s);
+  if (!SELLD_LEAN && s < s_end) prefetch(s);
   while (s < s_end) {
+    if (SELLD_LEAN) prefetch(s);  // nothing carried from slice to slice: fewer registers, more warps
     const int64_t row = s * QP_SELL_C + lane;
     const bool live = row < m.n;
     const double2* xbase = x + (live ? row : m.n - 1);  // dead lanes hold padding codes only
@@ -705,7 +712,7 @@ k_spmv_selld(DictView m, const double2* __restrict__ coef, const double2* __rest
     const double2 xr = n_xr, yv = n_yv, av = n_av;
     const bool any = n_off0 < n_off1;
     const int64_t s_next = s + nwarps;
-    if (s_next < s_end) prefetch(s_next);
+    if (!SELLD_LEAN && s_next < s_end) prefetch(s_next);
     double sr = 0.0, si = 0.0, sr2 = 0.0, si2 = 0.0;
     if (any) {
       for (;;) {
