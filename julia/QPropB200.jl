@@ -44,6 +44,7 @@ module NewtonB200 end
 
 const QP_LAYOUT_CSC = Int32(0)
 const QP_FORMAT_AUTO = Int32(0)
+const QP_FORMAT_BITFLIP = Int32(6)  # diagonal + (conditional) uniform bit flips, detected by the library (AUTO selects it)
 
 # ---------------------------------------------------------------------------------------
 # status -> exception (reference error conventions, SURVEY.md §5)

@@ -1416,3 +1416,26 @@ def test_newton_liouvillian_bitflip_vs_csr(qp, ctx, n_spins):
         outs[fmt] = qp.propagate(p)
         assert rel(outs[fmt], ref) < RTOL, fmt
     assert rel(outs["bitflip"], outs["csr"]) < 1e-12
+
+
+@pytest.mark.parametrize("N,masks", [
+    (96, [1, 2, 7, 16, 31]),                                  # N not a power of two: only in-warp partners keep r ^ m < N
+    (1 << 12, list(range(1, 41))),                            # 40 terms: nine+ shuffle candidates, more load terms than static slots
+    (1 << 13, [1 << k for k in range(13)] + [(1 << k) | 1 for k in range(1, 13)] + [4095, 8191, 5461]),
+])
+def test_operator_mul_bitflip_term_counts(qp, ctx, N, masks):
+    """Edge shapes of the bit-flip form: N not a power of two, more in-warp terms than shuffle slots (the rest
+    become loads), more load terms than compile-time constant-bank positions (the dynamic tail loop)."""
+    rng = np.random.default_rng(N + len(masks))
+    rows = np.arange(N)
+    vals = rng.standard_normal(len(masks)) + 1j * rng.standard_normal(len(masks))
+    X = sum(sp.csr_matrix((np.full(N, v, dtype=complex), (rows, rows ^ m)), shape=(N, N)) for m, v in zip(masks, vals)).tocsr()
+    D = sp.diags(rng.standard_normal(N).astype(complex)).tocsr()
+    gen = qp.DeviceGenerator(ctx, [D, X], 1, "bitflip")
+    assert gen.format == "bitflip"
+    x = rand_state(rng, N)
+    dx = qp.DeviceState.from_host(ctx, x)
+    for c in (0.8, 0.3 - 1.1j):
+        dy = qp.DeviceState(ctx, N).zero()
+        gen.mul(dy, dx, [c], 1.0, 0.0)
+        assert rel(dy.to_host(), (D + c * X) @ x) < 1e-13
