@@ -241,6 +241,269 @@ __global__ void k_bf_encode(DiagTabs t, const double* __restrict__ tab, int64_t 
   }
 }
 
+struct BfTerm {
+  uint32_t mask, cmask, cval;
+  double2 val;
+  int op;
+};
+struct BfCollect {
+  std::vector<BfTerm> terms;
+  bool values_real = true, diags_real = true;
+};
+
+// statistics of one CSR matrix (n rows) -> S
+static int32_t bf_scan_matrix(qp_ctx_t ctx, const uint32_t* ptr, const uint32_t* col, const double2* val, int64_t n, MaskSet* d_set,
+                              MaskSet& S) {
+  constexpr int ROWS_PER_BLOCK = 2048;
+  k_bf_set_init<<<1, 128, 0, ctx->stream>>>(d_set);
+  k_bf_scan<<<(unsigned)((n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), 256, 0, ctx->stream>>>(ptr, col, val, n, ROWS_PER_BLOCK, d_set);
+  ctx->launches += 2;
+  cudaMemcpyAsync(&S, d_set, sizeof(MaskSet), cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: operator scan failed");
+  return QP_OK;
+}
+
+// the flips of a scanned matrix (op = 0); false if the matrix is not a diagonal plus (conditional) uniform flips
+static bool bf_terms_from_set(const MaskSet& S, int64_t n, std::vector<BfTerm>& out, bool& has_diag) {
+  const bool pow2 = (n & (n - 1)) == 0;
+  has_diag = false;
+  if (S.bad || S.overflow) return false;
+  for (int t = 0; t < BF_SET_CAP; ++t) {
+    if (S.key[t] == 0ull) continue;
+    const uint32_t m = (uint32_t)(S.key[t] & 0xffffffffull);
+    if (m == 0u) {
+      has_diag = true;
+      continue;
+    }
+    // rows carrying the entry: all of them, or exactly the sub-cube (row AND cmask) == cval
+    uint32_t cmask = 0u, cval = 0u;
+    if ((int64_t)S.count[t] != n) {
+      if (!pow2) return false;
+      cmask = (S.ones[t] | S.zeros[t]) & (uint32_t)(n - 1);
+      cval = S.ones[t] & (uint32_t)(n - 1);
+      if ((int64_t)S.count[t] != (n >> __builtin_popcount(cmask))) return false;
+    }
+    BfTerm T;
+    T.mask = m;
+    T.cmask = cmask;
+    T.cval = cval;
+    memcpy(&T.val.x, &S.vre[t], 8);
+    memcpy(&T.val.y, &S.vim[t], 8);
+    T.op = 0;
+    out.push_back(T);
+  }
+  return true;
+}
+
+// sparse operators: every operator a diagonal plus (conditional) uniform flips
+static int32_t bf_collect_sparse(qp_gen_t g, qp_bitflip_s* B, MaskSet* d_set, int* d_flags, BfCollect& C, bool* ok) {
+  *ok = false;
+  qp_ctx_t ctx = g->ctx;
+  const int64_t n = g->n;
+  BitflipView& v = B->view;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  std::vector<MaskSet> h_set(1);
+  for (int l = 0; l < g->n_ops; ++l) {
+    qp_op_t op = g->ops[l];
+    if (op->dense || op->leftright) return QP_OK;
+    if (op->nnz == 0) continue;  // an all-zero operator contributes nothing
+    QP_CHECK(bf_scan_matrix(ctx, op->d_ptr, op->d_col, op->d_val, n, d_set, h_set[0]));
+    std::vector<BfTerm> flips;
+    bool has_diag = false;
+    if (!bf_terms_from_set(h_set[0], n, flips, has_diag)) return QP_OK;
+    for (BfTerm& T : flips) {
+      T.op = l;
+      if (T.val.y != 0.0) C.values_real = false;
+      C.terms.push_back(T);
+    }
+    if ((int)C.terms.size() > BF_MAX_TERMS + BF_MAX_LOW - 4) return QP_OK;
+    if (has_diag) {
+      if (v.n_diag >= BF_MAX_DIAG) return QP_OK;
+      double2* dc = nullptr;
+      double* dr = nullptr;
+      if (cudaMalloc(&dc, sizeof(double2) * n) != cudaSuccess || cudaMalloc(&dr, sizeof(double) * n) != cudaSuccess) {
+        cudaFree(dc);
+        return qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of a diagonal failed");
+      }
+      int h_flags[2] = {0, 0};
+      cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
+      k_bf_extract_diag<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n, dc, dr, d_flags);
+      ctx->launches++;
+      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaFree(dc);
+        cudaFree(dr);
+        return qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal extraction failed");
+      }
+      if (h_flags[1] == 0) {
+        cudaFree(dc);
+        B->owned.push_back(dr);
+        v.diag_r[v.n_diag] = dr;
+      } else {
+        cudaFree(dr);
+        B->owned.push_back(dc);
+        v.diag_c[v.n_diag] = dc;
+        C.diags_real = false;
+      }
+      v.diag_op[v.n_diag++] = l;
+    }
+  }
+  *ok = true;
+  return QP_OK;
+}
+
+// D[i + n j] += c * (dl ? dl[i] : 1) * (dr ? dr[j] : 1)
+__global__ void k_bf_outer_add(double2* __restrict__ D, const double2* __restrict__ dl, const double2* __restrict__ dr, double2 c,
+                               int64_t n) {
+  const int64_t total = n * n;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = r / n, i = r - j * n;
+    double2 t = c;
+    if (dl != nullptr) t = cmul2(t, dl[i]);
+    if (dr != nullptr) t = cmul2(t, dr[j]);
+    double2 d = D[r];
+    d.x += t.x;
+    d.y += t.y;
+    D[r] = d;
+  }
+}
+
+// Matrix-free left/right operators (qp_op_create_leftright): a term c P rho Q acts on the column-stacked index
+// i + n j as (Q^T (x) P).  If every factor is itself a diagonal plus (conditional) uniform flips on n rows, the
+// product is one on n^2 rows as long as no flip is multiplied by a NON-constant diagonal: flip x flip combines
+// masks and conditions, flip x (constant diagonal, e.g. the identity) scales the value, diagonal x diagonal is an
+// outer product added to the operator's diagonal vector.  This is the Liouvillian of config 4 WITHOUT ever building
+// the n^2 x n^2 matrices: H rho and rho H have the identity on the other side, sigma^- rho sigma^+ is flip x flip,
+// the anticommutator terms are diagonal.
+static int32_t bf_collect_lr(qp_gen_t g, qp_bitflip_s* B, MaskSet* d_set, int* d_flags, BfCollect& C, bool* ok) {
+  *ok = false;
+  qp_ctx_t ctx = g->ctx;
+  const int64_t nh = g->lr_n, N = g->n;
+  if (nh <= 0 || (nh & (nh - 1)) != 0 || nh * nh != N) return QP_OK;
+  int nb = 0;
+  while ((int64_t(1) << nb) < nh) ++nb;
+  BitflipView& v = B->view;
+  struct Factor {
+    bool ok = false, has_diag = false, diag_const = false;
+    double2 diag_c = {0.0, 0.0};
+    double2* d_diag = nullptr;  // device copy [nh] (nullptr: all ones)
+    std::vector<BfTerm> flips;
+  };
+  std::vector<std::pair<const void*, Factor>> cache;
+  std::vector<void*> temp;  // device arrays freed at the end
+  auto cleanup = [&](int32_t rc) {
+    for (void* p : temp) cudaFree(p);
+    return rc;
+  };
+  std::vector<MaskSet> h_set(1);
+  int32_t err = QP_OK;
+  auto analyse = [&](const uint32_t* ptr, const uint32_t* col, const double2* val) -> const Factor* {
+    for (auto& kv : cache)
+      if (kv.first == (const void*)ptr) return &kv.second;
+    Factor F;
+    if (ptr == nullptr) {  // identity
+      F.ok = F.has_diag = F.diag_const = true;
+      F.diag_c = make_double2(1.0, 0.0);
+    } else {
+      err = bf_scan_matrix(ctx, ptr, col, val, nh, d_set, h_set[0]);
+      if (err != QP_OK) return nullptr;
+      F.ok = bf_terms_from_set(h_set[0], nh, F.flips, F.has_diag);
+      if (F.ok && F.has_diag) {
+        double2* dc = nullptr;
+        double* dr = nullptr;
+        if (cudaMalloc(&dc, sizeof(double2) * nh) != cudaSuccess || cudaMalloc(&dr, sizeof(double) * nh) != cudaSuccess) {
+          cudaFree(dc);
+          err = qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed");
+          return nullptr;
+        }
+        temp.push_back(dc);
+        temp.push_back(dr);
+        cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
+        k_bf_extract_diag<<<(unsigned)((nh + 255) / 256), 256, 0, ctx->stream>>>(ptr, col, val, nh, dc, dr, d_flags);
+        ctx->launches++;
+        std::vector<double2> h((size_t)nh);
+        cudaMemcpyAsync(h.data(), dc, sizeof(double2) * nh, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+          err = qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal extraction failed");
+          return nullptr;
+        }
+        F.d_diag = dc;
+        F.diag_const = true;
+        for (int64_t i = 1; i < nh; ++i) F.diag_const = F.diag_const && h[i].x == h[0].x && h[i].y == h[0].y;
+        F.diag_c = h[0];
+      }
+    }
+    cache.emplace_back((const void*)ptr, F);
+    return &cache.back().second;
+  };
+  const unsigned oblocks = (unsigned)std::min<int64_t>((N + 255) / 256, (int64_t)ctx->sm_count * 16);
+  for (int l = 0; l < g->n_ops; ++l) {
+    qp_op_t op = g->ops[l];
+    if (!op->leftright) return cleanup(QP_OK);
+    struct Acc { uint32_t mask, cmask, cval; double2 val; };
+    std::vector<Acc> acc;
+    auto add = [&](uint32_t m, uint32_t cm, uint32_t cv, double2 val) {
+      for (Acc& a : acc)
+        if (a.mask == m && a.cmask == cm && a.cval == cv) {
+          a.val.x += val.x;
+          a.val.y += val.y;
+          return;
+        }
+      acc.push_back(Acc{m, cm, cv, val});
+    };
+    double2* D = nullptr;
+    for (const LRTermHost& T : op->lr_terms) {
+      const Factor* L = T.left ? analyse(T.left->d_ptr, T.left->d_col, T.left->d_val) : analyse(nullptr, nullptr, nullptr);
+      if (L == nullptr) return cleanup(err);
+      const Factor Lf = *L;  // the cache may reallocate
+      const Factor* R = analyse(T.d_rptr, T.d_rcol, T.d_rval);
+      if (R == nullptr) return cleanup(err);
+      const Factor Rf = *R;
+      if (!Lf.ok || !Rf.ok) return cleanup(QP_OK);
+      if (T.left && (T.left->dense || T.left->leftright)) return cleanup(QP_OK);
+      const double2 c = T.c;
+      auto mul = [](double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); };
+      if (Lf.has_diag && Rf.has_diag) {
+        if (D == nullptr) {
+          if (v.n_diag >= BF_MAX_DIAG) return cleanup(QP_OK);
+          if (cudaMalloc(&D, sizeof(double2) * N) != cudaSuccess) return cleanup(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of a diagonal failed"));
+          B->owned.push_back(D);
+          cudaMemsetAsync(D, 0, sizeof(double2) * N, ctx->stream);
+        }
+        k_bf_outer_add<<<oblocks, 256, 0, ctx->stream>>>(D, Lf.d_diag, Rf.d_diag, c, nh);
+        ctx->launches++;
+      }
+      for (const BfTerm& a : Lf.flips) {
+        if (Rf.has_diag) {
+          if (!Rf.diag_const) return cleanup(QP_OK);  // a flip times a row-dependent diagonal is not uniform
+          add(a.mask, a.cmask, a.cval, mul(c, mul(a.val, Rf.diag_c)));
+        }
+        for (const BfTerm& b : Rf.flips)
+          add(a.mask | (b.mask << nb), a.cmask | (b.cmask << nb), a.cval | (b.cval << nb), mul(c, mul(a.val, b.val)));
+      }
+      if (Lf.has_diag)
+        for (const BfTerm& b : Rf.flips) {
+          if (!Lf.diag_const) return cleanup(QP_OK);
+          add(b.mask << nb, b.cmask << nb, b.cval << nb, mul(c, mul(Lf.diag_c, b.val)));
+        }
+    }
+    for (const Acc& a : acc) {
+      if (a.val.x == 0.0 && a.val.y == 0.0) continue;
+      if (a.val.y != 0.0) C.values_real = false;
+      C.terms.push_back(BfTerm{a.mask, a.cmask, a.cval, a.val, l});
+    }
+    if ((int)C.terms.size() > BF_MAX_TERMS + BF_MAX_LOW - 4) return cleanup(QP_OK);
+    if (D != nullptr) {
+      v.diag_c[v.n_diag] = D;
+      v.diag_op[v.n_diag++] = l;
+      C.diags_real = false;
+    }
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return cleanup(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal assembly failed"));
+  *ok = true;
+  return cleanup(QP_OK);
+}
+
 // Tries to put the generator into bit-flip form.  *ok = false (nothing kept) if some operator is not a
 // diagonal plus (conditional) uniform bit flips.
 int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
@@ -248,7 +511,6 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
   qp_ctx_t ctx = g->ctx;
   const int64_t n = g->n;
   if (n % 32 != 0 || n < 64 || n >= (int64_t(1) << 32)) return QP_OK;
-  const bool pow2 = (n & (n - 1)) == 0;
   qp_bitflip_s* B = new qp_bitflip_s();
   BitflipView& v = B->view;
   memset(&v, 0, sizeof(v));
@@ -264,82 +526,19 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
   if (cudaMalloc(&d_flags, 2 * sizeof(int)) != cudaSuccess || cudaMalloc(&d_set, sizeof(MaskSet)) != cudaSuccess)
     return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc failed"));
   const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
-  bool values_real = true, diags_real = true;
-  struct Term { uint32_t mask, cmask, cval; double2 val; int op; };
-  std::vector<Term> terms;
-  std::vector<MaskSet> h_set(1);
-  for (int l = 0; l < g->n_ops; ++l) {
-    qp_op_t op = g->ops[l];
-    if (op->dense || op->leftright) return fail(QP_OK);
-    if (op->nnz == 0) continue;  // an all-zero operator contributes nothing
-    constexpr int ROWS_PER_BLOCK = 2048;
-    k_bf_set_init<<<1, 128, 0, ctx->stream>>>(d_set);
-    k_bf_scan<<<(unsigned)((n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n,
-                                                                                            ROWS_PER_BLOCK, d_set);
-    ctx->launches += 2;
-    cudaMemcpyAsync(h_set.data(), d_set, sizeof(MaskSet), cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: operator scan failed"));
-    const MaskSet& S = h_set[0];
-    if (S.bad || S.overflow) return fail(QP_OK);
-    bool has_diag = false;
-    for (int t = 0; t < BF_SET_CAP; ++t) {
-      if (S.key[t] == 0ull) continue;
-      const uint32_t m = (uint32_t)(S.key[t] & 0xffffffffull);
-      if (m == 0u) {
-        has_diag = true;
-        continue;
-      }
-      // rows carrying the entry: all of them, or exactly the sub-cube (row AND cmask) == cval
-      uint32_t cmask = 0u, cval = 0u;
-      if ((int64_t)S.count[t] != n) {
-        if (!pow2) return fail(QP_OK);
-        cmask = (S.ones[t] | S.zeros[t]) & (uint32_t)(n - 1);
-        cval = S.ones[t] & (uint32_t)(n - 1);
-        if ((int64_t)S.count[t] != (n >> __builtin_popcount(cmask))) return fail(QP_OK);
-      }
-      Term T;
-      T.mask = m;
-      T.cmask = cmask;
-      T.cval = cval;
-      memcpy(&T.val.x, &S.vre[t], 8);
-      memcpy(&T.val.y, &S.vim[t], 8);
-      T.op = l;
-      if (T.val.y != 0.0) values_real = false;
-      if (cmask != 0u) B->cond = true;
-      terms.push_back(T);
-      if ((int)terms.size() > BF_MAX_TERMS + BF_MAX_LOW - 4) return fail(QP_OK);
-    }
-    if (has_diag) {
-      if (v.n_diag >= BF_MAX_DIAG) return fail(QP_OK);
-      double2* dc = nullptr;
-      double* dr = nullptr;
-      if (cudaMalloc(&dc, sizeof(double2) * n) != cudaSuccess || cudaMalloc(&dr, sizeof(double) * n) != cudaSuccess) {
-        cudaFree(dc);
-        return fail(qp_fail(ctx, QP_ERR_OOM, "bit-flip form: cudaMalloc of a diagonal failed"));
-      }
-      int h_flags[2] = {0, 0};
-      cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream);
-      k_bf_extract_diag<<<blocks, 256, 0, ctx->stream>>>(op->d_ptr, op->d_col, op->d_val, n, dc, dr, d_flags);
-      ctx->launches++;
-      cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream);
-      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-        cudaFree(dc);
-        cudaFree(dr);
-        return fail(qp_fail(ctx, QP_ERR_CUDA, "bit-flip form: diagonal extraction failed"));
-      }
-      if (h_flags[1] == 0) {
-        cudaFree(dc);
-        B->owned.push_back(dr);
-        v.diag_r[v.n_diag] = dr;
-      } else {
-        cudaFree(dr);
-        B->owned.push_back(dc);
-        v.diag_c[v.n_diag] = dc;
-        diags_real = false;
-      }
-      v.diag_op[v.n_diag++] = l;
-    }
+  BfCollect C;
+  bool collected = false;
+  {
+    bool any_lr = false;
+    for (int l = 0; l < g->n_ops; ++l) any_lr = any_lr || g->ops[l]->leftright;
+    const int32_t rc = any_lr ? bf_collect_lr(g, B, d_set, d_flags, C, &collected) : bf_collect_sparse(g, B, d_set, d_flags, C, &collected);
+    if (rc != QP_OK || !collected) return fail(rc);
   }
+  std::vector<BfTerm>& terms = C.terms;
+  for (const BfTerm& t : terms)
+    if (t.cmask != 0u) B->cond = true;
+  const bool values_real = C.values_real, diags_real = C.diags_real;
+  typedef BfTerm Term;
   cudaFree(d_set);
   d_set = nullptr;
   if (terms.empty()) return fail(QP_OK);  // purely diagonal generators gain nothing here

@@ -869,7 +869,7 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
   }
   if (any_lr && !all_lr)
     return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: mixing matrix-free (left/right) operators and matrices is not supported");
-  if ((format == QP_FORMAT_LR) != all_lr && !(all_lr && format == QP_FORMAT_AUTO))
+  if ((format == QP_FORMAT_LR) != all_lr && !(all_lr && (format == QP_FORMAT_AUTO || format == QP_FORMAT_BITFLIP)))
     return qp_fail(ctx, QP_ERR_INVALID_ARG, "qp_gen_create: QP_FORMAT_LR is the format of left/right operators (and only theirs)");
   if (any_dense && !all_dense)
     return qp_fail(ctx, QP_ERR_UNSUPPORTED, "qp_gen_create: mixing dense and sparse operators is not supported");
@@ -932,6 +932,21 @@ extern "C" int32_t qp_gen_create(qp_ctx_t ctx, int32_t n_ops, const qp_op_t* ops
     G_CUDA(cudaMemcpy(g->d_lr_terms, h.data(), sizeof(LRTerm) * h.size(), cudaMemcpyHostToDevice));
     g->stored_entries = g->nnz_total;
     g->stored_bytes = g->matrix_bytes;
+    // factors that are diagonals + (conditional) bit flips: the n^2 x n^2 operator has the bit-flip form too
+    // (bitflip.cu), without ever being built -- thread-per-row kernel instead of the generic factor walk
+    if ((format == QP_FORMAT_AUTO && g->n >= (int64_t)ctx->sm_count * 1024 && !getenv("QPROP_NO_BITFLIP")) || format == QP_FORMAT_BITFLIP) {
+      bool bitflip_ok = false;
+      int32_t rc = qp_bitflip_build(g, &bitflip_ok);
+      if (rc == QP_OK && format == QP_FORMAT_BITFLIP && !bitflip_ok)
+        rc = qp_fail(ctx, QP_ERR_UNSUPPORTED,
+                     "qp_gen_create: QP_FORMAT_BITFLIP needs left/right factors that are diagonals plus uniform bit flips, no flip "
+                     "multiplied by a non-constant diagonal, n a power of two");
+      if (rc != QP_OK) return bail(rc);
+      if (bitflip_ok) {
+        g->format = QP_FORMAT_BITFLIP;
+        g->stored_bytes = qp_bitflip_stored_bytes(g->bitflip);
+      }
+    }
     *out = g;
     return QP_OK;
   }
@@ -1362,6 +1377,10 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   qp_ctx_t ctx = gen->ctx;
   const int64_t n = gen->n;
   cudaStream_t st = ctx->stream;
+  if (gen->format == QP_FORMAT_BITFLIP && gen->d_mptr == nullptr) {  // derived from matrix-free left/right operators
+    if (batch != 1) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "matrix-free left/right generators take single states (batch = %lld)", (long long)batch);
+    return qp_launch_bitflip(gen, EPI, x, e);
+  }
   if (gen->format == QP_FORMAT_LR) {
     if (batch != 1) return qp_fail(ctx, QP_ERR_UNSUPPORTED, "matrix-free left/right generators take single states (batch = %lld)", (long long)batch);
     // CTA = 256 rows of rho x a range of columns swept JB at a time; enough column ranges to fill

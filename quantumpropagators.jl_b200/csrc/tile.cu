@@ -705,7 +705,7 @@ static int32_t tile_launch_nops(qp_gen_t gen, int coef_stride, const double2* x,
 int32_t qp_launch_tile(qp_gen_t gen, int epi, int coef_stride, const double2* x, int64_t batch, const EpiArgs& e,
                        bool* handled) {
   *handled = false;
-  if (batch < 32 || batch % 32 != 0 || gen->format == QP_FORMAT_DENSE || gen->format == QP_FORMAT_LR) return QP_OK;
+  if (batch < 32 || batch % 32 != 0 || gen->format == QP_FORMAT_DENSE || gen->format == QP_FORMAT_LR || gen->d_mptr == nullptr) return QP_OK;
   QP_CHECK(tile_ensure(gen));
   if (!gen->tile->ok) return QP_OK;
   *handled = true;
@@ -741,7 +741,7 @@ int32_t qp_tile_info(qp_gen_t gen, int32_t* available, int32_t* S, int32_t* NH, 
 extern "C" int32_t qp_gen_tile_info(qp_gen_t gen, int32_t* available, int32_t* split, int32_t* blocks, int32_t* n_table,
                                     int64_t* entries) {
   if (!gen) return qp_fail(nullptr, QP_ERR_INVALID_ARG, "qp_gen_tile_info: null generator");
-  if (gen->format == QP_FORMAT_DENSE || gen->format == QP_FORMAT_LR) {
+  if (gen->format == QP_FORMAT_DENSE || gen->format == QP_FORMAT_LR || gen->d_mptr == nullptr) {
     if (available) *available = 0;
     return QP_OK;
   }

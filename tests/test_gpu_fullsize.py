@@ -279,6 +279,14 @@ def test_config4_full_size_explicit_vs_matrix_free_and_oracle(qp, ctx):
     f1 = qp.prop_step(pf).to_host()
     f2 = qp.prop_step(pf).to_host()
     assert rel(f1, step1) < RTOL and rel(f2, step2) < RTOL and rel(f1, ref1) < RTOL
+    # both of the above run on the bit-flip form (detected from the explicit matrices / composed from the
+    # factors); the generic matrix-free kernel is the independent third path
+    assert pf.wrk.krylov.gen.format == "bitflip"
+    del pf
+    pl = qp.init_prop(wf["psi0"], Gf, wf["tlist"], "newton", ctx=ctx, m_max=10, relerr=1e-12, matrix_format="leftright")
+    assert pl.wrk.krylov.gen.format == "leftright"
+    l1 = qp.prop_step(pl).to_host()
+    assert rel(l1, ref1) < RTOL and rel(l1, f1) < RTOL
     rho = f2.reshape(4096, 4096, order="F")
     assert abs(np.trace(rho) - 1) < 1e-10
 

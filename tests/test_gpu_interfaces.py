@@ -321,3 +321,72 @@ def test_propagate_with_shaped_amplitude(qp, ctx):
     assert np.linalg.norm(out_amp - out_fun) < 1e-13
     st = qp.DeviceState.from_host(ctx, w["psi0"])
     assert qp.check_generator(G_amp, state=st, tlist=w["tlist"], for_time_continuous=True)
+
+
+@pytest.mark.parametrize("n_spins", [4, 5])
+def test_liouvillian_matrix_free_bitflip_form(qp, ctx, n_spins):
+    """The factors of the matrix-free Liouvillian (H = diagonal + bit flips on the left or right of rho, the
+    decay channels sigma^- rho sigma^+ as conditional flips on both sides, the anticommutators as diagonals) compose
+    to the bit-flip form on n^2 rows without the n^2 x n^2 matrices: the library detects it (forced here, AUTO
+    from N >= 148 * 1024), and application and Newton propagation agree with the generic matrix-free kernel, with
+    the explicit super-operators and with the oracle."""
+    H0, H1, _ = qp.workloads.tfim_chain(n_spins)
+    nh = 1 << n_spins
+    sm = sp.csr_matrix(np.array([[0, 1], [0, 0]], dtype=complex))
+    c_ops = []
+    for k in range(n_spins):
+        left = sp.identity(1 << (n_spins - 1 - k), dtype=complex, format="csr")
+        right = sp.identity(1 << k, dtype=complex, format="csr")
+        c_ops.append(np.sqrt(0.05) * sp.kron(sp.kron(left, sm), right, format="csr"))
+    tlist = np.linspace(0.0, 0.4, 9)
+
+    def u1(t):
+        return float(np.sin(np.pi * t / 0.4) ** 2)
+
+    Lf = qp.liouvillian((H0, (H1, u1)), c_ops, convention="TDSE", matrix_free=True)
+    Lm = qp.liouvillian((H0, (H1, u1)), c_ops, convention="TDSE")
+    rng = np.random.default_rng(n_spins)
+    x = rand_state(rng, nh * nh)
+    dx = qp.DeviceState.from_host(ctx, x)
+    got = {}
+    for fmt in ("bitflip", "leftright"):
+        gen = qp.DeviceGenerator(ctx, list(Lf.ops), 1, fmt)
+        assert gen.format == fmt
+        dy = qp.DeviceState(ctx, nh * nh).zero()
+        gen.mul(dy, dx, [0.37], 1.0, 0.0)
+        got[fmt] = dy.to_host()
+    want = (Lm.ops[0] + 0.37 * Lm.ops[1]) @ x
+    assert np.linalg.norm(got["bitflip"] - want) / np.linalg.norm(want) < 1e-13
+    assert np.linalg.norm(got["bitflip"] - got["leftright"]) / np.linalg.norm(want) < 1e-13
+    psi = rand_state(rng, nh)
+    rho0 = np.outer(psi, psi.conj()).reshape(-1, order="F")
+    out_b = qp.propagate(rho0, Lf, tlist, "newton", ctx=ctx, matrix_format="bitflip")
+    ref = O.propagate(rho0, O.hamiltonian(Lm.ops[0], (Lm.ops[1], u1)), tlist, "newton")
+    assert np.linalg.norm(out_b - ref) / np.linalg.norm(ref) < 1e-10
+
+
+def test_leftright_bitflip_refuses_flip_times_varying_diagonal(qp, ctx):
+    """A flip on one side multiplied by a NON-constant diagonal on the other side is row dependent: not a
+    bit-flip operator (forced format: error; AUTO keeps the generic matrix-free kernel)."""
+    n = 16
+    rows = np.arange(n)
+    X = sp.csr_matrix((np.ones(n, dtype=complex), (rows, rows ^ 2)), shape=(n, n))
+    D = sp.diags(np.arange(1, n + 1).astype(complex)).tocsr()
+    op = qp.LeftRightOperator(n, [(X, D, 1.0)])
+    with pytest.raises(qp.QPropError):
+        qp.DeviceGenerator(ctx, [op], 0, "bitflip")
+    gen = qp.DeviceGenerator(ctx, [op], 0)
+    assert gen.format == "leftright"
+    rng = np.random.default_rng(3)
+    rho = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    dy = qp.DeviceState(ctx, n * n).zero()
+    gen.mul(dy, qp.DeviceState.from_host(ctx, rho.reshape(-1, order="F")), [], 1.0, 0.0)
+    want = (X @ rho @ D).reshape(-1, order="F")
+    assert np.linalg.norm(dy.to_host() - want) / np.linalg.norm(want) < 1e-13
+    # constant diagonal on the other side (a multiple of the identity): fine
+    op2 = qp.LeftRightOperator(n, [(X, 2.5 * sp.identity(n, dtype=complex, format="csr"), 1.0), (D, D, 0.5j)])
+    gen2 = qp.DeviceGenerator(ctx, [op2], 0, "bitflip")
+    assert gen2.format == "bitflip"
+    gen2.mul(dy, qp.DeviceState.from_host(ctx, rho.reshape(-1, order="F")), [], 1.0, 0.0)
+    want2 = (2.5 * X @ rho + 0.5j * D @ rho @ D).reshape(-1, order="F")
+    assert np.linalg.norm(dy.to_host() - want2) / np.linalg.norm(want2) < 1e-13
