@@ -118,7 +118,8 @@ int32_t qp_op_upload_dense(qp_ctx_t ctx, int64_t n, const qp_c128* colmajor, qp_
  *     1 (x) H  = (H, NULL),   H^T (x) 1 = (NULL, H),   (A^+)^T (x) A = (A, A^+),
  * so a Liouvillian of an n-dimensional system costs O(nnz(H)) memory instead of O(n * nnz(H)).
  * The result is an operator of dimension n^2; a generator is either made of such operators only
- * (format QP_FORMAT_LR, single states) or of matrices only.  `left` / `right` must be sparse
+ * (format QP_FORMAT_LR -- or QP_FORMAT_BITFLIP when the factors are diagonals plus bit flips that compose,
+ * which QP_FORMAT_AUTO detects -- single states) or of matrices only.  `left` / `right` must be sparse
  * operators of this context and outlive the new operator. */
 int32_t qp_op_create_leftright(qp_ctx_t ctx, int64_t n, int32_t n_terms, const qp_op_t* left,
                                const qp_op_t* right, const qp_c128* coeffs, qp_op_t* op);
