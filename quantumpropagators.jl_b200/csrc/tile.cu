@@ -38,6 +38,9 @@ using qptile::N_KINDS;
 #ifndef TILE_LEAN
 #define TILE_LEAN 1
 #endif
+#ifndef TILE_O_EARLY
+#define TILE_O_EARLY 1
+#endif
 constexpr int TILE_THREADS = TILE_THREADS_N;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 constexpr int TILE_RING = 3;
@@ -295,7 +298,7 @@ __device__ __forceinline__ void tile_rows(const TileView& tv, const ConstTab& ct
     uint4 ow = make_uint4(0u, 0u, 0u, 0u);
     Tab16 o_lo[2];
     double2 o_hi[2], o_x[2];
-    if (PASS == 1 && nw[5] > 0) {
+    if (TILE_O_EARLY && PASS == 1 && nw[5] > 0) {
       ow = lds_u32x4(cw + w0[5]);
       if (ow.x != 0u) {
 #pragma unroll
@@ -312,7 +315,9 @@ __device__ __forceinline__ void tile_rows(const TileView& tv, const ConstTab& ct
     if (NOPS > 2) tile_list<NOPS, 0, (NOPS > 2 ? 2 : 0), CT>(ctab, cw + w0[2], nw[2], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
     if (NOPS > 1) tile_list<NOPS, 1, 0, CT>(ctab, cw + w0[3], nw[3], ra.tab16_base, xs_row, xg_row, batch, pr, pi);
     tile_list<NOPS, 2, 0, CT>(ctab, cw + w0[4], nw[4], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
-    if (PASS == 1) {  // class O: the few couplings that straddle the split, from global memory
+    if (PASS == 1 && !TILE_O_EARLY) {
+      if (nw[5] > 0) tile_list<NOPS, 3, 0, CT>(ctab, cw + w0[5], nw[5], ra.tab32_base, xs_row, xg_row, batch, pr, pi);
+    } else if (PASS == 1) {  // class O: the few couplings that straddle the split, from global memory
       if (ow.x != 0u) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
