@@ -184,7 +184,8 @@ def init_prop(
     Cheby keywords: control_ranges, specrange_method, specrange_buffer, cheby_coeffs_limit,
     check_normalization, uniform_dt_tolerance + specrange kwargs (E_min, E_max, rng, ...).
     Newton keywords: m_max, func, norm_min, relerr, max_restarts.
-    Engine keyword: matrix_format in {"auto", "csr", "sell"} (device storage of the operators).
+    Engine keyword: matrix_format in {"auto", "csr", "sell", "selld", "bitflip", "dense", "leftright"} -- the device
+    storage of the operators (include/qprop.h: QP_FORMAT_*); "auto" picks the fastest one the operators allow.
     """
     name = _method_name(method)
     if name not in ("cheby", "newton"):
