@@ -28,6 +28,22 @@ struct ColCtl {
   double inv;    // 1 / |w|, used by the normalisation kernel
   double again;  // != 0: the DGKS criterion asks for a second projection round
 };
+// factor of the stored Krylov vector idx (ctl_base == nullptr: vectors are stored normalised)
+__device__ __forceinline__ double krylov_scale(const ColCtl* ctl_base, int idx) {
+  return (ctl_base == nullptr || idx == 0) ? 1.0 : ctl_base[idx - 1].inv;
+}
+
+
+// Lazy normalisation (single states; QPROP_KRYLOV_EAGER=1 restores the separate pass): a new Krylov vector is
+// NOT rescaled after its orthogonalisation -- a read-modify-write pass over the vector, 6 % of a Newton step on
+// config 4 -- but stored as it is, and its factor 1 / |w| (ColCtl::inv, still on the device) is applied where
+// the vector is used: as a device-side factor of alpha in the next application of the generator, to the dot
+// products and projection coefficients of the later columns (below), and by the host to the weights of
+// qp_krylov_combine and to the copy of qp_krylov_get.  q[0] and vectors set by qp_krylov_set have factor 1.
+static bool krylov_lazy() {
+  static const int eager = getenv("QPROP_KRYLOV_EAGER") ? atoi(getenv("QPROP_KRYLOV_EAGER")) : 0;
+  return !eager;
+}
 
 // partial[block][KV+1][2]: <q_i|w> for i < nv and |w|^2 in slot KV.  `gate` (or nullptr): the
 // launch is a no-op unless *gate != 0 (second Gram-Schmidt round, decided on the device).
@@ -81,7 +97,7 @@ k_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __rest
 // h[i] (+)= <q_i|w> ; slot 2 KV -> ctl->ww (first pass of the first round only)
 __global__ void __launch_bounds__(32 * (2 * KV + 1))
 k_multidot_final(const double* __restrict__ partial, int nblocks, int nv, double2* __restrict__ h, int accumulate,
-                 ColCtl* __restrict__ ctl, int write_ww, const double* __restrict__ gate) {
+                 ColCtl* __restrict__ ctl, int write_ww, const double* __restrict__ gate, const ColCtl* ctl_base, int i0) {
   pdl_sync();
   if (gate != nullptr && *gate == 0.0) return;
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,6 +110,7 @@ k_multidot_final(const double* __restrict__ partial, int nblocks, int nv, double
   if (is_ww) {
     if (write_ww) ctl->ww = t;
   } else {
+    t *= krylov_scale(ctl_base, i0 + (slot >> 1));  // <q_i|w> with q_i = scale_i * (stored vector)
     double* dst = reinterpret_cast<double*>(h + (slot >> 1)) + (slot & 1);
     *dst = accumulate ? *dst + t : t;
   }
@@ -104,12 +121,16 @@ k_multidot_final(const double* __restrict__ partial, int nblocks, int nv, double
 template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h,
-              double2* __restrict__ w, int64_t n, double* __restrict__ partial, const double* __restrict__ gate) {
+              double2* __restrict__ w, int64_t n, double* __restrict__ partial, const double* __restrict__ gate,
+              const ColCtl* ctl_base, int i0) {
   pdl_sync();
   if (gate != nullptr && *gate == 0.0) return;
   double2 hv[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) hv[i] = h[i];
+  for (int i = 0; i < NV; ++i) {
+    const double sc = krylov_scale(ctl_base, i0 + i);
+    hv[i] = make_double2(sc * h[i].x, sc * h[i].y);
+  }
   double nn = 0.0;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     double2 wv = w[r];
@@ -141,13 +162,14 @@ k_project_out(const double2* __restrict__ q0, int64_t stride, const double2* __r
 template <int NV>
 __global__ void __launch_bounds__(KBLOCK)
 k_project_multidot(const double2* __restrict__ q0, int64_t stride, const double2* __restrict__ h, double2* __restrict__ w,
-                   int64_t n, double* __restrict__ dots, double* __restrict__ norms) {
+                   int64_t n, double* __restrict__ dots, double* __restrict__ norms, const ColCtl* ctl_base) {
   pdl_sync();
   double2 hv[NV];
   double sr[NV], si[NV], nn = 0.0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    hv[i] = h[i];
+    const double sc = krylov_scale(ctl_base, i);
+    hv[i] = make_double2(sc * h[i].x, sc * h[i].y);
     sr[i] = si[i] = 0.0;
   }
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
@@ -486,6 +508,7 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
   double2* h_acc = K->d_hall + (size_t)j * (K->m_max + 2);
   double2* h_corr = K->d_h;  // this round's coefficients
   ColCtl* ctl = K->d_ctl + j;
+  const ColCtl* ctl_base = krylov_lazy() ? K->d_ctl : nullptr;
   static const double eta = getenv("QPROP_DGKS_ETA") ? atof(getenv("QPROP_DGKS_ETA")) : 0.70710678118654752;
   const double eta2 = eta * eta;
   static const int unfused = getenv("QPROP_GS_UNFUSED") ? atoi(getenv("QPROP_GS_UNFUSED")) : 0;
@@ -497,15 +520,16 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
     DISPATCH_NV(nvec, (qp_launch_pdl(k_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, w, n, partial, (const double*)nullptr)));
     QP_LAUNCHED(ctx);
     qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nvec, h_acc, 0, ctl, 1,
-                  (const double*)nullptr);
+                  (const double*)nullptr, ctl_base, 0);
     QP_LAUNCHED(ctx);
-    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_acc, w, n, partial, norms)));
+    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_acc, w, n, partial, norms, ctl_base)));
     QP_LAUNCHED(ctx);
     qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, norms, nblocks, ctl, 1, h_acc, h_corr, nvec, norm_min, eta2);
     QP_LAUNCHED(ctx);
-    qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nvec, h_corr, 0, ctl, 0, gate);
+    qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nvec, h_corr, 0, ctl, 0, gate,
+                  ctl_base, 0);
     QP_LAUNCHED(ctx);
-    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_corr, w, n, norms, gate)));
+    DISPATCH_NV(nvec, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, K->q, n, h_corr, w, n, norms, gate, ctl_base, 0)));
     QP_LAUNCHED(ctx);
     qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, norms, nblocks, ctl, 2, h_acc, h_corr, nvec, norm_min, eta2);
     QP_LAUNCHED(ctx);
@@ -520,13 +544,13 @@ static int32_t orthogonalise_async(qp_krylov_t K, int j, double norm_min) {
       DISPATCH_NV(nv, (qp_launch_pdl(k_multidot<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, w, n, partial, gate)));
       QP_LAUNCHED(ctx);
       qp_launch_pdl(k_multidot_final, dim3(1), dim3(32 * (2 * KV + 1)), 0, ctx->stream, partial, nblocks, nv, h + i0, 0, ctl,
-                    (round == 1 && i0 == 0) ? 1 : 0, gate);
+                    (round == 1 && i0 == 0) ? 1 : 0, gate, ctl_base, i0);
       QP_LAUNCHED(ctx);
     }
     for (int i0 = 0; i0 < nvec; i0 += KV) {
       const int nv = std::min(KV, nvec - i0);
       const double2* q0 = K->q + (size_t)i0 * n;
-      DISPATCH_NV(nv, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, h + i0, w, n, partial, gate)));
+      DISPATCH_NV(nv, (qp_launch_pdl(k_project_out<NV>, dim3(nblocks), dim3(KBLOCK), 0, ctx->stream, q0, n, h + i0, w, n, partial, gate, ctl_base, i0)));
       QP_LAUNCHED(ctx);
     }
     qp_launch_pdl(k_norm_decide, dim3(1), dim3(32), 0, ctx->stream, partial, nblocks, ctl, round, h_acc, h_corr, nvec, norm_min, eta2);
@@ -549,8 +573,10 @@ static int32_t fetch_columns(qp_krylov_t K, int j0, int j1, std::vector<double2>
 
 static int32_t krylov_matvec(qp_krylov_t K, int stride, int j) {
   // q[j+1] = H q[j]   ("matrix-vector product", src/arnoldi.jl:81-83)
-  return qp_gen_apply(K->gen, stride, make_double2(1.0, 0.0), make_double2(0.0, 0.0),
-                      K->q + (size_t)j * K->n, K->q + (size_t)(j + 1) * K->n, 1);
+  // lazy normalisation: q[j] is stored unnormalised, its factor multiplies alpha on the device
+  const double* alpha_dev = (krylov_lazy() && j > 0) ? &K->d_ctl[j - 1].inv : nullptr;
+  return qp_gen_apply_scaled(K->gen, stride, make_double2(1.0, 0.0), alpha_dev, make_double2(0.0, 0.0),
+                             K->q + (size_t)j * K->n, K->q + (size_t)(j + 1) * K->n, 1);
 }
 
 extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_t v, int32_t m, double dt,
@@ -578,7 +604,7 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
   for (int j = 0; j < m; ++j) {
     QP_CHECK(krylov_matvec(K, stride, j));
     QP_CHECK(orthogonalise_async(K, j, norm_min));
-    if (j + 1 < m || extended) {  // :88-97
+    if (!krylov_lazy() && (j + 1 < m || extended)) {  // :88-97
       qp_launch_pdl(k_scale_dev, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(j + 1) * n, K->d_ctl + j, n);
       QP_LAUNCHED(ctx);
     }
@@ -587,6 +613,10 @@ extern "C" int32_t qp_arnoldi(qp_krylov_t K, const qp_c128* op_coeffs, qp_state_
   std::vector<ColCtl> ctl;
   QP_CHECK(fetch_columns(K, 0, m, h_all, ctl));
   const size_t ldh = (size_t)K->m_max + 2;
+  K->h_scale.assign((size_t)K->m_max + 2, 1.0);
+  if (krylov_lazy())  // the last vector of a non-extended run stays unnormalised, as in the reference (:88-97)
+    for (int j = 0; j < m; ++j)
+      if (j + 1 < m || extended) K->h_scale[(size_t)j + 1] = ctl[j].inv;
   int m_eff = m;
   for (int j = 0; j < m; ++j) {
     for (int i = 0; i <= j; ++i) {  // Hess[i,j] = dt <q_i|q_{j+1}>   :85
@@ -626,8 +656,13 @@ extern "C" int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, in
   QP_CHECK(qp_gen_set_coeffs(K->gen, op_coeffs, 0, 1, &stride));
   hess[(size_t)(m - 2) * ld + (m - 1)].re = dt * hn;  // Hess[m, m-1]
   hess[(size_t)(m - 2) * ld + (m - 1)].im = 0.0;
-  qp_launch_pdl(k_scale_real, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
-  QP_LAUNCHED(ctx);
+  if (krylov_lazy()) {  // the factor 1 / hn is already in d_ctl[m - 2].inv (written when the column was orthogonalised)
+    if (K->h_scale.size() < (size_t)K->m_max + 2) K->h_scale.assign((size_t)K->m_max + 2, 1.0);
+    K->h_scale[(size_t)m - 1] = 1.0 / hn;
+  } else {
+    qp_launch_pdl(k_scale_real, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, K->q + (size_t)(m - 1) * n, 1.0 / hn, n);
+    QP_LAUNCHED(ctx);
+  }
   QP_CHECK(krylov_matvec(K, stride, m - 1));
   QP_CHECK(orthogonalise_async(K, m - 1, norm_min));
   std::vector<double2> h_all;
@@ -662,7 +697,11 @@ extern "C" int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* wts, int32_t 
     const int nv = std::min(KV, n_w - i0);
     Weights wt;
     memset(&wt, 0, sizeof(wt));
-    for (int i = 0; i < nv; ++i) wt.w[i] = make_double2(wts[i0 + i].re, wts[i0 + i].im);
+    for (int i = 0; i < nv; ++i) {
+      const size_t idx = (size_t)(first + i0 + i);
+      const double sc = (krylov_lazy() && idx < K->h_scale.size()) ? K->h_scale[idx] : 1.0;
+      wt.w[i] = make_double2(sc * wts[i0 + i].re, sc * wts[i0 + i].im);
+    }
     const double2* q0 = K->q + (size_t)(first + i0) * n;
     const int acc = (accumulate || i0 > 0) ? 1 : 0;
     DISPATCH_NV(nv, (qp_launch_pdl(k_combine<NV>, dim3(kgrid(ctx, n)), dim3(KBLOCK), 0, ctx->stream, q0, n, wt, st->d, n, acc)));
@@ -679,6 +718,10 @@ extern "C" int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst) {
   QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_get: index %d out of range", index);
   const size_t vec = (size_t)K->n * (size_t)K->batch;
   QP_CUDA(ctx, cudaMemcpyAsync(dst->d, K->q + (size_t)index * vec, sizeof(double2) * vec, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (K->batch == 1 && krylov_lazy() && (size_t)index < K->h_scale.size() && K->h_scale[(size_t)index] != 1.0) {
+    qp_launch_pdl(k_scale_real, dim3(kgrid(ctx, K->n)), dim3(KBLOCK), 0, ctx->stream, dst->d, K->h_scale[(size_t)index], K->n);
+    QP_LAUNCHED(ctx);
+  }
   return QP_OK;
 }
 
@@ -690,5 +733,14 @@ extern "C" int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src) {
   QP_REQUIRE(ctx, index >= 0 && index <= K->m_max, "qp_krylov_set: index %d out of range", index);
   const size_t vec = (size_t)K->n * (size_t)K->batch;
   QP_CUDA(ctx, cudaMemcpyAsync(K->q + (size_t)index * vec, src->d, sizeof(double2) * vec, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (K->batch == 1 && krylov_lazy()) {  // a vector that comes from outside carries no pending factor
+    if (K->h_scale.size() < (size_t)K->m_max + 2) K->h_scale.assign((size_t)K->m_max + 2, 1.0);
+    K->h_scale[(size_t)index] = 1.0;
+    if (index > 0) {
+      const double one = 1.0;
+      QP_CUDA(ctx, cudaMemcpyAsync(&K->d_ctl[index - 1].inv, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   return QP_OK;
 }

@@ -242,6 +242,9 @@ struct qp_krylov_s {
   int last_n_a = 0, last_n_leja = 0;
   double last_radius = 0.0;
   std::vector<qp_c128> last_a, last_leja;
+  // lazy normalisation (single states): q[i] is stored UNNORMALISED, its factor is h_scale[i] on the host and
+  // d_ctl[i - 1].inv on the device (q[0]: 1); krylov.cu
+  std::vector<double> h_scale;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -334,6 +337,9 @@ int32_t qp_gen_set_coeffs(qp_gen_t gen, const qp_c128* op_coeffs, int per_traj, 
                           int* coef_stride_out);
 
 // y <- beta*y + alpha*H x using the coefficients currently in gen->d_coef
+// y <- beta y + alpha * (*alpha_dev) * H x : alpha_dev (or nullptr) is a real factor in device memory
+int32_t qp_gen_apply_scaled(qp_gen_t gen, int coef_stride, double2 alpha, const double* alpha_dev, double2 beta, const double2* x,
+                            double2* y, int64_t batch);
 int32_t qp_gen_apply(qp_gen_t gen, int coef_stride, double2 alpha, double2 beta, const double2* x,
                      double2* y, int64_t batch);
 

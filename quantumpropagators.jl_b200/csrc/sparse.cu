@@ -1540,14 +1540,20 @@ int32_t qp_launch_fused(qp_gen_t gen, int epi, int coef_stride, const double2* x
   return qp_fail(gen->ctx, QP_ERR_INTERNAL, "bad epilogue %d", epi);
 }
 
-int32_t qp_gen_apply(qp_gen_t gen, int coef_stride, double2 alpha, double2 beta, const double2* x,
-                     double2* y, int64_t batch) {
+int32_t qp_gen_apply_scaled(qp_gen_t gen, int coef_stride, double2 alpha, const double* alpha_dev, double2 beta, const double2* x,
+                            double2* y, int64_t batch) {
   EpiArgs e;
   memset(&e, 0, sizeof(e));
   e.alpha = alpha;
+  e.alpha_dev = alpha_dev;
   e.betac = beta;
   e.y = y;
   return qp_launch_fused(gen, EPI_MUL, coef_stride, x, batch, e);
+}
+
+int32_t qp_gen_apply(qp_gen_t gen, int coef_stride, double2 alpha, double2 beta, const double2* x,
+                     double2* y, int64_t batch) {
+  return qp_gen_apply_scaled(gen, coef_stride, alpha, nullptr, beta, x, y, batch);
 }
 
 static int32_t check_gen_state(qp_gen_t gen, qp_state_t x, qp_state_t y, const char* what) {

@@ -38,6 +38,8 @@ __host__ __device__ constexpr bool epi_has_sums(int epi) {
 
 struct EpiArgs {
   double2 alpha, betac;  // EPI_MUL
+  const double* alpha_dev;  // EPI_MUL: alpha is multiplied by *alpha_dev (a real scale factor that is still on the
+                            // device: the pending normalisation of a Krylov vector, krylov.cu); nullptr = 1
   double2 c;             // Chebyshev prefactor (c for the first term, 2c afterwards)
   double beta;           // Chebyshev shift  Delta/2 + E_min
   double a0, ak;         // coefficients a_1 (FIRST/ONLY) and a_k
@@ -138,6 +140,12 @@ __device__ __forceinline__ void epi_apply(const EpiArgs& e, int64_t idx, double2
                                           double2 av, double& chk_dr, double& chk_di, double& chk_n) {
   if (EPI == EPI_MUL) {
     double2 r = cmul2(e.alpha, hx);
+    if (e.alpha_dev != nullptr) {  // written by the previous kernel of the stream: a coherent load, after the PDL wait
+      double sc;
+      asm volatile("ld.global.f64 %0, [%1];" : "=d"(sc) : "l"(e.alpha_dev) : "memory");
+      r.x *= sc;
+      r.y *= sc;
+    }
     if (e.betac.x != 0.0 || e.betac.y != 0.0) {
       const double2 t = cmul2(e.betac, yv);
       r.x += t.x;
