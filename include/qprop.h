@@ -258,7 +258,9 @@ int32_t qp_arnoldi_extend(qp_krylov_t K, const qp_c128* op_coeffs, int32_t m, do
 /* st <- (accumulate ? st : 0) + sum_{i<n_w} w[i] q_{first+i}   (src/newton.jl:346-352) */
 int32_t qp_krylov_combine(qp_krylov_t K, const qp_c128* w, int32_t first, int32_t n_w,
                           qp_state_t st, int32_t accumulate);
-/* copy Krylov vector q_{index} (0-based) to/from a state */
+/* copy Krylov vector q_{index} (0-based) to/from a state.  (Single states: the workspace keeps a new vector
+ * unnormalised and its factor 1/|w| apart -- applied wherever the vector is used -- so that no rescaling pass
+ * runs per column; qp_krylov_get returns the normalised q_{index}, qp_krylov_set stores a vector with factor 1.) */
 int32_t qp_krylov_get(qp_krylov_t K, int32_t index, qp_state_t dst);
 int32_t qp_krylov_set(qp_krylov_t K, int32_t index, qp_state_t src);
 
