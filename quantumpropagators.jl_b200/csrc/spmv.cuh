@@ -64,7 +64,7 @@ __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
 // in L1) is ordered after the wait.
 __device__ __forceinline__ double2 ld_x(const double2* p) {
   double2 r;
-  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));  // volatile: keeps its place after the (volatile) wait
   return r;
 }
 
@@ -110,7 +110,7 @@ __device__ __forceinline__ double2 vld(const double2* p, int hint) {
   return hint ? ld_hint(p, policy_evict_last()) : *p;
 }
 __device__ __forceinline__ double2 vldg(const double2* p, int hint) {
-  return hint ? ld_nc_hint(p, policy_evict_last()) : ld_x(p);
+  return hint ? ld_nc_hint(p, policy_evict_last()) : __ldg(p);
 }
 __device__ __forceinline__ void vst(double2* p, double2 v, int hint) {
   if (hint) st_hint(p, v, policy_evict_last());
@@ -120,7 +120,9 @@ __device__ __forceinline__ void vst(double2* p, double2 v, int hint) {
 // The epilogue is split in two so that kernels can request its operands (x_r, v_{k-1}[r],
 // acc[r]) at the START of a row block and consume them after the SpMV: their DRAM latency
 // is then hidden behind the matrix stream instead of being exposed once per block.
-template <int EPI>
+// PDL: the kernel is launched with programmatic dependent launch -- x must be read with a coherent load (ld_x);
+// everywhere else the read-only path is fine
+template <int EPI, int PDL = 0>
 __device__ __forceinline__ void epi_load(const EpiArgs& e, const double2* __restrict__ x, int64_t xidx,
                                          int64_t idx, double2& xr, double2& yv, double2& av) {
   xr = yv = av = make_double2(0.0, 0.0);
@@ -128,7 +130,7 @@ __device__ __forceinline__ void epi_load(const EpiArgs& e, const double2* __rest
     if (e.betac.x != 0.0 || e.betac.y != 0.0) yv = e.y[idx];  // beta == 0: y is not read (BLAS)
     return;
   }
-  xr = vldg(x + xidx, e.vec_hint);
+  xr = PDL ? ld_x(x + xidx) : vldg(x + xidx, e.vec_hint);
   if (EPI == EPI_CHEB_MID || EPI == EPI_CHEB_LAST) {
     yv = vld(e.y + idx, e.vec_hint);
     av = vld(e.acc + idx, e.vec_hint);
@@ -262,7 +264,7 @@ k_spmv_csr(MatView m, const double2* __restrict__ coef, int n_ops, const double2
   // epilogue operands requested before the gathers are consumed (one round trip less)
   double2 xr, yv, av;
   xr = yv = av = make_double2(0.0, 0.0);
-  if (active && lane == 0) epi_load<EPI>(e, x, row, row, xr, yv, av);
+  if (active && lane == 0) epi_load<EPI, 1>(e, x, row, row, xr, yv, av);
   if (active) {
     double2 pxv[4];
 #pragma unroll
