@@ -1404,6 +1404,14 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   if (gen->format == QP_FORMAT_DENSE) {
     if (batch != 1) return launch_dense_batched<EPI>(gen, coef_stride, x, batch, e);  // FP64 tensor cores
     EpiArgs e2 = e;
+    static const int gemv_cta = getenv("QPROP_GEMV_CTA") ? atoi(getenv("QPROP_GEMV_CTA")) : 1;
+    if (gemv_cta && n >= 2048) {  // CTA per row, grid-stride: few long contiguous streams (spmv.cuh)
+      const int64_t gblocks = std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
+      QP_CHECK(part_begin<EPI>(gen, e2, gblocks * 8));
+      k_gemv_dense_cta<EPI><<<(unsigned)gblocks, 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e2);
+      QP_LAUNCHED(ctx);
+      return part_end<EPI>(gen, e2, gblocks * 8);
+    }
     const int64_t gblocks = (n * 32 + 255) / 256;
     QP_CHECK(part_begin<EPI>(gen, e2, gblocks * 8));
     k_gemv_dense<EPI><<<(unsigned)gblocks, 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, gen->d_coef, x, e2);

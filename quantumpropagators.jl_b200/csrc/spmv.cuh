@@ -1041,6 +1041,66 @@ k_gemv_dense(const double2* const* __restrict__ ops, int n_ops, int64_t n,
   }
 }
 
+// The same for large n: a CTA of 8 warps takes one row at a time (grid-stride over the rows), its 256 lanes
+// stream the row in 4 KB steps and the partial sums meet in shared memory.  One warp per row (above) keeps
+// n concurrent row streams open -- 8192 on config 5, each advancing 512 B at a time -- and DRAM then runs at
+// half its rate; here the concurrent streams are the resident CTAs (~1000), each reading 4 KB contiguously.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_gemv_dense_cta(const double2* const* __restrict__ ops, int n_ops, int64_t n,
+                 const double2* __restrict__ coef, const double2* __restrict__ x, EpiArgs e) {
+  __shared__ double2 s_coef[QP_MAX_OPS];
+  __shared__ double s_part[8][2];
+  if (threadIdx.x < n_ops) s_coef[threadIdx.x] = coef[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double dr = 0, di = 0, nn = 0;
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+    double sr = 0.0, si = 0.0;
+    for (int l = 0; l < n_ops; ++l) {
+      const double2* __restrict__ a = ops[l] + row * n;
+      const double2 u = s_coef[l];
+      double pr = 0.0, pi = 0.0;
+#pragma unroll 4
+      for (int64_t j = threadIdx.x; j < n; j += 256) {
+        const double2 v = ld_stream(a + j);
+        const double2 xv = __ldg(x + j);
+        pr += v.x * xv.x - v.y * xv.y;
+        pi += v.x * xv.y + v.y * xv.x;
+      }
+      sr += u.x * pr - u.y * pi;
+      si += u.x * pi + u.y * pr;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      si += __shfl_xor_sync(0xffffffffu, si, o);
+    }
+    if (lane == 0) {
+      s_part[warp][0] = sr;
+      s_part[warp][1] = si;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tr = 0.0, ti = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // fixed order
+        tr += s_part[k][0];
+        ti += s_part[k][1];
+      }
+      epilogue<EPI>(e, x, row, row, make_double2(tr, ti), dr, di, nn);
+    }
+    __syncthreads();
+  }
+  if (epi_has_sums(EPI) && e.chk != nullptr && warp == 0) {  // only thread 0 holds sums
+    for (int o = 16; o > 0; o >>= 1) {
+      dr += __shfl_xor_sync(0xffffffffu, dr, o);
+      di += __shfl_xor_sync(0xffffffffu, di, o);
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
+  }
+}
+
 // two-pass tiled path for batched states (tile.cu); *handled = false: use the one-pass kernels
 // bit-flip (XOR-stencil) form (bitflip.cu): *ok = false if the generator does not have the structure
 int32_t qp_bitflip_build(qp_gen_t gen, bool* ok);

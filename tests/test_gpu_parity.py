@@ -1439,3 +1439,30 @@ def test_operator_mul_bitflip_term_counts(qp, ctx, N, masks):
         dy = qp.DeviceState(ctx, N).zero()
         gen.mul(dy, dx, [c], 1.0, 0.0)
         assert rel(dy.to_host(), (D + c * X) @ x) < 1e-13
+
+
+def test_dense_gemv_cta_per_row(qp, ctx):
+    """Dense generators on single states with N >= 2048 use the CTA-per-row GEMV (grid-stride over the rows,
+    partial sums through shared memory): mul!, fused expectation value (bit-reproducible) and one Chebyshev
+    step against NumPy / the oracle."""
+    rng = np.random.default_rng(2048)
+    n = 2048 + 64
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    Bm = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    gen = qp.DeviceGenerator(ctx, [A, Bm], 1)
+    assert gen.format == "dense"
+    x = rand_state(rng, n)
+    y0 = rand_state(rng, n)
+    dx = qp.DeviceState.from_host(ctx, x)
+    H = A + (0.3 - 0.2j) * Bm
+    for alpha, beta in [(1.0, 0.0), (0.5j, 1.0)]:
+        dy = qp.DeviceState.from_host(ctx, y0)
+        gen.mul(dy, dx, [0.3 - 0.2j], alpha, beta)
+        assert rel(dy.to_host(), alpha * (H @ x) + beta * y0) < 1e-13
+    vals = [gen.expval(dx, [0.3 - 0.2j]) for _ in range(3)]
+    assert abs(vals[0] - np.vdot(x, H @ x)) < 1e-11 and vals[0] == vals[1] == vals[2]
+    Hh = (A + A.conj().T) / 2
+    tlist = np.array([0.0, 0.05])
+    out = qp.propagate(x, (Hh,), tlist, "cheby", ctx=ctx)
+    ref = O.propagate(x, (Hh,), tlist, "cheby")
+    assert rel(out, ref) < RTOL
