@@ -1466,3 +1466,17 @@ def test_dense_gemv_cta_per_row(qp, ctx):
     out = qp.propagate(x, (Hh,), tlist, "cheby", ctx=ctx)
     ref = O.propagate(x, (Hh,), tlist, "cheby")
     assert rel(out, ref) < RTOL
+
+
+def test_bitflip_device_coefficient_path(qp, ctx):
+    """Launches whose coefficients only exist on the device take the products from shared memory (CK = 0): the
+    same bit-flip tests in a child process with that path forced (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, QPROP_BITFLIP_DEVICE_COEFS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_operator_mul_bitflip or test_cheby_tfim_vs_oracle_and_expm or test_newton_liouvillian_bitflip"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
