@@ -1404,6 +1404,20 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
   if (gen->format == QP_FORMAT_DENSE) {
     if (batch != 1) return launch_dense_batched<EPI>(gen, coef_stride, x, batch, e);  // FP64 tensor cores
     EpiArgs e2 = e;
+    static const int gemv_flat = getenv("QPROP_GEMV_FLAT") ? atoi(getenv("QPROP_GEMV_FLAT")) : 1;
+    if (gemv_flat && n >= 2048 && n % 128 == 0) {  // the matrix as one contiguous stream + a row-sum pass (spmv.cuh)
+      const int64_t ppr = n >> 7;
+      QP_CHECK(qp_ctx_reserve_red(ctx, (size_t)2 * (size_t)gen->n_ops * (size_t)n * (size_t)ppr));
+      double2* part = reinterpret_cast<double2*>(ctx->d_red);
+      const int64_t fblocks = (int64_t)ctx->sm_count * 8;
+      k_gemv_flat<0><<<(unsigned)fblocks, 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, x, part);
+      QP_LAUNCHED(ctx);
+      const int64_t rblocks = (n + 255) / 256;
+      QP_CHECK(part_begin<EPI>(gen, e2, rblocks * 8));
+      k_gemv_flat_fin<EPI><<<(unsigned)rblocks, 256, 0, st>>>(part, gen->n_ops, n, gen->d_coef, x, e2);
+      QP_LAUNCHED(ctx);
+      return part_end<EPI>(gen, e2, rblocks * 8);
+    }
     static const int gemv_cta = getenv("QPROP_GEMV_CTA") ? atoi(getenv("QPROP_GEMV_CTA")) : 1;
     if (gemv_cta && n >= 2048) {  // CTA per row, grid-stride: few long contiguous streams (spmv.cuh)
       const int64_t gblocks = std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);

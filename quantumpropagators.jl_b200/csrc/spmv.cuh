@@ -1101,6 +1101,79 @@ k_gemv_dense_cta(const double2* const* __restrict__ ops, int n_ops, int64_t n,
   }
 }
 
+// Flat two-pass GEMV for large dense operators (n a multiple of 128): the matrix is read as ONE contiguous stream
+// -- warp w of the grid takes the 2 KB pieces w, w + W, w + 2W, ... of the row-major array, so that at any moment
+// the grid reads one contiguous window (like the Krylov streaming kernels, which reach 6.2-6.3 TB/s), instead of
+// thousands of row streams 128 KB apart (0.64-0.67 of the roofline: DRAM page conflicts) -- and writes one partial
+// dot product per piece; the second kernel adds the n / 128 partials of a row in a fixed order and applies the
+// fused epilogue.  part[(l * n + row) * ppr + k].
+template <int UNUSED>  // a template only because this header is included by several translation units
+__global__ void __launch_bounds__(256)
+k_gemv_flat(const double2* const* __restrict__ ops, int n_ops, int64_t n, const double2* __restrict__ x,
+            double2* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ppr = n >> 7;  // pieces of 128 elements per row
+  const int64_t total = (int64_t)n_ops * n * ppr;
+  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total; p += warps) {
+    const int64_t lr = p / ppr, k = p - lr * ppr;  // (operator, row) and piece within the row
+    const int l = (int)(lr / n);
+    const int64_t row = lr - (int64_t)l * n;
+    const double2* __restrict__ a = ops[l] + row * n + (k << 7) + lane;
+    const double2* __restrict__ xs = x + (k << 7) + lane;
+    double2 v[4], xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = ld_stream(a + 32 * q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] = __ldg(xs + 32 * q);
+    double pr = 0.0, pi = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pr += v[q].x * xv[q].x - v[q].y * xv[q].y;
+      pi += v[q].x * xv[q].y + v[q].y * xv[q].x;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      pr += __shfl_xor_sync(0xffffffffu, pr, o);
+      pi += __shfl_xor_sync(0xffffffffu, pi, o);
+    }
+    if (lane == 0) part[p] = make_double2(pr, pi);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_gemv_flat_fin(const double2* __restrict__ part, int n_ops, int64_t n, const double2* __restrict__ coef,
+                const double2* __restrict__ x, EpiArgs e) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ppr = n >> 7;
+  double dr = 0, di = 0, nn = 0;
+  if (row < n) {
+    double sr = 0.0, si = 0.0;
+    for (int l = 0; l < n_ops; ++l) {
+      const double2* __restrict__ pp = part + ((int64_t)l * n + row) * ppr;
+      double pr = 0.0, pi = 0.0;
+      for (int64_t k = 0; k < ppr; ++k) {
+        const double2 t = pp[k];
+        pr += t.x;
+        pi += t.y;
+      }
+      const double2 u = coef[l];
+      sr += u.x * pr - u.y * pi;
+      si += u.x * pi + u.y * pr;
+    }
+    epilogue<EPI>(e, x, row, row, make_double2(sr, si), dr, di, nn);
+  }
+  if (epi_has_sums(EPI) && e.chk != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) {
+      dr += __shfl_xor_sync(0xffffffffu, dr, o);
+      di += __shfl_xor_sync(0xffffffffu, di, o);
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) chk_flush_warp(e, dr, di, nn);
+  }
+}
+
 // two-pass tiled path for batched states (tile.cu); *handled = false: use the one-pass kernels
 // bit-flip (XOR-stencil) form (bitflip.cu): *ok = false if the generator does not have the structure
 int32_t qp_bitflip_build(qp_gen_t gen, bool* ok);

@@ -1446,7 +1446,7 @@ def test_dense_gemv_cta_per_row(qp, ctx):
     partial sums through shared memory): mul!, fused expectation value (bit-reproducible) and one Chebyshev
     step against NumPy / the oracle."""
     rng = np.random.default_rng(2048)
-    n = 2048 + 64
+    n = 2048 + 128   # a multiple of 128: the flat two-pass GEMV; QPROP_GEMV_FLAT=0: CTA per row
     A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
     Bm = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
     gen = qp.DeviceGenerator(ctx, [A, Bm], 1)
