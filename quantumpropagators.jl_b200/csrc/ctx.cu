@@ -101,6 +101,7 @@ extern "C" int32_t qp_ctx_destroy(qp_ctx_t ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_red) cudaFree(ctx->d_red);
   if (ctx->d_part) cudaFree(ctx->d_part);
+  if (ctx->d_gemv) cudaFree(ctx->d_gemv);
   if (ctx->h_red) cudaFreeHost(ctx->h_red);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -164,6 +165,17 @@ int32_t qp_ctx_reserve_part(qp_ctx_t ctx, size_t doubles) {
   ctx->part_doubles = 0;
   QP_CUDA(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * doubles));
   ctx->part_doubles = doubles;
+  return QP_OK;
+}
+
+int32_t qp_ctx_reserve_gemv(qp_ctx_t ctx, size_t doubles) {
+  if (ctx->gemv_doubles >= doubles) return QP_OK;
+  QP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_gemv);
+  ctx->d_gemv = nullptr;
+  ctx->gemv_doubles = 0;
+  QP_CUDA(ctx, cudaMalloc(&ctx->d_gemv, sizeof(double) * doubles));
+  ctx->gemv_doubles = doubles;
   return QP_OK;
 }
 

@@ -50,6 +50,8 @@ struct qp_ctx_s {
   // per-warp / per-tile partial sums of the fused expectation value and the normalization check
   double* d_part = nullptr;
   size_t part_doubles = 0;
+  double* d_gemv = nullptr;  // partial dot products of the flat dense GEMV (spmv.cuh: k_gemv_flat)
+  size_t gemv_doubles = 0;
   // small pinned staging area for per-step coefficient uploads
   qp_c128* h_stage = nullptr;
   size_t stage_elems = 0;
@@ -283,6 +285,7 @@ int32_t qp_fail(qp_ctx_t ctx, int32_t code, const char* fmt, ...);
 
 int32_t qp_ctx_bind(qp_ctx_t ctx);  // cudaSetDevice
 int32_t qp_ctx_reserve_red(qp_ctx_t ctx, size_t doubles);
+int32_t qp_ctx_reserve_gemv(qp_ctx_t ctx, size_t doubles);
 int32_t qp_ctx_reserve_stage(qp_ctx_t ctx, size_t elems);
 int32_t qp_ctx_reserve_part(qp_ctx_t ctx, size_t doubles);
 // chk[b][k] = sum over the n_slots slots of part[slot][b][k] in a fixed order (deterministic)

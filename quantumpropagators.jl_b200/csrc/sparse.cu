@@ -1407,8 +1407,8 @@ static int32_t launch_epi(qp_gen_t gen, int coef_stride, const double2* x, int64
     static const int gemv_flat = getenv("QPROP_GEMV_FLAT") ? atoi(getenv("QPROP_GEMV_FLAT")) : 1;
     if (gemv_flat && n >= 2048 && n % 128 == 0) {  // the matrix as one contiguous stream + a row-sum pass (spmv.cuh)
       const int64_t ppr = n >> 7;
-      QP_CHECK(qp_ctx_reserve_red(ctx, (size_t)2 * (size_t)gen->n_ops * (size_t)n * (size_t)ppr));
-      double2* part = reinterpret_cast<double2*>(ctx->d_red);
+      QP_CHECK(qp_ctx_reserve_gemv(ctx, (size_t)2 * (size_t)gen->n_ops * (size_t)n * (size_t)ppr));
+      double2* part = reinterpret_cast<double2*>(ctx->d_gemv);
       const int64_t fblocks = (int64_t)ctx->sm_count * 8;
       k_gemv_flat<0><<<(unsigned)fblocks, 256, 0, st>>>(gen->d_dense_ops, gen->n_ops, n, x, part);
       QP_LAUNCHED(ctx);

@@ -1449,12 +1449,14 @@ def test_dense_gemv_cta_per_row(qp, ctx):
     n = 2048 + 128   # a multiple of 128: the flat two-pass GEMV; QPROP_GEMV_FLAT=0: CTA per row
     A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
     Bm = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    ctx = qp.Context(0)   # a fresh context: the first call below has to grow every scratch buffer
     gen = qp.DeviceGenerator(ctx, [A, Bm], 1)
     assert gen.format == "dense"
     x = rand_state(rng, n)
     y0 = rand_state(rng, n)
     dx = qp.DeviceState.from_host(ctx, x)
     H = A + (0.3 - 0.2j) * Bm
+    assert abs(gen.expval(dx, [0.3 - 0.2j]) - np.vdot(x, H @ x)) < 1e-11
     for alpha, beta in [(1.0, 0.0), (0.5j, 1.0)]:
         dy = qp.DeviceState.from_host(ctx, y0)
         gen.mul(dy, dx, [0.3 - 0.2j], alpha, beta)
