@@ -543,7 +543,12 @@ int32_t qp_bitflip_build(qp_gen_t g, bool* ok) {
   d_set = nullptr;
   if (terms.empty()) return fail(QP_OK);  // purely diagonal generators gain nothing here
   // deterministic order (the hash set's is not): by operator, then by mask
-  std::sort(terms.begin(), terms.end(), [](const Term& a, const Term& b) { return a.op != b.op ? a.op < b.op : a.mask < b.mask; });
+  std::sort(terms.begin(), terms.end(), [](const Term& a, const Term& b) {
+    if (a.op != b.op) return a.op < b.op;
+    if (a.mask != b.mask) return a.mask < b.mask;
+    if (a.cmask != b.cmask) return a.cmask < b.cmask;
+    return a.cval < b.cval;
+  });
   B->h_val.assign(BF_MAX_TERMS + BF_MAX_LOW, make_double2(0.0, 0.0));
   B->h_op.assign(BF_MAX_TERMS + BF_MAX_LOW, 0);
   const int max_low = getenv("QPROP_BITFLIP_SHUFFLES") ? std::min(BF_MAX_LOW, atoi(getenv("QPROP_BITFLIP_SHUFFLES"))) : BF_MAX_LOW;
