@@ -292,6 +292,12 @@ static bool bf_terms_from_set(const MaskSet& S, int64_t n, std::vector<BfTerm>& 
     T.op = 0;
     out.push_back(T);
   }
+  // the slot order of the hash set depends on the race of the insertions: sort
+  std::sort(out.begin(), out.end(), [](const BfTerm& a, const BfTerm& b) {
+    if (a.mask != b.mask) return a.mask < b.mask;
+    if (a.cmask != b.cmask) return a.cmask < b.cmask;
+    return a.cval < b.cval;
+  });
   return true;
 }
 
