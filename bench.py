@@ -573,6 +573,9 @@ def main():
                 "workload": workload_name(args.n_spins, n_c),
                 "parallelism": f"trajectory-sharded x{world} (independent replicas, no data-path collective)",
                 "matrix_format": fmt,
+                "matrix_format_note": ("chosen by QP_FORMAT_AUTO from the uploaded sparse matrices (diagonal operators + uniform bit flips, "
+                                       "csrc/bitflip.cu); a generator of the same size and sparsity without that structure runs on the "
+                                       "kernel of `arms.selld`" if fmt == "bitflip" else "chosen by QP_FORMAT_AUTO / --format"),
                 "l2": (f"working set per term {ws_mb:.0f} MB (matrix as stored {g.stored_bytes / 1e6:.1f} MB + {80 * N / 1e6:.1f} MB of vectors) "
                        + (f"> L2 ({L2_MB:.0f} MB): streamed from HBM every term" if ws_mb > 1.5 * L2_MB else
                           f"is NOT larger than L2 ({L2_MB:.0f} MB) and nothing is flushed between terms (a prop_step! is {n_terms} "
