@@ -352,3 +352,13 @@ def test_no_vector_load_is_scheduled_above_the_pdl_wait():
             bad = [l for l in loads if re.search(r"LDG\.E(\.NA)?\.128 ", l)]
             assert not bad, f"{fn}: plain 128-bit load above griddepcontrol.wait: {bad[0]}"
     assert total >= 100   # the CSR, SELL-D, bit-flip and Krylov kernels all use the attribute
+
+
+def test_format_constants_match_the_header():
+    """The storage-format codes of the ctypes mirror are the header's."""
+    text = open(os.path.join(ROOT, "include", "qprop.h")).read()
+    header = {name: int(val) for name, val in re.findall(r"#define\s+(QP_FORMAT_[A-Z]+)\s+(\d+)", text)}
+    assert len(header) >= 7
+    for name, val in header.items():
+        assert getattr(_lib, name) == val, name
+        assert val in _lib.FORMAT_NAMES
