@@ -761,11 +761,12 @@ k_spmv_bitflip(const __grid_constant__ BitflipView v, const double2* __restrict_
   // every warp of the grid runs the same number of rounds (a uniform trip count keeps the shuffles free of
   // re-convergence code); slices past the end (last CTA only) are computed on slice 0 and not stored -- predicating
   // their loads instead costs 13 % (the batches of gathers are broken up by branches)
-  int64_t s = (int64_t)blockIdx.x * rounds * nwarps + warp;
-  for (int it = 0; it < rounds; ++it, s += nwarps) {
-    const bool active = s < n_slices;
-    const int64_t row = (active ? s : 0) * 32 + lane;
-    const uint32_t r32 = (uint32_t)row;
+  // 32-bit slice / row arithmetic (n < 2^32 is a condition of the format): two registers less than with 64-bit indices
+  uint32_t s = blockIdx.x * (uint32_t)(rounds * nwarps) + (uint32_t)warp;
+  for (int it = 0; it < rounds; ++it, s += (uint32_t)nwarps) {
+    const bool active = s < (uint32_t)n_slices;
+    const uint32_t r32 = (active ? s : 0u) * 32u + (uint32_t)lane;
+    const int64_t row = (int64_t)r32;
     const double2 xown = ld_x(x + row);
     unsigned short code = 0;
     if (v.dcode != nullptr) code = __ldg(v.dcode + row);
